@@ -1,0 +1,235 @@
+/*
+ * alazgpu.h — C ABI of libalazgpu: the B200-native replacement for the
+ * service-map aggregation hot path of getanteon/alaz (reference @ 828b997f).
+ *
+ * The reference has no FFI boundary for this path; the seam this library sits
+ * behind is the aggregator's channel-in / DataStore-out pair:
+ *   in : *l7_req.L7Event              ebpf/l7_req/l7.go:396-421 (from bpfL7Event, l7.go:345-369)
+ *        *tcp_state.TcpConnectEvent   ebpf/tcp_state/tcp.go:75-84 (from BpfTcpEvent, tcp.go:63-72)
+ *        k8s.K8sResourceMessage       k8s/informer.go:236-240 -> processPod/processSvc
+ *                                     aggregator/persist.go:55-71, 114-130
+ *   out: datastore.DataStore.PersistRequest  datastore/datastore.go:13
+ *                                     (one row per request; this library instead
+ *                                     returns the rows grouped by (From,To))
+ *
+ * Rules: plain C, flat PODs, no pointer is retained past the call that
+ * received it (cgo rule), every entry point returns 0 on success or a negative
+ * alz_status. No exceptions cross the boundary. One handle drives one GPU.
+ * INTEGRATION.md shows the cgo binding a maintainer would add.
+ */
+#ifndef ALAZGPU_H
+#define ALAZGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ALZ_ABI_VERSION 1
+
+/* ---- status codes -------------------------------------------------------- */
+typedef enum alz_status {
+  ALZ_OK = 0,
+  ALZ_E_INVAL = -1,      /* bad argument */
+  ALZ_E_NOMEM = -2,      /* host or device allocation failed */
+  ALZ_E_CUDA = -3,       /* CUDA runtime error (alz_last_cuda_error) */
+  ALZ_E_NODEVICE = -4,   /* no CUDA device: there is NO CPU fallback */
+  ALZ_E_CAPACITY = -5,   /* pair/edge dictionary or output buffer too small */
+  ALZ_E_STATE = -6,      /* call not valid in this state (e.g. no comm) */
+  ALZ_E_NCCL = -7,       /* NCCL error or libnccl.so.2 not loadable */
+  ALZ_E_UNSUPPORTED = -8
+} alz_status;
+
+/* ---- wire enums: values equal the eBPF side (ebpf/l7_req/l7.go:19-29) ----- */
+enum {
+  ALZ_PROTO_UNKNOWN = 0, ALZ_PROTO_HTTP = 1, ALZ_PROTO_AMQP = 2,
+  ALZ_PROTO_POSTGRES = 3, ALZ_PROTO_HTTP2 = 4, ALZ_PROTO_REDIS = 5,
+  ALZ_PROTO_KAFKA = 6, ALZ_PROTO_MYSQL = 7, ALZ_PROTO_MONGO = 8
+};
+/* method enums that change routing (l7.go:91-95, 120-125) */
+enum { ALZ_AMQP_PUBLISH = 1, ALZ_AMQP_DELIVER = 2 };
+enum { ALZ_REDIS_COMMAND = 1, ALZ_REDIS_PUSHED_EVENT = 2, ALZ_REDIS_PING = 3 };
+
+/* method_flags byte of alz_l7_rec */
+#define ALZ_MF_METHOD_MASK 0x3Fu
+#define ALZ_MF_PAYLOAD_REJECT 0x40u /* host-side payload parser says the reference
+                                       would drop the row: Postgres/MySQL text query
+                                       without SQL keyword (aggregator/data.go:1440-1443,
+                                       1495-1497), Mongo parse failure (:1252-1255) */
+#define ALZ_MF_TLS 0x80u
+
+/* node kinds of an edge end (aggregator/data.go POD/SVC/OUTBOUND) */
+enum { ALZ_NODE_POD = 0, ALZ_NODE_SVC = 1, ALZ_NODE_OUTBOUND = 2 };
+/* tables of the join's build side (aggregator/cluster.go:15-16) */
+enum { ALZ_TABLE_POD = 0, ALZ_TABLE_SVC = 1 };
+
+#define ALZ_NB 64 /* latency histogram buckets, see docs/SPEC.md §4 */
+
+/* ---- records -------------------------------------------------------------- */
+
+/* Compact L7 record, 32 B. Lossless w.r.t. struct l7_event (ebpf/c/l7.c:19-47)
+ * for everything resolve/emit/reduce reads; pid/fd/payload stay host-side.
+ * saddr/daddr are host-order u32 with the first octet in the MSB, exactly the
+ * integer the reference feeds to IntToIPv4 (aggregator/data.go:1751-1767). */
+typedef struct alz_l7_rec {
+  uint32_t saddr;
+  uint32_t daddr;
+  uint16_t sport;
+  uint16_t dport;
+  uint16_t status;       /* l7_event.status saturated to 65535 */
+  uint8_t protocol;      /* ALZ_PROTO_* */
+  uint8_t method_flags;  /* method | ALZ_MF_* */
+  uint64_t duration_ns;  /* l7_event.duration (l7.c:788) */
+  uint64_t write_time_ns;
+} alz_l7_rec;
+
+/* tcp_state record, 40 B, from struct tcp_event (ebpf/c/struct.h:2-12).
+ * type: 1=ESTABLISHED 5=CLOSED (ebpf/tcp_state/tcp.go:19-25); addresses as in
+ * alz_l7_rec (first octet in MSB). */
+typedef struct alz_tcp_rec {
+  uint64_t fd;
+  uint64_t timestamp_ns;
+  uint32_t pid;
+  uint32_t saddr;
+  uint32_t daddr;
+  uint16_t sport;
+  uint16_t dport;
+  uint32_t type;
+  uint32_t _pad;
+} alz_tcp_rec;
+
+/* query / result of the temporal socket join (SocketLine.GetValue,
+ * aggregator/sock_num_line.go:82-158) */
+typedef struct alz_sock_query {
+  uint64_t fd;
+  uint64_t timestamp_ns;
+  uint32_t pid;
+  uint32_t _pad;
+} alz_sock_query;
+
+typedef struct alz_sock_result {
+  uint32_t found; /* 1 = SockInfo returned, 0 = the reference returns an error */
+  uint32_t saddr;
+  uint32_t daddr;
+  uint16_t sport;
+  uint16_t dport;
+} alz_sock_result;
+
+/* One edge of the service graph for one window. Rows the reference would have
+ * handed to PersistRequest (datastore/backend.go:819-847), grouped by
+ * (FromType,FromUID,ToType,ToUID). from/to are the caller's dense ids for pod
+ * and service ends and the raw IPv4 for outbound ends (aggregator/data.go:862). */
+typedef struct alz_edge_out {
+  uint8_t from_type; /* ALZ_NODE_* */
+  uint8_t to_type;
+  uint8_t _pad[6];
+  uint32_t from;
+  uint32_t to;
+  uint64_t count;
+  uint64_t err5xx;
+  uint64_t lat_sum_ns;
+  uint32_t hist[ALZ_NB];
+} alz_edge_out;
+
+typedef struct alz_config {
+  uint32_t abi_version;     /* ALZ_ABI_VERSION */
+  int32_t device;           /* CUDA device ordinal */
+  uint32_t max_endpoints;   /* pods + services the tables must hold */
+  uint32_t max_pairs;       /* distinct (saddr,daddr) pairs per window */
+  uint32_t max_edges;       /* distinct edges per window */
+  uint32_t max_batch;       /* largest n of one alz_submit_l7 (host staging) */
+  uint32_t flags;           /* ALZ_CFG_* */
+  uint32_t _reserved[9];
+} alz_config;
+
+#define ALZ_CFG_EAGER_JOIN 0x1u /* resolve every event through the tables before
+                                   reducing (the textbook plan) instead of
+                                   reducing per socket pair and joining the
+                                   distinct pairs (default); same results */
+
+typedef struct alz_stats {
+  uint64_t events_in;        /* records submitted */
+  uint64_t rows_emitted;     /* rows the reference would have persisted */
+  uint64_t not_request;      /* protocol switch emits no request row
+                                (HTTP2/KAFKA/UNKNOWN, payload reject) */
+  uint64_t src_unresolved;   /* setFromToV2 error: saddr is not a pod
+                                (aggregator/data.go:829-832) */
+  uint64_t pairs_live;
+  uint64_t edges_live;
+  uint64_t tcp_events_in;
+  uint64_t tcp_localhost_dropped; /* aggregator/data.go:409, 455 */
+  uint64_t _reserved[8];
+} alz_stats;
+
+typedef struct alz_handle alz_handle;
+
+/* ---- lifecycle -------------------------------------------------------------- */
+int alz_create(const alz_config* cfg, alz_handle** out);
+int alz_destroy(alz_handle* h);
+const char* alz_strerror(int status);
+const char* alz_last_cuda_error(alz_handle* h);
+/* Run all device work of this handle on `cuda_stream` (a cudaStream_t; 0 =
+ * the library's own stream). Lets a host time the work with its own events. */
+int alz_set_stream(alz_handle* h, void* cuda_stream);
+int alz_sync(alz_handle* h);
+
+/* ---- join build side: replaces ClusterInfo map writes ------------------------
+ * (aggregator/persist.go:55-71 PodIPToPodUid, :114-130 ServiceIPToServiceUid).
+ * UID strings stay with the caller, who interns them to dense ids < 2^29.
+ * Single writer. Changes become visible to submits after alz_table_commit,
+ * which first folds everything already submitted through the old tables, so
+ * each event is resolved by the tables in force when it was submitted. */
+int alz_table_upsert(alz_handle* h, int table, uint32_t ipv4, uint32_t id);
+int alz_table_erase(alz_handle* h, int table, uint32_t ipv4);
+int alz_table_commit(alz_handle* h);
+
+/* ---- event ingest: replaces processL7 .. PersistRequest --------------------
+ * (aggregator/data.go:1364-1383 dispatch, :1081-1362 row build,
+ *  :827-870 setFromToV2). */
+int alz_submit_l7(alz_handle* h, const alz_l7_rec* host_recs, size_t n);
+/* same, records already resident in this GPU's HBM */
+int alz_submit_l7_device(alz_handle* h, const alz_l7_rec* dev_recs, size_t n);
+/* n raw perf samples exactly as perf.Reader yields them: 1096-B
+ * struct l7_event (ebpf/l7_req/l7.go:345-369, :704); payload ignored. */
+int alz_submit_l7_raw(alz_handle* h, const void* host_bpf_l7_events, size_t n);
+#define ALZ_BPF_L7_EVENT_SIZE 1096
+
+/* ---- window result: the grouped rows ----------------------------------------
+ * Folds pending pairs, (multi-GPU: merges all ranks, one all-reduce on the
+ * accumulators), writes the live edges sorted by (from_type,from,to_type,to)
+ * and resets the window. n_out is always set to the number of live edges; if
+ * cap is too small returns ALZ_E_CAPACITY and keeps the window. */
+int alz_window_flush(alz_handle* h, alz_edge_out* out, size_t cap, size_t* n_out);
+/* as above but leaves the result on the device for alz_gnn_score / peers;
+ * *dev_edges stays valid until the next flush on this handle */
+int alz_window_flush_device(alz_handle* h, const alz_edge_out** dev_edges, size_t* n_out);
+int alz_get_stats(alz_handle* h, alz_stats* out);
+
+/* ---- GNN anomaly pass over the last flushed window (docs/SPEC.md §6) -------- */
+int alz_gnn_score(alz_handle* h, float* edge_scores, size_t cap, size_t* n_out);
+/* quantiles from the histogram, the same float64 interpolation the scores use */
+int alz_edge_quantiles(const alz_edge_out* e, const double* qs, size_t nq, double* out_ns);
+
+/* ---- tcp_state sink + temporal socket join -------------------
+ * alz_submit_tcp replaces processTcpConnect (aggregator/data.go:404-506) +
+ * SocketLine.AddValue (sock_num_line.go:62-80); alz_sock_lookup replaces
+ * SocketLine.GetValue (sock_num_line.go:82-158). */
+int alz_submit_tcp(alz_handle* h, const alz_tcp_rec* host_recs, size_t n);
+int alz_sock_lookup(alz_handle* h, const alz_sock_query* host_q, size_t n,
+                    alz_sock_result* host_out);
+
+/* ---- multi-GPU: one rank per GPU, events pre-partitioned by alz_owner_rank ---- */
+#define ALZ_COMM_ID_BYTES 128
+int alz_comm_unique_id(void* out_id /* ALZ_COMM_ID_BYTES */);
+int alz_comm_init(alz_handle* h, int nranks, int rank, const void* id);
+/* rank that owns an event: hash of the source address only, so every event of
+ * an edge lands on one rank before any resolve (From is the pod at saddr,
+ * aggregator/data.go:834-835) */
+uint32_t alz_owner_rank(uint32_t saddr, uint32_t nranks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALAZGPU_H */

@@ -1,0 +1,185 @@
+"""ctypes wrapper over oracle/_build/liboracle.so (CPU oracle + host synth).
+
+Test infrastructure: imported by tests/, bench.py (cpu_baseline / --impl
+reference) and __graft_entry__.smoke() only. The product never imports this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from alaz_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+
+
+def build(force=False):
+    src = [os.path.join(ROOT, "oracle", "alz_oracle.c"),
+           os.path.join(ROOT, "oracle", "alz_oracle.h"),
+           os.path.join(ROOT, "alaz_b200", "synth", "alz_synth_topo.c"),
+           os.path.join(ROOT, "alaz_b200", "synth", "alz_synth.h"),
+           os.path.join(ROOT, "include", "alazgpu.h")]
+    if not force and os.path.exists(LIB_PATH):
+        t = os.path.getmtime(LIB_PATH)
+        if all(os.path.getmtime(s) <= t for s in src):
+            return LIB_PATH
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")],
+                          stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB_PATH)
+        vp, u32, u64, sz = C.c_void_p, C.c_uint32, C.c_uint64, C.c_size_t
+        L.orc_create.restype = vp
+        L.orc_destroy.argtypes = [vp]
+        L.orc_table_upsert.argtypes = [vp, C.c_int, u32, u32]
+        L.orc_table_erase.argtypes = [vp, C.c_int, u32]
+        L.orc_process_l7.argtypes = [vp, vp, sz, C.c_int]
+        L.orc_edges.argtypes = [vp, vp, sz]
+        L.orc_edges.restype = sz
+        L.orc_window_reset.argtypes = [vp]
+        L.orc_stats.argtypes = [vp, C.POINTER(abi.Stats)]
+        L.orc_bucket.argtypes = [u64]
+        L.orc_bucket.restype = u32
+        L.orc_quantile.argtypes = [vp, C.c_double]
+        L.orc_quantile.restype = C.c_double
+        L.orc_compact_raw.argtypes = [vp, sz, vp]
+        L.orc_sockline_create.restype = vp
+        L.orc_sockline_destroy.argtypes = [vp]
+        L.orc_sockline_add.argtypes = [vp, u64, vp]
+        L.orc_sockline_get.argtypes = [vp, u64, vp]
+        L.orc_sockline_get.restype = C.c_int
+        L.orc_sockline_len.argtypes = [vp]
+        L.orc_sockline_len.restype = sz
+        L.orc_sockmaps_create.restype = vp
+        L.orc_sockmaps_destroy.argtypes = [vp]
+        L.orc_sockmaps_process_tcp.argtypes = [vp, vp, sz, C.POINTER(u64)]
+        L.orc_sockmaps_lookup.argtypes = [vp, vp, sz, vp]
+        L.alz_synth_topo_create.argtypes = [u32, u64, u32]
+        L.alz_synth_topo_create.restype = C.POINTER(abi.SynthTopo)
+        L.alz_synth_topo_destroy.argtypes = [C.POINTER(abi.SynthTopo)]
+        L.alz_synth_fill.argtypes = [C.POINTER(abi.SynthTopo), u64, u64, vp]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    """The reference aggregator's resolve/emit path, restated (oracle/alz_oracle.c)."""
+
+    def __init__(self):
+        self.L = lib()
+        self.h = self.L.orc_create()
+
+    def close(self):
+        if self.h:
+            self.L.orc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def upsert(self, table, ip, id_):
+        self.L.orc_table_upsert(self.h, table, int(ip), int(id_))
+
+    def erase(self, table, ip):
+        self.L.orc_table_erase(self.h, table, int(ip))
+
+    def load_tables(self, pod_ip, svc_ip):
+        for k, v in enumerate(pod_ip):
+            self.upsert(abi.TABLE_POD, int(v), k)
+        for k, v in enumerate(svc_ip):
+            self.upsert(abi.TABLE_SVC, int(v), k)
+
+    def process(self, recs, nthreads=1):
+        recs = np.ascontiguousarray(recs, dtype=abi.L7_REC)
+        self.L.orc_process_l7(self.h, _ptr(recs), len(recs), nthreads)
+
+    def edges(self):
+        n = self.L.orc_edges(self.h, None, 0)
+        out = np.zeros(n, dtype=abi.EDGE_OUT)
+        if n:
+            self.L.orc_edges(self.h, _ptr(out), n)
+        return out
+
+    def reset_window(self):
+        self.L.orc_window_reset(self.h)
+
+    def stats(self):
+        st = abi.Stats()
+        self.L.orc_stats(self.h, C.byref(st))
+        return st.as_dict()
+
+
+def bucket(d):
+    return int(lib().orc_bucket(int(d)))
+
+
+def quantile(hist, q):
+    h = np.ascontiguousarray(hist, dtype=np.uint32)
+    return float(lib().orc_quantile(_ptr(h), float(q)))
+
+
+def compact_raw(raw):
+    raw = np.ascontiguousarray(raw, dtype=np.uint8)
+    n = raw.size // abi.BPF_L7_EVENT_SIZE
+    out = np.zeros(n, dtype=abi.L7_REC)
+    lib().orc_compact_raw(_ptr(raw), n, _ptr(out))
+    return out
+
+
+class Topo:
+    """Synthetic cluster + stream tables (alaz_b200/synth/alz_synth_topo.c), host side."""
+
+    def __init__(self, n_services, seed=0xA1A20000, mix=abi.MIX_SURVEY):
+        self.L = lib()
+        self.p = self.L.alz_synth_topo_create(n_services, seed, mix)
+        if not self.p:
+            raise MemoryError("alz_synth_topo_create failed")
+        t = self.p.contents
+        self.n_services, self.n_pods = t.n_services, t.n_pods
+        self.n_edges, self.n_outbound = t.n_edges, t.n_outbound
+        self.pod_ip = np.ctypeslib.as_array(t.pod_ip, (t.n_pods,)).copy()
+        self.svc_ip = np.ctypeslib.as_array(t.svc_ip, (t.n_services,)).copy()
+        self.out_ip = np.ctypeslib.as_array(t.out_ip, (t.n_outbound,)).copy()
+
+    def arrays(self):
+        """Copies of the sampling tables (for upload to the device generator)."""
+        t = self.p.contents
+        E = t.n_edges
+        return dict(
+            edge_saddr=np.ctypeslib.as_array(t.edge_saddr, (E,)).copy(),
+            edge_daddr=np.ctypeslib.as_array(t.edge_daddr, (E,)).copy(),
+            edge_flags=np.ctypeslib.as_array(t.edge_flags, (E,)).copy(),
+            alias_thresh=np.ctypeslib.as_array(t.alias_thresh, (E,)).copy(),
+            alias_idx=np.ctypeslib.as_array(t.alias_idx, (E,)).copy(),
+            lat_q=np.ctypeslib.as_array(t.lat_q, (4097,)).copy(),
+        )
+
+    def view(self):
+        return self.p.contents.view
+
+    def events(self, first, n):
+        out = np.zeros(n, dtype=abi.L7_REC)
+        self.L.alz_synth_fill(self.p, int(first), int(n), _ptr(out))
+        return out
+
+    def close(self):
+        if self.p:
+            self.L.alz_synth_topo_destroy(self.p)
+            self.p = None
+
+    def __del__(self):
+        self.close()

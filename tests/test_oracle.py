@@ -1,0 +1,238 @@
+"""CPU tests of the oracle itself: the oracle is only trusted after it passes
+the hand-derived branch vectors, agrees with the independent Python
+restatement, and reproduces the reference's own SocketLine KATs."""
+import ctypes as C
+import sys, os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from alaz_b200 import abi
+from helpers import load_branches, edges_equal, explain_diff, pyref_edges
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+import ref_py  # noqa: E402
+
+
+def _c_oracle(pods, svcs):
+    o = ol.Oracle()
+    for ip, i in pods.items():
+        o.upsert(abi.TABLE_POD, ip, i)
+    for ip, i in svcs.items():
+        o.upsert(abi.TABLE_SVC, ip, i)
+    return o
+
+
+def _py_oracle(pods, svcs):
+    a = ref_py.Aggregator()
+    for ip, i in pods.items():
+        a.pod_ip_to_uid[ref_py.ip_string(ip)] = "pod-%d" % i
+    for ip, i in svcs.items():
+        a.svc_ip_to_uid[ref_py.ip_string(ip)] = "svc-%d" % i
+    return a
+
+
+def test_c_oracle_matches_hand_derived_branches():
+    pods, svcs, recs, exp, exp_stats = load_branches()
+    o = _c_oracle(pods, svcs)
+    o.process(recs)
+    got = o.edges()
+    assert edges_equal(got, exp), explain_diff(got, exp)
+    st = o.stats()
+    for k, v in exp_stats.items():
+        assert st[k] == v, (k, st[k], v)
+
+
+def test_py_restatement_matches_hand_derived_branches():
+    pods, svcs, recs, exp, exp_stats = load_branches()
+    a = _py_oracle(pods, svcs)
+    for r in recs:
+        a.process_l7(r)
+    got = pyref_edges(a)
+    assert edges_equal(got, exp), explain_diff(got, exp)
+    assert a.stats == exp_stats
+
+
+@pytest.mark.parametrize("mix", [abi.MIX_SURVEY, abi.MIX_ALL])
+def test_c_oracle_matches_py_restatement_on_synthetic(mix):
+    t = ol.Topo(50, seed=1234 + mix, mix=mix)
+    ev = t.events(0, 20000)
+    o = ol.Oracle()
+    o.load_tables(t.pod_ip, t.svc_ip)
+    o.process(ev)
+    a = ref_py.Aggregator()
+    for k, v in enumerate(t.pod_ip):
+        a.pod_ip_to_uid[ref_py.ip_string(int(v))] = "pod-%d" % k
+    for k, v in enumerate(t.svc_ip):
+        a.svc_ip_to_uid[ref_py.ip_string(int(v))] = "svc-%d" % k
+    for r in ev:
+        a.process_l7(r)
+    got, exp = o.edges(), pyref_edges(a)
+    assert edges_equal(got, exp), explain_diff(got, exp)
+    st = o.stats()
+    for k, v in a.stats.items():
+        assert st[k] == v
+    assert st["rows_emitted"] == int(got["count"].sum())
+
+
+def test_multithreaded_oracle_is_identical():
+    t = ol.Topo(100, seed=7, mix=abi.MIX_ALL)
+    ev = t.events(0, 200000)
+    a, b = ol.Oracle(), ol.Oracle()
+    a.load_tables(t.pod_ip, t.svc_ip)
+    b.load_tables(t.pod_ip, t.svc_ip)
+    a.process(ev, 1)
+    b.process(ev, 4)
+    assert a.edges().tobytes() == b.edges().tobytes()
+    assert a.stats() == b.stats()
+
+
+def test_table_erase_and_update_follow_persist_go():
+    # persist.go:55-71: UPDATE overwrites, DELETE removes
+    o = ol.Oracle()
+    o.upsert(abi.TABLE_POD, abi.ip("10.1.1.1"), 5)
+    o.upsert(abi.TABLE_SVC, abi.ip("172.16.1.1"), 9)
+    rec = np.zeros(1, dtype=abi.L7_REC)
+    rec[0] = (abi.ip("10.1.1.1"), abi.ip("172.16.1.1"), 1, 2, 200, abi.PROTO_HTTP, 1, 10, 0)
+    o.process(rec)
+    o.upsert(abi.TABLE_POD, abi.ip("10.1.1.1"), 6)      # UPDATE: same IP, new UID
+    o.process(rec)
+    o.erase(abi.TABLE_SVC, abi.ip("172.16.1.1"))        # DELETE: now outbound by raw IP
+    o.process(rec)
+    o.erase(abi.TABLE_POD, abi.ip("10.1.1.1"))          # source gone: dropped
+    o.process(rec)
+    e = o.edges()
+    keys = {(int(x["from_type"]), int(x["from"]), int(x["to_type"]), int(x["to"])) for x in e}
+    assert keys == {(0, 5, 1, 9), (0, 6, 1, 9), (0, 6, 2, abi.ip("172.16.1.1"))}
+    assert o.stats()["src_unresolved"] == 1
+
+
+def test_bucket_function_edges():
+    assert ol.bucket(0) == 0 and ol.bucket(255) == 0 and ol.bucket(256) == 0
+    assert ol.bucket(383) == 0 and ol.bucket(384) == 1 and ol.bucket(511) == 1
+    assert ol.bucket(512) == 2 and ol.bucket(767) == 2 and ol.bucket(768) == 3
+    assert ol.bucket((1 << 40) - 1) == 63 and ol.bucket(1 << 40) == 63
+    assert ol.bucket((1 << 64) - 1) == 63
+    for d in [1, 300, 1000, 123456, 2_000_000, 10**9, 10**12, 10**15]:
+        assert ol.bucket(d) == ref_py.bucket(d)
+    prev = 0
+    for sh in range(0, 50):
+        for m in (2, 3):
+            b = ol.bucket(m << sh)
+            assert b >= prev
+            prev = b
+
+
+def test_quantile_interpolation():
+    h = np.zeros(64, dtype=np.uint32)
+    h[4] = 10           # [1024, 1536)
+    assert ol.quantile(h, 0.5) == pytest.approx(1024 + 0.5 * 512, rel=1e-12)
+    assert ol.quantile(h, 1.0) == pytest.approx(1536, rel=1e-12)
+    h[5] = 10           # [1536, 2048)
+    assert ol.quantile(h, 0.75) == pytest.approx(1536 + 0.5 * 512, rel=1e-12)
+    assert ol.quantile(np.zeros(64, dtype=np.uint32), 0.5) == 0.0
+
+
+def test_compact_raw_reads_go_struct_offsets():
+    # bpfL7Event, ebpf/l7_req/l7.go:345-369
+    raw = np.zeros(2 * abi.BPF_L7_EVENT_SIZE, dtype=np.uint8)
+    v = raw[abi.BPF_L7_EVENT_SIZE:]
+    v[8:16] = np.frombuffer(np.uint64(111).tobytes(), np.uint8)       # WriteTimeNs
+    v[20:24] = np.frombuffer(np.uint32(70000).tobytes(), np.uint8)    # Status (saturates)
+    v[24:32] = np.frombuffer(np.uint64(222).tobytes(), np.uint8)      # Duration
+    v[32], v[33] = 5, 2                                               # Protocol, Method
+    v[1066] = 1                                                       # IsTls
+    v[1076:1080] = np.frombuffer(np.uint32(abi.ip("10.0.0.1")).tobytes(), np.uint8)
+    v[1080:1082] = np.frombuffer(np.uint16(4444).tobytes(), np.uint8)
+    v[1084:1088] = np.frombuffer(np.uint32(abi.ip("10.0.0.2")).tobytes(), np.uint8)
+    v[1088:1090] = np.frombuffer(np.uint16(6379).tobytes(), np.uint8)
+    out = ol.compact_raw(raw)
+    assert out[0].tobytes() == bytes(32)
+    r = out[1]
+    assert (int(r["saddr"]), int(r["daddr"]), int(r["sport"]), int(r["dport"])) == (
+        abi.ip("10.0.0.1"), abi.ip("10.0.0.2"), 4444, 6379)
+    assert int(r["status"]) == 65535 and int(r["protocol"]) == 5
+    assert int(r["method_flags"]) == (2 | abi.MF_TLS)
+    assert int(r["duration_ns"]) == 222 and int(r["write_time_ns"]) == 111
+
+
+# ---------------- SocketLine KATs: the reference's own tests ----------------
+class _SI(C.Structure):
+    _fields_ = [("saddr", C.c_uint32), ("daddr", C.c_uint32), ("sport", C.c_uint16), ("dport", C.c_uint16)]
+
+
+class _Line:
+    def __init__(self):
+        self.L = ol.lib()
+        self.h = self.L.orc_sockline_create()
+
+    def add(self, ts, si):
+        self.L.orc_sockline_add(self.h, ts, C.byref(si) if si is not None else None)
+
+    def get(self, ts):
+        out = _SI()
+        ok = self.L.orc_sockline_get(self.h, ts, C.byref(out))
+        return out if ok else None
+
+    def __len__(self):
+        return self.L.orc_sockline_len(self.h)
+
+
+def test_kat_TestSocketLine():
+    # aggregator/sock_line_test.go:11-349: 309 opens with identical (empty)
+    # SockInfo collapse to the first; GetValue(33835107729129) must succeed.
+    ts_list = [33805065332163, 33805065990716, 33805066400606, 33805066937463,
+               33805067507004, 33805068082621, 33805068543449, 33805069106660,
+               33805069572630, 33805070210774, 33805070772370, 33805071162619,
+               33805071625600, 33805073482028, 33805073841739, 33805074342888,
+               33805074573808, 33805075080976, 33805075542978, 33805076175534,
+               33807002886899, 33807004747817, 33815077484050, 33945231235604,
+               33945232859491, 33945234961387, 33945235683085, 33945236269094,
+               33945236611501, 33947002331172, 33947004517045]
+    ln = _Line()
+    for ts in ts_list:
+        ln.add(ts, _SI())
+    assert len(ln) == 1           # dedupe at sock_num_line.go:72-77
+    assert ln.get(33835107729129) is not None   # sock_line_test.go:342-347
+
+
+def test_kat_TestXxx_open_close_pairs():
+    # sock_line_test.go:351-441: opens at 10/30/50, closes at 20/40/60
+    ln = _Line()
+    for ts, si in [(10, _SI()), (20, None), (30, _SI()), (40, None), (50, _SI()), (60, None)]:
+        ln.add(ts, si)
+    assert ln.get(52) is not None     # inside [50,60): "should return 50"
+    assert ln.get(33) is not None     # inside [30,40)
+    assert ln.get(45) is not None     # closed gap, same daddr/dport both sides -> closest
+    assert ln.get(5) is not None      # before first entry, first is open (:107-115)
+
+
+def test_kat_TestXxx2_later_socket_wins():
+    # sock_line_test.go:443-473
+    ln = _Line()
+    s1, s2 = _SI(saddr=0x7878), _SI(saddr=0x7979)   # "xx", "yy"
+    ln.add(0, s2)
+    ln.add(247453008321477, s1)
+    got = ln.get(247453008321499)
+    assert got is not None and got.saddr == 0x7878
+
+
+def test_kat_TestAlreadyEstablishCanBeFound():
+    # sock_line_test.go:475-501: index-0 branch returns the first open socket
+    ln = _Line()
+    ln.add(0, _SI(saddr=0x7979))
+    got = ln.get(0)
+    assert got is not None and got.saddr == 0x7979
+
+
+def test_sockline_closed_last_entry_rules():
+    # sock_num_line.go:94-105
+    ln = _Line()
+    ln.add(100, _SI(saddr=1, daddr=2, dport=80))
+    ln.add(200, None)
+    assert ln.get(250).saddr == 1                      # within one minute of the open
+    assert ln.get(100 + 60 * 10**9 + 1) is None        # too late: "closed socket on last entry"
+    ln2 = _Line()
+    ln2.add(100, None)
+    assert ln2.get(50) is None                         # :117-118 first entry is a close
