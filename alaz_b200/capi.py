@@ -1,0 +1,264 @@
+"""ctypes binding of libalazgpu.so (include/alazgpu.h). Thin: every method is
+one C call. Fails loudly when the library or a CUDA device is missing — there
+is no Python or CPU fallback for any of it."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi, build as _build
+
+
+class AlzError(RuntimeError):
+    def __init__(self, status, what, detail=""):
+        self.status = status
+        super().__init__(f"{what}: status {status} {detail}".strip())
+
+
+_lib = None
+
+# every symbol include/alazgpu.h declares (tests/test_abi.py checks the header against this)
+EXPORTS = [
+    "alz_create", "alz_destroy", "alz_strerror", "alz_last_cuda_error", "alz_set_stream", "alz_sync",
+    "alz_table_upsert", "alz_table_erase", "alz_table_commit", "alz_submit_l7", "alz_submit_l7_device",
+    "alz_submit_l7_raw", "alz_window_flush", "alz_window_flush_device", "alz_get_stats", "alz_gnn_score",
+    "alz_edge_quantiles", "alz_submit_tcp", "alz_sock_lookup", "alz_comm_unique_id", "alz_comm_init",
+    "alz_owner_rank",
+]
+
+
+def load(rebuild=False):
+    """dlopen alaz_b200/lib/libalazgpu.so (building it first when it is missing and nvcc exists)."""
+    global _lib
+    if _lib is not None and not rebuild:
+        return _lib
+    path = _build.LIB
+    if rebuild or not os.path.exists(path):
+        path = _build.build(force=rebuild)
+    L = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    vp, u32, u64, sz, i = C.c_void_p, C.c_uint32, C.c_uint64, C.c_size_t, C.c_int
+    pp = C.POINTER(vp)
+    sig = {
+        "alz_create": ([C.POINTER(abi.Config), pp], i),
+        "alz_destroy": ([vp], i),
+        "alz_strerror": ([i], C.c_char_p),
+        "alz_last_cuda_error": ([vp], C.c_char_p),
+        "alz_set_stream": ([vp, vp], i),
+        "alz_sync": ([vp], i),
+        "alz_table_upsert": ([vp, i, u32, u32], i),
+        "alz_table_erase": ([vp, i, u32], i),
+        "alz_table_commit": ([vp], i),
+        "alz_submit_l7": ([vp, vp, sz], i),
+        "alz_submit_l7_device": ([vp, vp, sz], i),
+        "alz_submit_l7_raw": ([vp, vp, sz], i),
+        "alz_window_flush": ([vp, vp, sz, C.POINTER(sz)], i),
+        "alz_window_flush_device": ([vp, pp, C.POINTER(sz)], i),
+        "alz_get_stats": ([vp, C.POINTER(abi.Stats)], i),
+        "alz_gnn_score": ([vp, vp, sz, C.POINTER(sz)], i),
+        "alz_edge_quantiles": ([vp, vp, sz, vp], i),
+        "alz_submit_tcp": ([vp, vp, sz], i),
+        "alz_sock_lookup": ([vp, vp, sz, vp], i),
+        "alz_comm_unique_id": ([vp], i),
+        "alz_comm_init": ([vp, i, i, vp], i),
+        "alz_owner_rank": ([u32, u32], u32),
+        "alz_pinned_alloc": ([sz, pp], i),
+        "alz_pinned_free": ([vp], i),
+        "alz_dev_alloc": ([vp, sz, pp], i),
+        "alz_dev_free": ([vp, vp], i),
+        "alz_memcpy_h2d": ([vp, vp, vp, sz], i),
+        "alz_memcpy_d2h": ([vp, vp, vp, sz], i),
+        "alz_fold": ([vp], i),
+        "alz_synth_topo_create": ([u32, u64, u32], C.POINTER(abi.SynthTopo)),
+        "alz_synth_topo_destroy": ([C.POINTER(abi.SynthTopo)], None),
+        "alz_synth_fill": ([C.POINTER(abi.SynthTopo), u64, u64, vp], None),
+        "alz_synth_dev_create": ([vp, C.POINTER(abi.SynthTopo), pp], i),
+        "alz_synth_dev_fill": ([vp, vp, u64, u64, vp], i),
+        "alz_synth_dev_destroy": ([vp, vp], i),
+    }
+    for name, (args, res) in sig.items():
+        f = getattr(L, name)   # AttributeError = header/library mismatch: loud
+        f.argtypes, f.restype = args, res
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class PinnedBuffer:
+    """Library-owned pinned host memory exposed as a numpy array."""
+
+    def __init__(self, n, dtype):
+        self.L = load()
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(n) * self.dtype.itemsize
+        p = C.c_void_p()
+        rc = self.L.alz_pinned_alloc(max(self.nbytes, 1), C.byref(p))
+        if rc != 0:
+            raise AlzError(rc, "alz_pinned_alloc")
+        self.ptr = p.value
+        buf = (C.c_char * max(self.nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(n))
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self.L.alz_pinned_free(self.ptr)
+            self.ptr = None
+
+
+class Handle:
+    """One GPU's aggregator instance (alz_handle)."""
+
+    def __init__(self, device=0, max_endpoints=1 << 16, max_pairs=1 << 20, max_edges=0,
+                 max_batch=1 << 22, flags=0):
+        self.L = load()
+        cfg = abi.Config(abi_version=abi.ABI_VERSION, device=device, max_endpoints=max_endpoints,
+                         max_pairs=max_pairs, max_edges=max_edges, max_batch=max_batch, flags=flags)
+        h = C.c_void_p()
+        rc = self.L.alz_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise AlzError(rc, "alz_create", self.L.alz_strerror(rc).decode())
+        self.h = h
+        self.max_edges = max_edges or max_pairs
+
+    def _ck(self, rc, what, allow=()):
+        if rc != 0 and rc not in allow:
+            raise AlzError(rc, what, self.L.alz_strerror(rc).decode() + " | " +
+                           self.L.alz_last_cuda_error(self.h).decode())
+        return rc
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.alz_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- tables
+    def upsert(self, table, ip, id_):
+        self._ck(self.L.alz_table_upsert(self.h, table, int(ip), int(id_)), "alz_table_upsert")
+
+    def erase(self, table, ip):
+        self._ck(self.L.alz_table_erase(self.h, table, int(ip)), "alz_table_erase")
+
+    def commit(self):
+        self._ck(self.L.alz_table_commit(self.h), "alz_table_commit")
+
+    def load_tables(self, pod_ip, svc_ip):
+        for k, v in enumerate(pod_ip):
+            self.upsert(abi.TABLE_POD, int(v), k)
+        for k, v in enumerate(svc_ip):
+            self.upsert(abi.TABLE_SVC, int(v), k)
+        self.commit()
+
+    # ---- ingest
+    def submit(self, recs):
+        recs = np.ascontiguousarray(recs, dtype=abi.L7_REC)
+        self._ck(self.L.alz_submit_l7(self.h, _ptr(recs), len(recs)), "alz_submit_l7")
+
+    def submit_ptr(self, host_ptr, n):
+        self._ck(self.L.alz_submit_l7(self.h, C.c_void_p(host_ptr), n), "alz_submit_l7")
+
+    def submit_device(self, dev_ptr, n):
+        self._ck(self.L.alz_submit_l7_device(self.h, C.c_void_p(dev_ptr), n), "alz_submit_l7_device")
+
+    def submit_raw(self, raw):
+        raw = np.ascontiguousarray(raw, dtype=np.uint8)
+        n = raw.size // abi.BPF_L7_EVENT_SIZE
+        self._ck(self.L.alz_submit_l7_raw(self.h, _ptr(raw), n), "alz_submit_l7_raw")
+
+    def submit_raw_ptr(self, host_ptr, n):
+        self._ck(self.L.alz_submit_l7_raw(self.h, C.c_void_p(host_ptr), n), "alz_submit_l7_raw")
+
+    # ---- results
+    def flush(self, cap=None):
+        cap = self.max_edges if cap is None else cap
+        out = np.zeros(cap, dtype=abi.EDGE_OUT)
+        n = C.c_size_t(0)
+        self._ck(self.L.alz_window_flush(self.h, _ptr(out), cap, C.byref(n)), "alz_window_flush")
+        return out[: n.value].copy()
+
+    def flush_device(self):
+        p = C.c_void_p()
+        n = C.c_size_t(0)
+        self._ck(self.L.alz_window_flush_device(self.h, C.byref(p), C.byref(n)), "alz_window_flush_device")
+        return p.value, n.value
+
+    def stats(self):
+        st = abi.Stats()
+        self._ck(self.L.alz_get_stats(self.h, C.byref(st)), "alz_get_stats")
+        return st.as_dict()
+
+    def fold(self):
+        self._ck(self.L.alz_fold(self.h), "alz_fold")
+
+    def sync(self):
+        self._ck(self.L.alz_sync(self.h), "alz_sync")
+
+    def set_stream(self, cuda_stream):
+        self._ck(self.L.alz_set_stream(self.h, C.c_void_p(cuda_stream)), "alz_set_stream")
+
+    # ---- device helpers (bench/test support)
+    def dev_alloc(self, nbytes):
+        p = C.c_void_p()
+        self._ck(self.L.alz_dev_alloc(self.h, nbytes, C.byref(p)), "alz_dev_alloc")
+        return p.value
+
+    def dev_free(self, p):
+        self._ck(self.L.alz_dev_free(self.h, C.c_void_p(p)), "alz_dev_free")
+
+    def h2d(self, dev_ptr, arr):
+        arr = np.ascontiguousarray(arr)
+        self._ck(self.L.alz_memcpy_h2d(self.h, C.c_void_p(dev_ptr), _ptr(arr), arr.nbytes), "alz_memcpy_h2d")
+
+    def d2h(self, dev_ptr, n, dtype):
+        out = np.zeros(n, dtype=dtype)
+        self._ck(self.L.alz_memcpy_d2h(self.h, _ptr(out), C.c_void_p(dev_ptr), out.nbytes), "alz_memcpy_d2h")
+        return out
+
+
+class Topo:
+    """Synthetic cluster + stream tables via libalazgpu's own copy of the generator."""
+
+    def __init__(self, n_services, seed=0xA1A20000, mix=abi.MIX_SURVEY):
+        self.L = load()
+        self.p = self.L.alz_synth_topo_create(n_services, seed, mix)
+        if not self.p:
+            raise MemoryError("alz_synth_topo_create")
+        t = self.p.contents
+        self.n_services, self.n_pods, self.n_edges = t.n_services, t.n_pods, t.n_edges
+        self.pod_ip = np.ctypeslib.as_array(t.pod_ip, (t.n_pods,)).copy()
+        self.svc_ip = np.ctypeslib.as_array(t.svc_ip, (t.n_services,)).copy()
+        self.dev = None
+        self._handle = None
+
+    def events(self, first, n):
+        out = np.zeros(n, dtype=abi.L7_REC)
+        self.L.alz_synth_fill(self.p, int(first), int(n), _ptr(out))
+        return out
+
+    def to_device(self, handle):
+        d = C.c_void_p()
+        handle._ck(self.L.alz_synth_dev_create(handle.h, self.p, C.byref(d)), "alz_synth_dev_create")
+        self.dev, self._handle = d, handle
+        return d
+
+    def fill_device(self, handle, first, n, dev_ptr):
+        if self.dev is None:
+            self.to_device(handle)
+        handle._ck(self.L.alz_synth_dev_fill(handle.h, self.dev, int(first), int(n), C.c_void_p(dev_ptr)),
+                   "alz_synth_dev_fill")
+
+    def close(self):
+        if self.dev is not None and self._handle is not None and getattr(self._handle, "h", None):
+            self.L.alz_synth_dev_destroy(self._handle.h, self.dev)
+        self.dev = None
+        if self.p:
+            self.L.alz_synth_topo_destroy(self.p)
+            self.p = None

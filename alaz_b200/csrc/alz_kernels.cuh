@@ -1,0 +1,23 @@
+// alz_kernels.cuh — launcher declarations shared by the kernels and the C-ABI layer.
+#pragma once
+#include "alz_device.cuh"
+#include "../synth/alz_synth.h"
+
+namespace alz {
+void launch_ingest_pairs(const alz_l7_rec* recs, uint64_t n, const AccTable& fwd, const AccTable& rev,
+                         Counters* ctr, int sms, cudaStream_t s);
+void launch_ingest_eager(const alz_l7_rec* recs, uint64_t n, const EpEntry* ep, uint32_t ep_mask,
+                         const AccTable& edges, Counters* ctr, int sms, cudaStream_t s);
+void launch_fold_pairs(const AccTable& pairs, bool rev, const EpEntry* ep, uint32_t ep_mask,
+                       const AccTable& edges, Counters* ctr, int sms, cudaStream_t s);
+void launch_compact_edges(const AccTable& edges, uint64_t* keys, uint32_t* rows, Counters* ctr, int sms,
+                          cudaStream_t s);
+void launch_gather_edges(const AccTable& edges, const uint64_t* keys, const uint32_t* rows, uint32_t n_live,
+                         alz_edge_out* out, bool reset, int sms, cudaStream_t s);
+void launch_compact_raw(const uint8_t* raw, uint64_t n, alz_l7_rec* out, int sms, cudaStream_t s);
+void launch_synth(const alz_synth_view& v, uint64_t first, uint64_t n, alz_l7_rec* out, int sms, cudaStream_t s);
+// radix sort of (edge key, row) pairs by key (alz_sort.cu)
+size_t sort_pairs_temp_bytes(uint32_t n);
+void sort_pairs(void* temp, size_t temp_bytes, const uint64_t* keys_in, uint64_t* keys_out,
+                const uint32_t* vals_in, uint32_t* vals_out, uint32_t n, cudaStream_t s);
+}  // namespace alz

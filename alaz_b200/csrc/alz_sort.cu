@@ -1,0 +1,18 @@
+// alz_sort.cu — key/value radix sort used once per window flush to put the live
+// edges in canonical (packed-key) order. Off the per-event hot path; uses the
+// CUDA toolkit's CUB device radix sort.
+#include <cub/device/device_radix_sort.cuh>
+#include "alz_kernels.cuh"
+
+namespace alz {
+size_t sort_pairs_temp_bytes(uint32_t n) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
+                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);
+  return bytes;
+}
+void sort_pairs(void* temp, size_t temp_bytes, const uint64_t* keys_in, uint64_t* keys_out,
+                const uint32_t* vals_in, uint32_t* vals_out, uint32_t n, cudaStream_t s) {
+  cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, (int)n, 0, 64, s);
+}
+}  // namespace alz

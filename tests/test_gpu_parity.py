@@ -1,0 +1,258 @@
+"""GPU parity: the CUDA path, driven through the C ABI, against the CPU oracle —
+bit-exact per-edge integers on the same inputs (hand-derived vectors, seeded
+synthetic streams), plus size-independent properties at BASELINE size."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from alaz_b200 import abi, capi
+from helpers import load_branches, edges_equal, explain_diff
+
+pytestmark = pytest.mark.gpu
+
+PLANS = [0, abi.CFG_EAGER_JOIN]
+
+
+def _oracle_for(topo, events, nthreads=4):
+    o = ol.Oracle()
+    o.load_tables(topo.pod_ip, topo.svc_ip)
+    o.process(events, nthreads)
+    return o
+
+
+@pytest.mark.parametrize("flags", PLANS)
+def test_hand_derived_branch_vectors(flags):
+    pods, svcs, recs, exp, exp_stats = load_branches()
+    h = capi.Handle(max_endpoints=64, max_pairs=1024, flags=flags)
+    for ip, i in pods.items():
+        h.upsert(abi.TABLE_POD, ip, i)
+    for ip, i in svcs.items():
+        h.upsert(abi.TABLE_SVC, ip, i)
+    h.commit()
+    h.submit(recs)
+    h.fold()
+    st = h.stats()
+    got = h.flush()
+    assert edges_equal(got, exp), explain_diff(got, exp)
+    for k, v in exp_stats.items():
+        assert st[k] == v, (k, st[k], v)
+    h.close()
+
+
+@pytest.mark.parametrize("flags", PLANS)
+@pytest.mark.parametrize("mix", [abi.MIX_SURVEY, abi.MIX_ALL])
+def test_synthetic_stream_bit_exact_vs_oracle(flags, mix):
+    S, N = 1000, 2_000_000
+    t = ol.Topo(S, seed=0xA1A20001 + mix, mix=mix)
+    ev = t.events(0, N)
+    o = _oracle_for(t, ev)
+    h = capi.Handle(max_endpoints=4 * S, max_pairs=1 << 16, max_batch=300_000, flags=flags)  # forces chunking
+    h.load_tables(t.pod_ip, t.svc_ip)
+    h.submit(ev)
+    h.fold()
+    st, ost = h.stats(), o.stats()
+    got, exp = h.flush(), o.edges()
+    assert edges_equal(got, exp), explain_diff(got, exp)
+    for k in ("events_in", "rows_emitted", "not_request", "src_unresolved"):
+        assert st[k] == ost[k], (k, st[k], ost[k])
+    assert int(got["count"].sum()) == st["rows_emitted"]
+    assert np.array_equal(got["hist"].sum(axis=1), got["count"])
+    h.close()
+
+
+def test_device_generator_equals_host_generator():
+    t = capi.Topo(500, seed=77, mix=abi.MIX_ALL)
+    h = capi.Handle()
+    n = 1_000_003
+    d = h.dev_alloc(n * 32)
+    t.fill_device(h, 11, n, d)
+    h.sync()
+    dev = h.d2h(d, n, abi.L7_REC)
+    assert dev.tobytes() == t.events(11, n).tobytes()
+    h.dev_free(d)
+    t.close()
+    h.close()
+
+
+@pytest.mark.parametrize("flags", PLANS)
+def test_hbm_resident_submit_and_windows(flags):
+    S, N = 2000, 3_000_000
+    ot = ol.Topo(S, seed=5)
+    t = capi.Topo(S, seed=5)
+    h = capi.Handle(max_endpoints=4 * S, max_pairs=1 << 17, flags=flags)
+    h.load_tables(t.pod_ip, t.svc_ip)
+    d = h.dev_alloc(N * 32)
+    t.fill_device(h, 0, N, d)
+    # window 1: first 2M events in two submits; window 2: the rest
+    h.submit_device(d, 1_000_000)
+    h.submit_device(d + 1_000_000 * 32, 1_000_000)
+    w1 = h.flush()
+    h.submit_device(d + 2_000_000 * 32, N - 2_000_000)
+    w2 = h.flush()
+    w3 = h.flush()   # nothing submitted: empty window
+    o = ol.Oracle()
+    o.load_tables(ot.pod_ip, ot.svc_ip)
+    o.process(ot.events(0, 2_000_000), 4)
+    assert edges_equal(w1, o.edges()), explain_diff(w1, o.edges())
+    o.reset_window()
+    o.process(ot.events(2_000_000, N - 2_000_000), 4)
+    assert edges_equal(w2, o.edges()), explain_diff(w2, o.edges())
+    assert len(w3) == 0
+    h.dev_free(d)
+    t.close()
+    h.close()
+
+
+@pytest.mark.parametrize("flags", PLANS)
+def test_table_changes_between_submits_resolve_like_the_reference(flags):
+    # events are resolved by the tables in force when they were submitted
+    # (persist.go:55-71 / :114-130 mutate the maps between events)
+    S = 200
+    t = ol.Topo(S, seed=3, mix=abi.MIX_ALL)
+    a, b, c = t.events(0, 100_000), t.events(100_000, 100_000), t.events(200_000, 100_000)
+    o = ol.Oracle()
+    h = capi.Handle(max_endpoints=4 * S, max_pairs=1 << 15, flags=flags)
+    o.load_tables(t.pod_ip, t.svc_ip)
+    h.load_tables(t.pod_ip, t.svc_ip)
+    o.process(a); h.submit(a)
+    # DELETE some pods and services, UPDATE a pod's UID, ADD a service on a pod IP
+    for k in range(0, 40):
+        o.erase(abi.TABLE_POD, int(t.pod_ip[k])); h.erase(abi.TABLE_POD, int(t.pod_ip[k]))
+    for k in range(0, 30):
+        o.erase(abi.TABLE_SVC, int(t.svc_ip[k])); h.erase(abi.TABLE_SVC, int(t.svc_ip[k]))
+    o.upsert(abi.TABLE_POD, int(t.pod_ip[50]), 9000); h.upsert(abi.TABLE_POD, int(t.pod_ip[50]), 9000)
+    o.upsert(abi.TABLE_SVC, int(t.pod_ip[60]), 9001); h.upsert(abi.TABLE_SVC, int(t.pod_ip[60]), 9001)
+    h.commit()
+    o.process(b); h.submit(b)
+    for k in range(0, 40):   # ADD them back under new ids
+        o.upsert(abi.TABLE_POD, int(t.pod_ip[k]), 5000 + k); h.upsert(abi.TABLE_POD, int(t.pod_ip[k]), 5000 + k)
+    h.commit()
+    o.process(c); h.submit(c)
+    got, exp = h.flush(), o.edges()
+    assert edges_equal(got, exp), explain_diff(got, exp)
+    st, ost = h.stats(), o.stats()
+    for k in ("events_in", "rows_emitted", "not_request", "src_unresolved"):
+        assert st[k] == ost[k], (k, st[k], ost[k])
+    h.close()
+
+
+def _to_raw(recs):
+    """compact records -> 1096-B struct l7_event samples (ebpf/l7_req/l7.go:345-369)."""
+    n = len(recs)
+    raw = np.zeros((n, abi.BPF_L7_EVENT_SIZE), dtype=np.uint8)
+    def put(off, arr, dt):
+        b = np.ascontiguousarray(arr.astype(dt)).view(np.uint8).reshape(n, -1)
+        raw[:, off:off + b.shape[1]] = b
+    put(0, np.arange(n) % 97, "<u8")                       # fd
+    put(8, recs["write_time_ns"], "<u8")
+    put(16, np.arange(n) % 4001, "<u4")                    # pid
+    put(20, recs["status"], "<u4")
+    put(24, recs["duration_ns"], "<u8")
+    raw[:, 32] = recs["protocol"]
+    raw[:, 33] = recs["method_flags"] & abi.MF_METHOD_MASK
+    raw[:, 36:36 + 16] = np.frombuffer(b"GET /user HTTP1.", dtype=np.uint8)   # payload is ignored
+    raw[:, 1066] = (recs["method_flags"] & abi.MF_TLS) != 0
+    put(1076, recs["saddr"], "<u4")
+    put(1080, recs["sport"], "<u2")
+    put(1084, recs["daddr"], "<u4")
+    put(1088, recs["dport"], "<u2")
+    return raw.reshape(-1)
+
+
+def test_raw_perf_samples_ingest():
+    S, N = 300, 200_000
+    t = ol.Topo(S, seed=21, mix=abi.MIX_SURVEY)
+    ev = t.events(0, N)
+    raw = _to_raw(ev)
+    assert ol.compact_raw(raw).tobytes() == ev.tobytes()
+    o = _oracle_for(t, ev)
+    h = capi.Handle(max_endpoints=4 * S, max_pairs=1 << 15, max_batch=50_000)
+    h.load_tables(t.pod_ip, t.svc_ip)
+    h.submit_raw(raw)
+    got = h.flush()
+    assert edges_equal(got, o.edges()), explain_diff(got, o.edges())
+    h.close()
+
+
+def test_edge_cases_empty_single_ragged_and_sentinel_pair():
+    h = capi.Handle(max_endpoints=64, max_pairs=256)
+    o = ol.Oracle()
+    for hh in (h, o):
+        hh.upsert(abi.TABLE_POD, 0xFFFFFFFF, 7)        # 255.255.255.255 as a pod: collides with the
+        hh.upsert(abi.TABLE_POD, abi.ip("10.0.0.1"), 1)  # dictionary's empty marker
+    h.commit()
+    h.submit(np.zeros(0, dtype=abi.L7_REC))
+    assert len(h.flush()) == 0
+    recs = np.zeros(37, dtype=abi.L7_REC)               # ragged: not a multiple of a warp
+    recs["protocol"] = abi.PROTO_HTTP
+    recs["method_flags"] = 1
+    recs["saddr"] = 0xFFFFFFFF
+    recs["daddr"] = 0xFFFFFFFF
+    recs["status"] = 500
+    recs["duration_ns"] = np.arange(37, dtype=np.uint64) * 1_000_003
+    recs[5]["saddr"] = abi.ip("10.0.0.1")
+    recs[6]["daddr"] = abi.ip("10.0.0.1")
+    h.submit(recs[:1]); h.submit(recs[1:])
+    o.process(recs)
+    got, exp = h.flush(), o.edges()
+    assert edges_equal(got, exp), explain_diff(got, exp)
+    assert len(got) == 3
+    h.close()
+
+
+def test_capacity_is_reported_not_silent():
+    t = ol.Topo(500, seed=8)
+    ev = t.events(0, 300_000)
+    h = capi.Handle(max_endpoints=4096, max_pairs=64, max_edges=64)   # far too small
+    h.load_tables(t.pod_ip, t.svc_ip)
+    h.submit(ev)
+    with pytest.raises(capi.AlzError) as e:
+        h.flush()
+    assert e.value.status == abi.E_CAPACITY
+    h.close()
+
+
+def test_full_size_properties_config2():
+    """BASELINE configs[1]: 10k services / 100M events on one GPU. The oracle would take
+    minutes here, so check what must hold at any size: conservation of rows, count ==
+    sum(hist), total latency == sum of the emitted rows' durations (numpy over the stream),
+    and window linearity (A then B in one window == whole)."""
+    S, N, CH = 10_000, 100_000_000, 10_000_000
+    t = capi.Topo(S, seed=0xA1A20000 + 1)
+    h = capi.Handle(max_endpoints=4 * S, max_pairs=1 << 20)
+    h.load_tables(t.pod_ip, t.svc_ip)
+    d = h.dev_alloc(N * 32)
+    t.fill_device(h, 0, N, d)
+    h.submit_device(d, N)
+    st_before = None
+    edges = h.flush()
+    st = h.stats()
+    assert st["events_in"] == N
+    assert int(edges["count"].sum()) == st["rows_emitted"] == N - st["not_request"] - st["src_unresolved"]
+    assert np.array_equal(edges["hist"].sum(axis=1), edges["count"])
+    # independent numpy pass over the stream, chunked D2H
+    pods = np.sort(t.pod_ip)
+    lat = 0
+    rows = 0
+    err = 0
+    for c in range(0, N, CH):
+        ev = h.d2h(d + c * 32, CH, abi.L7_REC)
+        emit = np.isin(ev["protocol"], [abi.PROTO_HTTP, abi.PROTO_AMQP, abi.PROTO_REDIS])
+        idx = np.searchsorted(pods, ev["saddr"])
+        idx[idx == len(pods)] = 0
+        known = pods[idx] == ev["saddr"]
+        m = emit & known
+        rows += int(m.sum())
+        lat += int(ev["duration_ns"][m].sum(dtype=np.uint64))
+        err += int((m & (ev["protocol"] == abi.PROTO_HTTP) & (ev["status"] >= 500) & (ev["status"] < 600)).sum())
+    assert rows == st["rows_emitted"]
+    assert lat == int(edges["lat_sum_ns"].sum(dtype=np.uint64))
+    assert err == int(edges["err5xx"].sum())
+    # linearity: two halves submitted separately into one window give the same edges
+    h.submit_device(d, N // 2)
+    h.submit_device(d + (N // 2) * 32, N - N // 2)
+    again = h.flush()
+    assert edges_equal(again, edges)
+    h.dev_free(d)
+    t.close()
+    h.close()
