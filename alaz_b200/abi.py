@@ -25,6 +25,7 @@ MF_METHOD_MASK, MF_PAYLOAD_REJECT, MF_TLS = 0x3F, 0x40, 0x80
 NODE_POD, NODE_SVC, NODE_OUTBOUND = 0, 1, 2
 TABLE_POD, TABLE_SVC = 0, 1
 CFG_EAGER_JOIN = 0x1
+CFG_NO_SMEM_CACHE = 0x2
 MIX_SURVEY, MIX_ALL = 0, 1
 
 L7_REC = np.dtype([

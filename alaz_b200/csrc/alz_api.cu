@@ -45,16 +45,20 @@ static bool is_lib_pinned(const void* p, size_t bytes) {
   return false;
 }
 
-static int alloc_table(alz_handle* h, AccTable* t, uint32_t cap, bool with_count) {
-  t->cap = cap;
-  const size_t rows = (size_t)cap + 1;
-  CK(cudaMalloc(&t->keys, rows * 8));
+static int alloc_table(alz_handle* h, AccTable* t, uint32_t max_rows, uint32_t* n_rows_dev, bool with_count) {
+  t->max_rows = max_rows;
+  t->n_rows = n_rows_dev;
+  const uint32_t dict_cap = next_pow2(2ull * max_rows);
+  t->dict_mask = dict_cap - 1;
+  const size_t rows = (size_t)max_rows + 1;
+  CK(cudaMalloc(&t->dict, (size_t)dict_cap * sizeof(DictEnt)));
+  CK(cudaMalloc(&t->row_key, rows * 8));
   CK(cudaMalloc(&t->lat_sum, rows * 8));
   CK(cudaMalloc(&t->err5xx, rows * 8));
   t->count = nullptr;
   if (with_count) CK(cudaMalloc(&t->count, rows * 8));
   CK(cudaMalloc(&t->hist, rows * ALZ_NB * 4));
-  CK(cudaMemsetAsync(t->keys, 0xFF, rows * 8, h->stream));
+  CK(cudaMemsetAsync(t->dict, 0xFF, (size_t)dict_cap * sizeof(DictEnt), h->stream));
   CK(cudaMemsetAsync(t->lat_sum, 0, rows * 8, h->stream));
   CK(cudaMemsetAsync(t->err5xx, 0, rows * 8, h->stream));
   if (with_count) CK(cudaMemsetAsync(t->count, 0, rows * 8, h->stream));
@@ -62,8 +66,15 @@ static int alloc_table(alz_handle* h, AccTable* t, uint32_t cap, bool with_count
   return ALZ_OK;
 }
 static void free_table(AccTable* t) {
-  cudaFree(t->keys); cudaFree(t->lat_sum); cudaFree(t->err5xx); cudaFree(t->count); cudaFree(t->hist);
+  cudaFree(t->dict); cudaFree(t->row_key); cudaFree(t->lat_sum); cudaFree(t->err5xx); cudaFree(t->count);
+  cudaFree(t->hist);
   memset(t, 0, sizeof(*t));
+}
+// all keys out of the dictionary, row allocator back to zero (rows were zeroed by fold / gather)
+static int clear_dict(alz_handle* h, AccTable* t) {
+  CK(cudaMemsetAsync(t->dict, 0xFF, ((size_t)t->dict_mask + 1) * sizeof(DictEnt), h->stream));
+  CK(cudaMemsetAsync(t->n_rows, 0, 4, h->stream));
+  return ALZ_OK;
 }
 
 extern "C" const char* alz_strerror(int s) {
@@ -121,17 +132,15 @@ extern "C" int alz_create(const alz_config* cfg, alz_handle** out) {
   h->ep_cap = next_pow2(2ull * h->cfg.max_endpoints);
   CKC(cudaMalloc(&h->d_ep, (size_t)h->ep_cap * sizeof(EpEntry)));
   CKC(cudaMemsetAsync(h->d_ep, 0, (size_t)h->ep_cap * sizeof(EpEntry), h->stream));
-  const uint32_t pcap = next_pow2(2ull * h->cfg.max_pairs);
-  const uint32_t rcap = std::max<uint32_t>(1024u, pcap >> 3);
-  const uint32_t ecap = next_pow2(2ull * h->cfg.max_edges);
-  int rc;
-  if (!(h->cfg.flags & ALZ_CFG_EAGER_JOIN)) {
-    if ((rc = alloc_table(h, &h->pairs_fwd, pcap, false)) != ALZ_OK) return fail(rc);
-    if ((rc = alloc_table(h, &h->pairs_rev, rcap, false)) != ALZ_OK) return fail(rc);
-  }
-  if ((rc = alloc_table(h, &h->edges, ecap, true)) != ALZ_OK) return fail(rc);
   CKC(cudaMalloc(&h->d_ctr, sizeof(Counters)));
   CKC(cudaMemsetAsync(h->d_ctr, 0, sizeof(Counters), h->stream));
+  int rc;
+  if (!(h->cfg.flags & ALZ_CFG_EAGER_JOIN)) {
+    if ((rc = alloc_table(h, &h->pairs_fwd, h->cfg.max_pairs, &h->d_ctr->fwd_rows, false)) != ALZ_OK) return fail(rc);
+    if ((rc = alloc_table(h, &h->pairs_rev, std::max<uint32_t>(1024u, h->cfg.max_pairs >> 3), &h->d_ctr->rev_rows,
+                          false)) != ALZ_OK) return fail(rc);
+  }
+  if ((rc = alloc_table(h, &h->edges, h->cfg.max_edges, &h->d_ctr->edge_rows, true)) != ALZ_OK) return fail(rc);
   CKC(cudaMallocHost(&h->h_ctr, sizeof(Counters)));
   for (int b = 0; b < 2; ++b) {
     CKC(cudaMalloc(&h->d_keys[b], (size_t)h->cfg.max_edges * 8));
@@ -232,8 +241,10 @@ int alz_internal_fold(alz_handle* h) {
   launch_fold_pairs(h->pairs_fwd, false, h->d_ep, h->ep_cap - 1, h->edges, h->d_ctr, h->sms, h->stream);
   launch_fold_pairs(h->pairs_rev, true, h->d_ep, h->ep_cap - 1, h->edges, h->d_ctr, h->sms, h->stream);
   CK(cudaGetLastError());
+  int rc = clear_dict(h, &h->pairs_fwd);
+  if (rc == ALZ_OK) rc = clear_dict(h, &h->pairs_rev);
   h->pending_since_fold = 0;
-  return ALZ_OK;
+  return rc;
 }
 
 extern "C" int alz_table_commit(alz_handle* h) {
@@ -266,7 +277,8 @@ static int ingest_device(alz_handle* h, const alz_l7_rec* d, uint64_t n) {
   if (h->cfg.flags & ALZ_CFG_EAGER_JOIN)
     launch_ingest_eager(d, n, h->d_ep, h->ep_cap - 1, h->edges, h->d_ctr, h->sms, h->stream);
   else
-    launch_ingest_pairs(d, n, h->pairs_fwd, h->pairs_rev, h->d_ctr, h->sms, h->stream);
+    launch_ingest_pairs(d, n, h->pairs_fwd, h->pairs_rev, h->d_ctr, h->sms, h->stream,
+                        (h->cfg.flags & ALZ_CFG_NO_SMEM_CACHE) ? 0 : 1);
   CK(cudaGetLastError());
   h->events_in += n;
   h->pending_since_fold += n;
@@ -360,19 +372,17 @@ static int read_counters(alz_handle* h) {
   return ALZ_OK;
 }
 
-// fold + compact + sort (no reset). After it h->n_live edges sit in d_keys[1]/d_rows[1].
+// fold + sort of the live edge keys (no reset). After it h->n_live edges sit in d_keys[1]/d_rows[1].
 static int prepare_flush(alz_handle* h) {
   int rc = alz_internal_fold(h);
   if (rc != ALZ_OK) return rc;
-  CK(cudaMemsetAsync(&h->d_ctr->n_live, 0, 8, h->stream));
-  launch_compact_edges(h->edges, h->d_keys[0], h->d_rows[0], h->d_ctr, h->sms, h->stream);
-  CK(cudaGetLastError());
   rc = read_counters(h);
   if (rc != ALZ_OK) return rc;
-  h->n_live = (uint32_t)h->h_ctr->n_live;
-  if (h->n_live > h->cfg.max_edges) return ALZ_E_CAPACITY;
+  h->n_live = h->h_ctr->edge_rows;
+  if (h->n_live > h->cfg.max_edges) { h->n_live = h->cfg.max_edges; return ALZ_E_CAPACITY; }
   if (h->n_live) {
-    sort_pairs(h->d_sort_tmp, h->sort_tmp_bytes, h->d_keys[0], h->d_keys[1], h->d_rows[0], h->d_rows[1],
+    launch_iota(h->d_rows[0], h->n_live, h->sms, h->stream);
+    sort_pairs(h->d_sort_tmp, h->sort_tmp_bytes, h->edges.row_key, h->d_keys[1], h->d_rows[0], h->d_rows[1],
                h->n_live, h->stream);
     CK(cudaGetLastError());
   }
@@ -382,9 +392,8 @@ static int prepare_flush(alz_handle* h) {
 static int finish_flush(alz_handle* h) {
   launch_gather_edges(h->edges, h->d_keys[1], h->d_rows[1], h->n_live, h->d_out, true, h->sms, h->stream);
   CK(cudaGetLastError());
-  // window counters restart; cumulative ones (not_request, src_unresolved) keep running
-  CK(cudaMemsetAsync(&h->d_ctr->pairs_inserted, 0, 8, h->stream));
-  CK(cudaMemsetAsync(&h->d_ctr->edges_inserted, 0, 8, h->stream));
+  int rc = clear_dict(h, &h->edges);
+  if (rc != ALZ_OK) return rc;
   h->last_n_edges = h->n_live;
   h->windows++;
   return ALZ_OK;
@@ -441,8 +450,8 @@ extern "C" int alz_get_stats(alz_handle* h, alz_stats* st) {
   st->not_request = h->h_ctr->not_request;
   st->src_unresolved = h->h_ctr->src_unresolved;   // complete once pending pairs are folded
   st->rows_emitted = h->events_in - st->not_request - st->src_unresolved - h->h_ctr->capacity_events;
-  st->pairs_live = h->h_ctr->pairs_inserted;
-  st->edges_live = h->h_ctr->edges_inserted;
+  st->pairs_live = (uint64_t)h->h_ctr->fwd_rows + h->h_ctr->rev_rows;
+  st->edges_live = h->h_ctr->edge_rows;
   st->tcp_events_in = h->tcp_events_in;
   st->tcp_localhost_dropped = h->tcp_localhost_dropped;
   return ALZ_OK;

@@ -90,33 +90,61 @@ __device__ __forceinline__ uint32_t latency_bucket(uint64_t d) {
   return 2u * (o - 8u) + (uint32_t)((d >> (o - 1u)) & 1ull);
 }
 
-// ---- open-addressed u64 dictionary with accumulator rows ---------------------------
+// ---- open-addressed u64 dictionary -> dense accumulator rows ---------------------------
+// The dictionary only maps a key to a row number; rows are handed out densely
+// by an atomic counter, so the accumulators of the live keys stay contiguous
+// (190k live pairs x 280 B = 53 MB: L2-resident) however large the dictionary
+// was sized. v1 indexed the accumulators by dictionary slot and every
+// reduction missed L2 (profiles/r1_v2_ingest_ncu.txt: 11 GB DRAM reads for a
+// 3.2 GB stream).
+struct __align__(16) DictEnt {
+  uint64_t key;   // kEmptyKey = free
+  uint32_t row;   // kNoRow until the inserting thread has published it
+  uint32_t pad;
+};
+constexpr uint32_t kNoRow = 0xFFFFFFFFu;
+constexpr uint32_t kLostRow = 0xFFFFFFFEu;  // dictionary or row pool exhausted
+
 struct AccTable {
-  uint64_t* keys;     // [cap + 1]; row `cap` is the overflow/sentinel row
-  uint64_t* lat_sum;  // [cap + 1]
-  uint64_t* err5xx;   // [cap + 1]
-  uint64_t* count;    // [cap + 1] (edge tables only; pair tables derive it from hist)
-  uint32_t* hist;     // [(cap + 1) * ALZ_NB]
-  uint32_t cap;       // power of two
+  DictEnt* dict;      // [dict_mask + 1]
+  uint32_t dict_mask;
+  uint32_t max_rows;  // rows [0, max_rows) are allocatable; row max_rows is the sentinel row
+  uint32_t* n_rows;   // device counter of allocated rows
+  uint64_t* row_key;  // [max_rows + 1]
+  uint64_t* lat_sum;  // [max_rows + 1]
+  uint64_t* err5xx;   // [max_rows + 1]
+  uint64_t* count;    // [max_rows + 1] (edge table only; pair tables derive it from hist)
+  uint32_t* hist;     // [(max_rows + 1) * ALZ_NB]
 };
 
-// returns the row of `key`, inserting it if absent; cap = table full (counted by caller)
-__device__ __forceinline__ uint32_t find_or_insert(const AccTable& t, uint64_t key, uint32_t* inserted) {
-  if (key == kEmptyKey) return t.cap;  // the one key that collides with the marker
-  const uint32_t mask = t.cap - 1u;
-  uint32_t slot = (uint32_t)hash64(key) & mask;
+// row of `key`, inserting it if absent; >= kLostRow when capacity is exhausted
+__device__ __forceinline__ uint32_t find_or_insert(const AccTable& t, uint64_t key) {
+  if (key == kEmptyKey) return t.max_rows;  // the one key that collides with the free marker
+  uint32_t slot = (uint32_t)hash64(key) & t.dict_mask;
+#pragma unroll 1
   for (uint32_t p = 0; p < kMaxProbe; ++p) {
-    uint64_t k = __ldcg(&t.keys[slot]);
-    if (k == key) return slot;
+    const uint4 e = __ldcg(reinterpret_cast<const uint4*>(&t.dict[slot]));
+    uint64_t k = ((uint64_t)e.y << 32) | e.x;
+    uint32_t row = e.z;
     if (k == kEmptyKey) {
-      const uint64_t old = atomicCAS((unsigned long long*)&t.keys[slot], (unsigned long long)kEmptyKey,
+      const uint64_t old = atomicCAS((unsigned long long*)&t.dict[slot].key, (unsigned long long)kEmptyKey,
                                      (unsigned long long)key);
-      if (old == kEmptyKey) { if (inserted) *inserted += 1u; return slot; }
-      if (old == key) return slot;
+      if (old == kEmptyKey) {
+        row = atomicAdd(t.n_rows, 1u);
+        if (row >= t.max_rows) row = kLostRow; else t.row_key[row] = key;
+        *reinterpret_cast<volatile uint32_t*>(&t.dict[slot].row) = row;
+        return row;
+      }
+      k = old;
+      row = kNoRow;
     }
-    slot = (slot + 1u) & mask;
+    if (k == key) {
+      while (row == kNoRow) row = *reinterpret_cast<volatile uint32_t*>(&t.dict[slot].row);
+      return row;
+    }
+    slot = (slot + 1u) & t.dict_mask;
   }
-  return 0xFFFFFFFFu;
+  return kLostRow;
 }
 
 // probe the endpoint table; returns state bits (0 = absent) and ids
@@ -165,15 +193,14 @@ __device__ __forceinline__ uint32_t rec_protocol(const Rec& r) { return (r.w[3] 
 __device__ __forceinline__ uint32_t rec_mflags(const Rec& r) { return r.w[3] >> 24; }
 __device__ __forceinline__ uint64_t rec_duration(const Rec& r) { return ((uint64_t)r.w[5] << 32) | r.w[4]; }
 
-// device-side counters (one cache line per handle)
+// device-side counters (per handle)
 struct Counters {
   unsigned long long not_request;
   unsigned long long src_unresolved;
-  unsigned long long pairs_inserted;
-  unsigned long long edges_inserted;
-  unsigned long long capacity_events;  // events/pairs lost to a full dictionary
-  unsigned long long n_live;           // scratch for compaction
-  unsigned long long pad[2];
+  unsigned long long capacity_events;  // events lost to an exhausted dictionary / row pool
+  unsigned long long pad0;
+  uint32_t fwd_rows, rev_rows, edge_rows, pad1;  // row allocators of the three tables
+  unsigned long long pad2[2];
 };
 
 }  // namespace alz

@@ -7,54 +7,226 @@
 // reductions per event — and joins only the DISTINCT pairs against the tables
 // (fold_pairs_kernel). ALZ_CFG_EAGER_JOIN keeps the textbook plan (join every
 // event, then reduce) for comparison; both give bit-identical edges.
+//
+// Control flow in the per-event loops is kept warp-convergent on purpose: every
+// lane walks the same statements under predicates and meets at __syncwarp()
+// between the divergent dictionary probes and the reductions. The first
+// version let lanes leave the probe loops on their own paths and the
+// reductions then issued with ~2 active lanes per instruction
+// (profiles/r1_v2_ingest_ncu.txt).
 #include "alz_kernels.cuh"
 
 namespace alz {
 
+// per-event fields every plan needs
+struct Ev {
+  uint64_t key;   // (saddr << 32) | daddr
+  uint64_t dur;
+  uint32_t bucket;
+  bool act;       // the reference would hand a row to PersistRequest (before resolve)
+  bool rev;       // ReverseDirection applies
+  bool err;       // counts as 5xx
+};
+__device__ __forceinline__ Ev decode(const Rec& r, bool live) {
+  Ev e;
+  const uint32_t proto = rec_protocol(r), mf = rec_mflags(r);
+  e.act = live && emits_request_row(proto, mf);
+  e.rev = is_reversed(proto, mf);
+  e.key = ((uint64_t)rec_saddr(r) << 32) | rec_daddr(r);
+  e.dur = rec_duration(r);
+  e.bucket = latency_bucket(e.dur);
+  e.err = is_5xx(proto, rec_status(r));
+  return e;
+}
+
+__device__ __forceinline__ void global_accumulate(const AccTable& t, uint32_t row, uint32_t bucket, uint64_t dur,
+                                                  bool err) {
+  atomicAdd(&t.hist[(size_t)row * ALZ_NB + bucket], 1u);
+  atomicAdd((unsigned long long*)&t.lat_sum[row], (unsigned long long)dur);
+  if (err) atomicAdd((unsigned long long*)&t.err5xx[row], 1ull);
+}
+
+__device__ __forceinline__ void flush_thread_counters(Counters* ctr, uint32_t not_request, uint32_t unresolved,
+                                                      uint32_t lost) {
+  for (int o = 16; o > 0; o >>= 1) {
+    not_request += __shfl_xor_sync(0xFFFFFFFFu, not_request, o);
+    unresolved += __shfl_xor_sync(0xFFFFFFFFu, unresolved, o);
+    lost += __shfl_xor_sync(0xFFFFFFFFu, lost, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (not_request) atomicAdd(&ctr->not_request, (unsigned long long)not_request);
+    if (unresolved) atomicAdd(&ctr->src_unresolved, (unsigned long long)unresolved);
+    if (lost) atomicAdd(&ctr->capacity_events, (unsigned long long)lost);
+  }
+}
+
 // ---------------------------------------------------------------------------
-// ingest, default plan: events -> per-socket-pair accumulators
+// ingest v1 (ALZ_CFG_NO_SMEM_CACHE): global reductions only
 // ---------------------------------------------------------------------------
 template <int UNROLL>
 __global__ void __launch_bounds__(256) ingest_pairs_kernel(const alz_l7_rec* __restrict__ recs, uint64_t n,
                                                            AccTable fwd, AccTable rev, Counters* ctr) {
-  uint32_t not_request = 0, inserted = 0, lost = 0;
+  uint32_t not_request = 0, lost = 0;
+  const uint32_t lane = threadIdx.x & 31u;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (; i < n; i += stride * UNROLL) {
+  for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride * UNROLL) {
     Rec r[UNROLL];
     bool live[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-      const uint64_t j = i + (uint64_t)u * stride;
+      const uint64_t j = base + (uint64_t)u * stride + lane;
       live[u] = j < n;
       if (live[u]) r[u] = load_rec(recs + j);
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-      if (!live[u]) continue;
-      const uint32_t proto = rec_protocol(r[u]), mf = rec_mflags(r[u]);
-      if (!emits_request_row(proto, mf)) { ++not_request; continue; }
-      const uint64_t key = ((uint64_t)rec_saddr(r[u]) << 32) | rec_daddr(r[u]);
-      const AccTable& t = is_reversed(proto, mf) ? rev : fwd;
-      const uint32_t slot = find_or_insert(t, key, &inserted);
-      if (slot == 0xFFFFFFFFu) { ++lost; continue; }
-      const uint64_t dur = rec_duration(r[u]);
-      atomicAdd(&t.hist[(size_t)slot * ALZ_NB + latency_bucket(dur)], 1u);
-      atomicAdd((unsigned long long*)&t.lat_sum[slot], (unsigned long long)dur);
-      if (is_5xx(proto, rec_status(r[u]))) atomicAdd((unsigned long long*)&t.err5xx[slot], 1ull);
+      const Ev e = decode(r[u], live[u]);
+      not_request += (live[u] && !e.act) ? 1u : 0u;
+      uint32_t row = kLostRow;
+      if (e.act) row = find_or_insert(e.rev ? rev : fwd, e.key);
+      __syncwarp();
+      if (e.act) {
+        if (row >= kLostRow) ++lost;
+        else global_accumulate(e.rev ? rev : fwd, row, e.bucket, e.dur, e.err);
+      }
     }
   }
-  // warp-aggregate the rare counters
-  for (int o = 16; o > 0; o >>= 1) {
-    not_request += __shfl_xor_sync(0xFFFFFFFFu, not_request, o);
-    inserted += __shfl_xor_sync(0xFFFFFFFFu, inserted, o);
-    lost += __shfl_xor_sync(0xFFFFFFFFu, lost, o);
+  flush_thread_counters(ctr, not_request, 0u, lost);
+}
+
+// ---------------------------------------------------------------------------
+// ingest v2 (default): per-CTA shared-memory cache of hot socket pairs.
+// The stream is Zipf-skewed: a handful of pairs take most events, and their
+// global reductions serialise in one L2 slice (v1: 17 ms / 100M events, all of
+// it same-address atomics, profiles/r1_v1_launches.csv). Each CTA admits the
+// first pairs it sees into an open-addressed table in shared memory
+// (first-come is hot-biased under Zipf) and reduces them there; cold pairs go
+// straight to the global dictionary. At the end the CTA adds its private rows
+// into the global table, one reduction per non-zero cell.
+//
+// smem row = 64 hist cells + lat_lo + lat_hi + err5xx = 67 words: the odd
+// stride spreads equal buckets of different pairs over the banks.
+// ---------------------------------------------------------------------------
+constexpr int kRowWords = ALZ_NB + 3;
+struct SmemTab {
+  uint64_t* keys;   // [slots]
+  uint32_t* rows;   // [slots * kRowWords]
+  uint32_t* used;   // admitted pairs
+  uint32_t mask;    // slots - 1
+  uint32_t limit;   // admission stops here (load factor)
+};
+
+__device__ __forceinline__ int smem_find_or_admit(const SmemTab& t, uint64_t key) {
+  if (key == kEmptyKey) return -1;
+  uint32_t slot = (uint32_t)(hash64(key) >> 32) & t.mask;
+#pragma unroll 1
+  for (int p = 0; p < 6; ++p) {
+    const uint64_t k = t.keys[slot];
+    if (k == key) return (int)slot;
+    if (k == kEmptyKey) {
+      if (*reinterpret_cast<volatile uint32_t*>(t.used) >= t.limit) return -1;
+      const uint64_t old = atomicCAS((unsigned long long*)&t.keys[slot], (unsigned long long)kEmptyKey,
+                                     (unsigned long long)key);
+      if (old == kEmptyKey) { atomicAdd(t.used, 1u); return (int)slot; }
+      if (old == key) return (int)slot;
+    }
+    slot = (slot + 1u) & t.mask;
   }
-  if ((threadIdx.x & 31) == 0) {
-    if (not_request) atomicAdd(&ctr->not_request, (unsigned long long)not_request);
-    if (inserted) atomicAdd(&ctr->pairs_inserted, (unsigned long long)inserted);
-    if (lost) atomicAdd(&ctr->capacity_events, (unsigned long long)lost);
+  return -1;
+}
+
+__device__ __forceinline__ void smem_accumulate(const SmemTab& t, int slot, uint32_t bucket, uint64_t dur, bool err) {
+  uint32_t* row = t.rows + (size_t)slot * kRowWords;
+  atomicAdd(&row[bucket], 1u);
+  const uint32_t lo = (uint32_t)dur;
+  const uint32_t old = atomicAdd(&row[ALZ_NB], lo);
+  const uint32_t hi = (uint32_t)(dur >> 32) + ((old + lo < old) ? 1u : 0u);
+  if (hi) atomicAdd(&row[ALZ_NB + 1], hi);
+  if (err) atomicAdd(&row[ALZ_NB + 2], 1u);
+}
+
+// add one private table into the global one; a warp per row
+__device__ __forceinline__ void smem_drain(const SmemTab& s, const AccTable& g, uint32_t* lost) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (uint32_t slot = warp; slot <= s.mask; slot += nwarps) {
+    const uint64_t key = s.keys[slot];
+    if (key == kEmptyKey) continue;   // warp-uniform
+    const uint32_t* row = s.rows + (size_t)slot * kRowWords;
+    uint32_t grow = 0;
+    if (lane == 0) grow = find_or_insert(g, key);
+    grow = __shfl_sync(0xFFFFFFFFu, grow, 0);
+    const uint32_t h0 = row[lane], h1 = row[32u + lane];
+    if (grow >= kLostRow) {
+      uint32_t c = h0 + h1;
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+      if (lane == 0) *lost += c;
+      continue;
+    }
+    if (h0) atomicAdd(&g.hist[(size_t)grow * ALZ_NB + lane], h0);
+    if (h1) atomicAdd(&g.hist[(size_t)grow * ALZ_NB + 32u + lane], h1);
+    if (lane == 0) {
+      const uint64_t lat = ((uint64_t)row[ALZ_NB + 1] << 32) + row[ALZ_NB];
+      if (lat) atomicAdd((unsigned long long*)&g.lat_sum[grow], (unsigned long long)lat);
+      if (row[ALZ_NB + 2]) atomicAdd((unsigned long long*)&g.err5xx[grow], (unsigned long long)row[ALZ_NB + 2]);
+    }
   }
+}
+
+template <int UNROLL, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) ingest_pairs_smem_kernel(const alz_l7_rec* __restrict__ recs, uint64_t n,
+                                                                        AccTable fwd, AccTable rev, Counters* ctr,
+                                                                        uint32_t fwd_slots, uint32_t rev_slots) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __shared__ uint32_t s_used[2];
+  SmemTab sf, sr;
+  sf.keys = reinterpret_cast<uint64_t*>(smem_raw);
+  sr.keys = sf.keys + fwd_slots;
+  sf.rows = reinterpret_cast<uint32_t*>(sr.keys + rev_slots);
+  sr.rows = sf.rows + (size_t)fwd_slots * kRowWords;
+  sf.used = &s_used[0]; sr.used = &s_used[1];
+  sf.mask = fwd_slots - 1u; sr.mask = rev_slots - 1u;
+  sf.limit = fwd_slots - (fwd_slots >> 2); sr.limit = rev_slots - (rev_slots >> 2);
+  for (uint32_t i = threadIdx.x; i < fwd_slots + rev_slots; i += THREADS) sf.keys[i] = kEmptyKey;
+  for (uint32_t i = threadIdx.x; i < (fwd_slots + rev_slots) * kRowWords; i += THREADS) sf.rows[i] = 0u;
+  if (threadIdx.x < 2) s_used[threadIdx.x] = 0u;
+  __syncthreads();
+
+  uint32_t not_request = 0, lost = 0;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t stride = (uint64_t)gridDim.x * THREADS;
+  for (uint64_t base = (uint64_t)blockIdx.x * THREADS + (threadIdx.x & ~31u); base < n; base += stride * UNROLL) {
+    Rec r[UNROLL];
+    bool live[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const uint64_t j = base + (uint64_t)u * stride + lane;
+      live[u] = j < n;
+      if (live[u]) r[u] = load_rec(recs + j);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const Ev e = decode(r[u], live[u]);
+      not_request += (live[u] && !e.act) ? 1u : 0u;
+      // 1) shared-memory table
+      int ss = -1;
+      if (e.act) ss = smem_find_or_admit(e.rev ? sr : sf, e.key);
+      __syncwarp();
+      if (ss >= 0) smem_accumulate(e.rev ? sr : sf, ss, e.bucket, e.dur, e.err);
+      // 2) the rest: global dictionary
+      const bool g = e.act && ss < 0;
+      uint32_t row = kLostRow;
+      if (g) row = find_or_insert(e.rev ? rev : fwd, e.key);
+      __syncwarp();
+      if (g) {
+        if (row >= kLostRow) ++lost;
+        else global_accumulate(e.rev ? rev : fwd, row, e.bucket, e.dur, e.err);
+      }
+    }
+  }
+  __syncthreads();
+  smem_drain(sf, fwd, &lost);
+  smem_drain(sr, rev, &lost);
+  flush_thread_counters(ctr, not_request, 0u, lost);
 }
 
 // ---------------------------------------------------------------------------
@@ -63,117 +235,91 @@ __global__ void __launch_bounds__(256) ingest_pairs_kernel(const alz_l7_rec* __r
 __global__ void __launch_bounds__(256) ingest_eager_kernel(const alz_l7_rec* __restrict__ recs, uint64_t n,
                                                            const EpEntry* __restrict__ ep, uint32_t ep_mask,
                                                            AccTable edges, Counters* ctr) {
-  uint32_t not_request = 0, unresolved = 0, inserted = 0, lost = 0;
+  uint32_t not_request = 0, unresolved = 0, lost = 0;
+  const uint32_t lane = threadIdx.x & 31u;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const Rec r = load_rec(recs + i);
-    const uint32_t proto = rec_protocol(r), mf = rec_mflags(r);
-    if (!emits_request_row(proto, mf)) { ++not_request; continue; }
-    uint64_t ekey;
-    if (!resolve_edge(ep, ep_mask, rec_saddr(r), rec_daddr(r), is_reversed(proto, mf), &ekey)) {
-      ++unresolved; continue;
+  for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+    const uint64_t j = base + lane;
+    const bool live = j < n;
+    Rec r = {};
+    if (live) r = load_rec(recs + j);
+    const Ev e = decode(r, live);
+    not_request += (live && !e.act) ? 1u : 0u;
+    uint64_t ekey = 0;
+    bool ok = false;
+    if (e.act) ok = resolve_edge(ep, ep_mask, (uint32_t)(e.key >> 32), (uint32_t)e.key, e.rev, &ekey);
+    __syncwarp();
+    unresolved += (e.act && !ok) ? 1u : 0u;
+    uint32_t row = kLostRow;
+    if (ok) row = find_or_insert(edges, ekey);
+    __syncwarp();
+    if (ok) {
+      if (row >= kLostRow) ++lost;
+      else {
+        global_accumulate(edges, row, e.bucket, e.dur, e.err);
+        atomicAdd((unsigned long long*)&edges.count[row], 1ull);
+      }
     }
-    const uint32_t slot = find_or_insert(edges, ekey, &inserted);
-    if (slot == 0xFFFFFFFFu) { ++lost; continue; }
-    const uint64_t dur = rec_duration(r);
-    atomicAdd(&edges.hist[(size_t)slot * ALZ_NB + latency_bucket(dur)], 1u);
-    atomicAdd((unsigned long long*)&edges.lat_sum[slot], (unsigned long long)dur);
-    atomicAdd((unsigned long long*)&edges.count[slot], 1ull);
-    if (is_5xx(proto, rec_status(r))) atomicAdd((unsigned long long*)&edges.err5xx[slot], 1ull);
   }
-  for (int o = 16; o > 0; o >>= 1) {
-    not_request += __shfl_xor_sync(0xFFFFFFFFu, not_request, o);
-    unresolved += __shfl_xor_sync(0xFFFFFFFFu, unresolved, o);
-    inserted += __shfl_xor_sync(0xFFFFFFFFu, inserted, o);
-    lost += __shfl_xor_sync(0xFFFFFFFFu, lost, o);
-  }
-  if ((threadIdx.x & 31) == 0) {
-    if (not_request) atomicAdd(&ctr->not_request, (unsigned long long)not_request);
-    if (unresolved) atomicAdd(&ctr->src_unresolved, (unsigned long long)unresolved);
-    if (inserted) atomicAdd(&ctr->edges_inserted, (unsigned long long)inserted);
-    if (lost) atomicAdd(&ctr->capacity_events, (unsigned long long)lost);
-  }
+  flush_thread_counters(ctr, not_request, unresolved, lost);
 }
 
 // ---------------------------------------------------------------------------
 // fold: the hash join proper, on distinct socket pairs. One warp per pair row:
-// resolve (saddr,daddr) -> edge, add the row into the edge accumulators, and
-// return the row to the empty state.
+// resolve (saddr,daddr) -> edge, add the row into the edge accumulators and
+// zero it. The caller clears the pair dictionary afterwards.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fold_pairs_kernel(AccTable pairs, bool rev, const EpEntry* __restrict__ ep,
                                                          uint32_t ep_mask, AccTable edges, Counters* ctr) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warps_per_grid = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row <= pairs.cap; row += warps_per_grid) {
-    uint64_t key = pairs.keys[row];
-    uint32_t h0 = pairs.hist[(size_t)row * ALZ_NB + lane];
-    uint32_t h1 = pairs.hist[(size_t)row * ALZ_NB + 32u + lane];
+  const uint32_t n_rows = min(*pairs.n_rows, pairs.max_rows);
+  // rows [0, n_rows) plus the sentinel row (index n_rows stands for row max_rows)
+  for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i <= n_rows; i += warps_per_grid) {
+    const uint32_t row = (i == n_rows) ? pairs.max_rows : i;
+    const uint32_t h0 = pairs.hist[(size_t)row * ALZ_NB + lane];
+    const uint32_t h1 = pairs.hist[(size_t)row * ALZ_NB + 32u + lane];
     uint64_t cnt = (uint64_t)h0 + h1;
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
-    if (row == pairs.cap) {
-      if (cnt == 0) continue;       // sentinel row unused
-      key = kEmptyKey;              // it stands for saddr = daddr = 255.255.255.255
-    } else if (key == kEmptyKey) {
-      continue;
-    }
+    if (cnt == 0) continue;  // unused sentinel row (allocated rows always hold >= 1 event)
+    const uint64_t key = (row == pairs.max_rows) ? kEmptyKey : pairs.row_key[row];
     uint64_t ekey = 0;
-    uint32_t eslot = 0xFFFFFFFFu;
-    bool ok = false;
+    uint32_t erow = kLostRow;
+    int ok = 0;
     if (lane == 0) {
-      ok = resolve_edge(ep, ep_mask, (uint32_t)(key >> 32), (uint32_t)key, rev, &ekey);
+      ok = resolve_edge(ep, ep_mask, (uint32_t)(key >> 32), (uint32_t)key, rev, &ekey) ? 1 : 0;
       if (ok) {
-        uint32_t ins = 0;
-        eslot = find_or_insert(edges, ekey, &ins);
-        if (ins) atomicAdd(&ctr->edges_inserted, 1ull);
-        if (eslot == 0xFFFFFFFFu) atomicAdd(&ctr->capacity_events, (unsigned long long)cnt);
+        erow = find_or_insert(edges, ekey);
+        if (erow >= kLostRow) atomicAdd(&ctr->capacity_events, (unsigned long long)cnt);
       } else {
-        atomicAdd(&ctr->src_unresolved, (unsigned long long)cnt);
+        atomicAdd(&ctr->src_unresolved, (unsigned long long)cnt);   // data.go:829-832
       }
     }
-    ok = __shfl_sync(0xFFFFFFFFu, ok ? 1 : 0, 0) != 0;
-    eslot = __shfl_sync(0xFFFFFFFFu, eslot, 0);
-    if (ok && eslot != 0xFFFFFFFFu) {
-      if (h0) atomicAdd(&edges.hist[(size_t)eslot * ALZ_NB + lane], h0);
-      if (h1) atomicAdd(&edges.hist[(size_t)eslot * ALZ_NB + 32u + lane], h1);
+    ok = __shfl_sync(0xFFFFFFFFu, ok, 0);
+    erow = __shfl_sync(0xFFFFFFFFu, erow, 0);
+    if (ok && erow < kLostRow) {
+      if (h0) atomicAdd(&edges.hist[(size_t)erow * ALZ_NB + lane], h0);
+      if (h1) atomicAdd(&edges.hist[(size_t)erow * ALZ_NB + 32u + lane], h1);
       if (lane == 0) {
-        atomicAdd((unsigned long long*)&edges.count[eslot], (unsigned long long)cnt);
-        atomicAdd((unsigned long long*)&edges.lat_sum[eslot], (unsigned long long)pairs.lat_sum[row]);
+        atomicAdd((unsigned long long*)&edges.count[erow], (unsigned long long)cnt);
+        atomicAdd((unsigned long long*)&edges.lat_sum[erow], (unsigned long long)pairs.lat_sum[row]);
         const uint64_t e = pairs.err5xx[row];
-        if (e) atomicAdd((unsigned long long*)&edges.err5xx[eslot], (unsigned long long)e);
+        if (e) atomicAdd((unsigned long long*)&edges.err5xx[erow], (unsigned long long)e);
       }
     }
-    // row back to empty
     pairs.hist[(size_t)row * ALZ_NB + lane] = 0u;
     pairs.hist[(size_t)row * ALZ_NB + 32u + lane] = 0u;
-    if (lane == 0) {
-      if (row != pairs.cap) pairs.keys[row] = kEmptyKey;
-      pairs.lat_sum[row] = 0ull;
-      pairs.err5xx[row] = 0ull;
-    }
+    if (lane == 0) { pairs.lat_sum[row] = 0ull; pairs.err5xx[row] = 0ull; }
   }
 }
 
 // ---------------------------------------------------------------------------
-// flush: live edges -> (key, row) list; after the sort, gather rows into the
-// caller-facing layout and return them to the empty state.
+// flush: rows [0, n) of the edge table are the live edges. iota -> sort by key
+// (alz_sort.cu) -> gather into the caller-facing layout, zeroing the rows.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) compact_edges_kernel(AccTable edges, uint64_t* out_keys, uint32_t* out_rows,
-                                                            Counters* ctr) {
+__global__ void __launch_bounds__(256) iota_kernel(uint32_t* out, uint32_t n) {
   const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t row = blockIdx.x * blockDim.x + threadIdx.x; row <= edges.cap; row += stride) {
-    const uint64_t key = edges.keys[row];
-    const bool live = (row == edges.cap) ? (edges.count[row] != 0ull) : (key != kEmptyKey);
-    const uint32_t m = __ballot_sync(__activemask(), live);
-    if (!live) continue;
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t leader = __ffs(m) - 1u;
-    unsigned long long base = 0;
-    if (lane == leader) base = atomicAdd(&ctr->n_live, (unsigned long long)__popc(m));
-    base = __shfl_sync(m, base, leader);
-    const uint32_t pos = (uint32_t)base + __popc(m & ((1u << lane) - 1u));
-    out_keys[pos] = key;
-    out_rows[pos] = row;
-  }
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = i;
 }
 
 __global__ void __launch_bounds__(256) gather_edges_kernel(AccTable edges, const uint64_t* __restrict__ keys,
@@ -184,10 +330,8 @@ __global__ void __launch_bounds__(256) gather_edges_kernel(AccTable edges, const
   for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_live; i += warps_per_grid) {
     const uint32_t row = rows[i];
     alz_edge_out* o = &out[i];
-    const uint32_t h0 = edges.hist[(size_t)row * ALZ_NB + lane];
-    const uint32_t h1 = edges.hist[(size_t)row * ALZ_NB + 32u + lane];
-    o->hist[lane] = h0;
-    o->hist[32u + lane] = h1;
+    o->hist[lane] = edges.hist[(size_t)row * ALZ_NB + lane];
+    o->hist[32u + lane] = edges.hist[(size_t)row * ALZ_NB + 32u + lane];
     if (lane == 0) {
       uint8_t ft, tt; uint32_t f, t;
       unpack_edge_key(keys[i], &ft, &f, &tt, &t);
@@ -201,10 +345,7 @@ __global__ void __launch_bounds__(256) gather_edges_kernel(AccTable edges, const
     if (reset) {
       edges.hist[(size_t)row * ALZ_NB + lane] = 0u;
       edges.hist[(size_t)row * ALZ_NB + 32u + lane] = 0u;
-      if (lane == 0) {
-        if (row != edges.cap) edges.keys[row] = kEmptyKey;
-        edges.count[row] = 0ull; edges.err5xx[row] = 0ull; edges.lat_sum[row] = 0ull;
-      }
+      if (lane == 0) { edges.count[row] = 0ull; edges.err5xx[row] = 0ull; edges.lat_sum[row] = 0ull; }
     }
   }
 }
@@ -258,9 +399,22 @@ __global__ void __launch_bounds__(256) synth_kernel(alz_synth_view v, uint64_t f
 static inline unsigned grid_for(int sms, int per_sm) { return (unsigned)(sms * per_sm); }
 
 void launch_ingest_pairs(const alz_l7_rec* recs, uint64_t n, const AccTable& fwd, const AccTable& rev,
-                         Counters* ctr, int sms, cudaStream_t s) {
+                         Counters* ctr, int sms, cudaStream_t s, int variant) {
   if (n == 0) return;
-  ingest_pairs_kernel<4><<<grid_for(sms, 8), 256, 0, s>>>(recs, n, fwd, rev, ctr);
+  if (variant == 0) {  // v1: global reductions only (kept for the ncu comparison)
+    ingest_pairs_kernel<4><<<grid_for(sms, 8), 256, 0, s>>>(recs, n, fwd, rev, ctr);
+    return;
+  }
+  constexpr int kThreads = 1024;
+  const uint32_t fwd_slots = 512, rev_slots = 64;
+  const size_t smem = (size_t)(fwd_slots + rev_slots) * (8 + kRowWords * 4);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(ingest_pairs_smem_kernel<2, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  ingest_pairs_smem_kernel<2, kThreads><<<grid_for(sms, 1), kThreads, smem, s>>>(recs, n, fwd, rev, ctr, fwd_slots,
+                                                                               rev_slots);
 }
 void launch_ingest_eager(const alz_l7_rec* recs, uint64_t n, const EpEntry* ep, uint32_t ep_mask,
                          const AccTable& edges, Counters* ctr, int sms, cudaStream_t s) {
@@ -271,9 +425,9 @@ void launch_fold_pairs(const AccTable& pairs, bool rev, const EpEntry* ep, uint3
                        const AccTable& edges, Counters* ctr, int sms, cudaStream_t s) {
   fold_pairs_kernel<<<grid_for(sms, 8), 256, 0, s>>>(pairs, rev, ep, ep_mask, edges, ctr);
 }
-void launch_compact_edges(const AccTable& edges, uint64_t* keys, uint32_t* rows, Counters* ctr, int sms,
-                          cudaStream_t s) {
-  compact_edges_kernel<<<grid_for(sms, 8), 256, 0, s>>>(edges, keys, rows, ctr);
+void launch_iota(uint32_t* out, uint32_t n, int sms, cudaStream_t s) {
+  if (n == 0) return;
+  iota_kernel<<<grid_for(sms, 4), 256, 0, s>>>(out, n);
 }
 void launch_gather_edges(const AccTable& edges, const uint64_t* keys, const uint32_t* rows, uint32_t n_live,
                          alz_edge_out* out, bool reset, int sms, cudaStream_t s) {

@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--events", type=int, default=100_000_000, help="events per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=8_000_000, help="events timed on the CPU arm")
     ap.add_argument("--eager", action="store_true", help="ALZ_CFG_EAGER_JOIN plan")
+    ap.add_argument("--no-smem-cache", action="store_true", help="ingest v1: global reductions only")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--gnn", action="store_true", help="also time the GNN pass per step (extra key)")
@@ -168,10 +169,11 @@ def main():
     S, N = args.services, args.events
     seed = 0xA1A20001
     topo = capi.Topo(S, seed=seed)
-    flags = abi.CFG_EAGER_JOIN if args.eager else 0
+    flags = (abi.CFG_EAGER_JOIN if args.eager else 0) | (abi.CFG_NO_SMEM_CACHE if args.no_smem_cache else 0)
     h = capi.Handle(device=local_rank, max_endpoints=4 * S, max_pairs=max(1 << 20, 16 * S),
                     max_batch=1 << 22, flags=flags)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # a real stream: handle 0 would mean "library's own"
+    torch.cuda.set_stream(stream)
     h.set_stream(stream.cuda_stream)
     h.load_tables(topo.pod_ip, topo.svc_ip)
 

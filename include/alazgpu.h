@@ -149,6 +149,9 @@ typedef struct alz_config {
                                    reducing per socket pair and joining the
                                    distinct pairs (default); same results */
 
+#define ALZ_CFG_NO_SMEM_CACHE 0x2u /* ingest without the per-CTA shared-memory cache of
+                                      hot socket pairs (profiling comparison only) */
+
 typedef struct alz_stats {
   uint64_t events_in;        /* records submitted */
   uint64_t rows_emitted;     /* rows the reference would have persisted */

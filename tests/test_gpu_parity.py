@@ -10,7 +10,7 @@ from helpers import load_branches, edges_equal, explain_diff
 
 pytestmark = pytest.mark.gpu
 
-PLANS = [0, abi.CFG_EAGER_JOIN]
+PLANS = [0, abi.CFG_EAGER_JOIN, abi.CFG_NO_SMEM_CACHE]
 
 
 def _oracle_for(topo, events, nthreads=4):
