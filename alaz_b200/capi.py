@@ -73,6 +73,7 @@ def load(rebuild=False):
         "alz_synth_fill": ([C.POINTER(abi.SynthTopo), u64, u64, vp], None),
         "alz_synth_dev_create": ([vp, C.POINTER(abi.SynthTopo), pp], i),
         "alz_synth_dev_fill": ([vp, vp, u64, u64, vp], i),
+        "alz_synth_dev_fill_owned": ([vp, vp, u64, u32, u32, vp, u64, C.POINTER(u64), C.POINTER(u64)], i),
         "alz_synth_dev_destroy": ([vp, vp], i),
     }
     for name, (args, res) in sig.items():

@@ -464,10 +464,7 @@ extern "C" int alz_fold(alz_handle* h) {
   return alz_internal_fold(h);
 }
 
-extern "C" uint32_t alz_owner_rank(uint32_t saddr, uint32_t nranks) {
-  if (nranks <= 1) return 0;
-  return (uint32_t)(((uint64_t)hash32(saddr ^ 0xA1A2B200u) * nranks) >> 32);
-}
+extern "C" uint32_t alz_owner_rank(uint32_t saddr, uint32_t nranks) { return owner_rank(saddr, nranks); }
 
 // ---- device memory helpers + synthetic stream (include/alazgpu_synth.h) ---------------------------
 extern "C" int alz_dev_alloc(alz_handle* h, size_t bytes, void** out) {
@@ -531,6 +528,29 @@ extern "C" int alz_synth_dev_fill(alz_handle* h, alz_synth_dev* d, uint64_t firs
   CK(cudaSetDevice(h->device));
   launch_synth(d->view, first, n, dev_out, h->sms, h->stream);
   CK(cudaGetLastError());
+  return ALZ_OK;
+}
+// First `want` events of the global stream (indices first, first+1, ...) that rank `rank` of `nranks` owns,
+// scanning in chunks; *n_scanned = how many global events were looked at. Order within dev_out is arbitrary.
+extern "C" int alz_synth_dev_fill_owned(alz_handle* h, alz_synth_dev* d, uint64_t first, uint32_t nranks, uint32_t rank,
+                                        alz_l7_rec* dev_out, uint64_t want, uint64_t* n_written, uint64_t* n_scanned) {
+  if (!h || !d || !dev_out || !n_written || !n_scanned || nranks == 0 || rank >= nranks) return ALZ_E_INVAL;
+  CK(cudaSetDevice(h->device));
+  unsigned long long* d_cnt = nullptr;
+  CK(cudaMalloc(&d_cnt, 8));
+  CK(cudaMemsetAsync(d_cnt, 0, 8, h->stream));
+  const uint64_t chunk = std::max<uint64_t>(1u << 20, want / 4);
+  unsigned long long got = 0;
+  uint64_t scanned = 0;
+  while (got < want && scanned < want * (uint64_t)nranks * 64ull) {
+    launch_synth_owned(d->view, first + scanned, chunk, nranks, rank, dev_out, want, d_cnt, h->sms, h->stream);
+    scanned += chunk;
+    CK(cudaMemcpyAsync(&got, d_cnt, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  cudaFree(d_cnt);
+  *n_written = got < want ? got : want;
+  *n_scanned = scanned;
   return ALZ_OK;
 }
 extern "C" int alz_synth_dev_destroy(alz_handle* h, alz_synth_dev* d) {

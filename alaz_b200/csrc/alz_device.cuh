@@ -37,6 +37,12 @@ __host__ __device__ __forceinline__ uint64_t hash64(uint64_t x) {
   return x;
 }
 
+// rank that owns an event (alz_owner_rank): a function of the source address only
+__host__ __device__ __forceinline__ uint32_t owner_rank(uint32_t saddr, uint32_t nranks) {
+  if (nranks <= 1u) return 0u;
+  return (uint32_t)(((uint64_t)hash32(saddr ^ 0xA1A2B200u) * nranks) >> 32);
+}
+
 // ---- packed edge key (docs/SPEC.md §3) -----------------------------------------
 // One end of every edge is the pod that setFromToV2 resolved from saddr.
 //   bit 63      rev: 0 = pod is From, 1 = pod is To (row was reversed)

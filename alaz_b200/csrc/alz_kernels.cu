@@ -108,35 +108,42 @@ __global__ void __launch_bounds__(256) ingest_pairs_kernel(const alz_l7_rec* __r
 // stride spreads equal buckets of different pairs over the banks.
 // ---------------------------------------------------------------------------
 constexpr int kRowWords = ALZ_NB + 3;
-struct SmemTab {
-  uint64_t* keys;   // [slots]
-  uint32_t* rows;   // [slots * kRowWords]
-  uint32_t* used;   // admitted pairs
-  uint32_t mask;    // slots - 1
-  uint32_t limit;   // admission stops here (load factor)
+// One shared array holds both private tables (forward pairs, then reversed pairs); a
+// table is selected by integer offsets so every access stays a shared-space LDS/ATOMS
+// (selecting between two structs of pointers made them generic loads: long-scoreboard
+// stalls on the probe, profiles/r1_v3_ingest_ncu.txt).
+struct SmemView {
+  uint64_t* keys;   // [fwd_slots + rev_slots]
+  uint32_t* rows;   // [(fwd_slots + rev_slots) * kRowWords]
+  uint32_t* used;   // [2] admitted pairs per table
+  uint32_t fwd_slots, rev_slots;
 };
 
-__device__ __forceinline__ int smem_find_or_admit(const SmemTab& t, uint64_t key) {
+// slot (global index into keys/rows) of `key` in table `rv`, admitting it while the table is open; -1 = not cached
+__device__ __forceinline__ int smem_find_or_admit(const SmemView& v, bool rv, uint64_t key) {
+  const uint32_t base = rv ? v.fwd_slots : 0u;
+  const uint32_t mask = (rv ? v.rev_slots : v.fwd_slots) - 1u;
+  const uint32_t limit = (mask + 1u) - ((mask + 1u) >> 2);
   if (key == kEmptyKey) return -1;
-  uint32_t slot = (uint32_t)(hash64(key) >> 32) & t.mask;
+  uint32_t slot = (uint32_t)(hash64(key) >> 32) & mask;
 #pragma unroll 1
   for (int p = 0; p < 6; ++p) {
-    const uint64_t k = t.keys[slot];
-    if (k == key) return (int)slot;
+    const uint64_t k = v.keys[base + slot];
+    if (k == key) return (int)(base + slot);
     if (k == kEmptyKey) {
-      if (*reinterpret_cast<volatile uint32_t*>(t.used) >= t.limit) return -1;
-      const uint64_t old = atomicCAS((unsigned long long*)&t.keys[slot], (unsigned long long)kEmptyKey,
+      if (*reinterpret_cast<volatile uint32_t*>(&v.used[rv ? 1 : 0]) >= limit) return -1;
+      const uint64_t old = atomicCAS((unsigned long long*)&v.keys[base + slot], (unsigned long long)kEmptyKey,
                                      (unsigned long long)key);
-      if (old == kEmptyKey) { atomicAdd(t.used, 1u); return (int)slot; }
-      if (old == key) return (int)slot;
+      if (old == kEmptyKey) { atomicAdd(&v.used[rv ? 1 : 0], 1u); return (int)(base + slot); }
+      if (old == key) return (int)(base + slot);
     }
-    slot = (slot + 1u) & t.mask;
+    slot = (slot + 1u) & mask;
   }
   return -1;
 }
 
-__device__ __forceinline__ void smem_accumulate(const SmemTab& t, int slot, uint32_t bucket, uint64_t dur, bool err) {
-  uint32_t* row = t.rows + (size_t)slot * kRowWords;
+__device__ __forceinline__ void smem_accumulate(const SmemView& v, int slot, uint32_t bucket, uint64_t dur, bool err) {
+  uint32_t* row = v.rows + (size_t)slot * kRowWords;
   atomicAdd(&row[bucket], 1u);
   const uint32_t lo = (uint32_t)dur;
   const uint32_t old = atomicAdd(&row[ALZ_NB], lo);
@@ -145,13 +152,15 @@ __device__ __forceinline__ void smem_accumulate(const SmemTab& t, int slot, uint
   if (err) atomicAdd(&row[ALZ_NB + 2], 1u);
 }
 
-// add one private table into the global one; a warp per row
-__device__ __forceinline__ void smem_drain(const SmemTab& s, const AccTable& g, uint32_t* lost) {
+// add the private slots [first, first + count) into global table g; a warp per slot
+__device__ __forceinline__ void smem_drain(const SmemView& v, uint32_t first, uint32_t count, const AccTable& g,
+                                           uint32_t* lost) {
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (uint32_t slot = warp; slot <= s.mask; slot += nwarps) {
-    const uint64_t key = s.keys[slot];
+  for (uint32_t i = warp; i < count; i += nwarps) {
+    const uint32_t slot = first + i;
+    const uint64_t key = v.keys[slot];
     if (key == kEmptyKey) continue;   // warp-uniform
-    const uint32_t* row = s.rows + (size_t)slot * kRowWords;
+    const uint32_t* row = v.rows + (size_t)slot * kRowWords;
     uint32_t grow = 0;
     if (lane == 0) grow = find_or_insert(g, key);
     grow = __shfl_sync(0xFFFFFFFFu, grow, 0);
@@ -178,16 +187,13 @@ __global__ void __launch_bounds__(THREADS, 1) ingest_pairs_smem_kernel(const alz
                                                                         uint32_t fwd_slots, uint32_t rev_slots) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ uint32_t s_used[2];
-  SmemTab sf, sr;
-  sf.keys = reinterpret_cast<uint64_t*>(smem_raw);
-  sr.keys = sf.keys + fwd_slots;
-  sf.rows = reinterpret_cast<uint32_t*>(sr.keys + rev_slots);
-  sr.rows = sf.rows + (size_t)fwd_slots * kRowWords;
-  sf.used = &s_used[0]; sr.used = &s_used[1];
-  sf.mask = fwd_slots - 1u; sr.mask = rev_slots - 1u;
-  sf.limit = fwd_slots - (fwd_slots >> 2); sr.limit = rev_slots - (rev_slots >> 2);
-  for (uint32_t i = threadIdx.x; i < fwd_slots + rev_slots; i += THREADS) sf.keys[i] = kEmptyKey;
-  for (uint32_t i = threadIdx.x; i < (fwd_slots + rev_slots) * kRowWords; i += THREADS) sf.rows[i] = 0u;
+  SmemView sv;
+  sv.keys = reinterpret_cast<uint64_t*>(smem_raw);
+  sv.rows = reinterpret_cast<uint32_t*>(smem_raw + (size_t)(fwd_slots + rev_slots) * 8);
+  sv.used = s_used;
+  sv.fwd_slots = fwd_slots; sv.rev_slots = rev_slots;
+  for (uint32_t i = threadIdx.x; i < fwd_slots + rev_slots; i += THREADS) sv.keys[i] = kEmptyKey;
+  for (uint32_t i = threadIdx.x; i < (fwd_slots + rev_slots) * kRowWords; i += THREADS) sv.rows[i] = 0u;
   if (threadIdx.x < 2) s_used[threadIdx.x] = 0u;
   __syncthreads();
 
@@ -209,9 +215,9 @@ __global__ void __launch_bounds__(THREADS, 1) ingest_pairs_smem_kernel(const alz
       not_request += (live[u] && !e.act) ? 1u : 0u;
       // 1) shared-memory table
       int ss = -1;
-      if (e.act) ss = smem_find_or_admit(e.rev ? sr : sf, e.key);
+      if (e.act) ss = smem_find_or_admit(sv, e.rev, e.key);
       __syncwarp();
-      if (ss >= 0) smem_accumulate(e.rev ? sr : sf, ss, e.bucket, e.dur, e.err);
+      if (ss >= 0) smem_accumulate(sv, ss, e.bucket, e.dur, e.err);
       // 2) the rest: global dictionary
       const bool g = e.act && ss < 0;
       uint32_t row = kLostRow;
@@ -224,8 +230,8 @@ __global__ void __launch_bounds__(THREADS, 1) ingest_pairs_smem_kernel(const alz
     }
   }
   __syncthreads();
-  smem_drain(sf, fwd, &lost);
-  smem_drain(sr, rev, &lost);
+  smem_drain(sv, 0u, fwd_slots, fwd, &lost);
+  smem_drain(sv, fwd_slots, rev_slots, rev, &lost);
   flush_thread_counters(ctr, not_request, 0u, lost);
 }
 
@@ -393,6 +399,30 @@ __global__ void __launch_bounds__(256) synth_kernel(alz_synth_view v, uint64_t f
   }
 }
 
+// events first..first+n of the global stream, keeping only those owned by `rank`
+// (alz_owner_rank: hash of saddr). Appends in arbitrary order; stops writing at cap.
+__global__ void __launch_bounds__(256) synth_owned_kernel(alz_synth_view v, uint64_t first, uint64_t n, uint32_t nranks,
+                                                          uint32_t rank, alz_l7_rec* __restrict__ out, uint64_t cap,
+                                                          unsigned long long* n_written) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+    const uint64_t i = base + lane;
+    alz_l7_rec r;
+    bool mine = false;
+    if (i < n) {
+      alz_synth_event(&v, first + i, &r);
+      mine = owner_rank(r.saddr, nranks) == rank;
+    }
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
+    if (m == 0u) continue;
+    unsigned long long pos = 0;
+    if (lane == 0) pos = atomicAdd(n_written, (unsigned long long)__popc(m));
+    pos = __shfl_sync(0xFFFFFFFFu, pos, 0) + __popc(m & ((1u << lane) - 1u));
+    if (mine && pos < cap) out[pos] = r;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
@@ -441,6 +471,11 @@ void launch_compact_raw(const uint8_t* raw, uint64_t n, alz_l7_rec* out, int sms
 void launch_synth(const alz_synth_view& v, uint64_t first, uint64_t n, alz_l7_rec* out, int sms, cudaStream_t s) {
   if (n == 0) return;
   synth_kernel<<<grid_for(sms, 8), 256, 0, s>>>(v, first, n, out);
+}
+void launch_synth_owned(const alz_synth_view& v, uint64_t first, uint64_t n, uint32_t nranks, uint32_t rank,
+                        alz_l7_rec* out, uint64_t cap, unsigned long long* n_written, int sms, cudaStream_t s) {
+  if (n == 0) return;
+  synth_owned_kernel<<<grid_for(sms, 8), 256, 0, s>>>(v, first, n, nranks, rank, out, cap, n_written);
 }
 
 }  // namespace alz

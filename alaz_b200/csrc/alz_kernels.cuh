@@ -15,8 +15,12 @@ void launch_gather_edges(const AccTable& edges, const uint64_t* keys, const uint
                          alz_edge_out* out, bool reset, int sms, cudaStream_t s);
 void launch_compact_raw(const uint8_t* raw, uint64_t n, alz_l7_rec* out, int sms, cudaStream_t s);
 void launch_synth(const alz_synth_view& v, uint64_t first, uint64_t n, alz_l7_rec* out, int sms, cudaStream_t s);
+void launch_synth_owned(const alz_synth_view& v, uint64_t first, uint64_t n, uint32_t nranks, uint32_t rank,
+                        alz_l7_rec* out, uint64_t cap, unsigned long long* n_written, int sms, cudaStream_t s);
 // radix sort of (edge key, row) pairs by key (alz_sort.cu)
 size_t sort_pairs_temp_bytes(uint32_t n);
 void sort_pairs(void* temp, size_t temp_bytes, const uint64_t* keys_in, uint64_t* keys_out,
                 const uint32_t* vals_in, uint32_t* vals_out, uint32_t n, cudaStream_t s);
+size_t scan_temp_bytes(uint32_t n);
+void exclusive_scan_u32(void* temp, size_t temp_bytes, const uint32_t* in, uint32_t* out, uint32_t n, cudaStream_t s);
 }  // namespace alz

@@ -1,7 +1,8 @@
-// alz_sort.cu — key/value radix sort used once per window flush to put the live
-// edges in canonical (packed-key) order. Off the per-event hot path; uses the
-// CUDA toolkit's CUB device radix sort.
+// alz_sort.cu — key/value radix sort and prefix scan used once per window flush
+// (canonical edge order, cross-rank key merge, CSR build). Off the per-event
+// hot path; uses the CUDA toolkit's CUB device primitives.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include "alz_kernels.cuh"
 
 namespace alz {
@@ -14,5 +15,13 @@ size_t sort_pairs_temp_bytes(uint32_t n) {
 void sort_pairs(void* temp, size_t temp_bytes, const uint64_t* keys_in, uint64_t* keys_out,
                 const uint32_t* vals_in, uint32_t* vals_out, uint32_t n, cudaStream_t s) {
   cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, (int)n, 0, 64, s);
+}
+size_t scan_temp_bytes(uint32_t n) {
+  size_t bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);
+  return bytes;
+}
+void exclusive_scan_u32(void* temp, size_t temp_bytes, const uint32_t* in, uint32_t* out, uint32_t n, cudaStream_t s) {
+  cub::DeviceScan::ExclusiveSum(temp, temp_bytes, in, out, (int)n, s);
 }
 }  // namespace alz

@@ -26,6 +26,8 @@ int alz_fold(alz_handle* h);
 typedef struct alz_synth_dev alz_synth_dev;
 int alz_synth_dev_create(alz_handle* h, const alz_synth_topo* topo, alz_synth_dev** out);
 int alz_synth_dev_fill(alz_handle* h, alz_synth_dev* d, uint64_t first, uint64_t n, alz_l7_rec* dev_out);
+int alz_synth_dev_fill_owned(alz_handle* h, alz_synth_dev* d, uint64_t first, uint32_t nranks, uint32_t rank,
+                             alz_l7_rec* dev_out, uint64_t want, uint64_t* n_written, uint64_t* n_scanned);
 int alz_synth_dev_destroy(alz_handle* h, alz_synth_dev* d);
 
 #ifdef __cplusplus
