@@ -438,11 +438,8 @@ void launch_ingest_pairs(const alz_l7_rec* recs, uint64_t n, const AccTable& fwd
   constexpr int kThreads = 1024;
   const uint32_t fwd_slots = 512, rev_slots = 64;
   const size_t smem = (size_t)(fwd_slots + rev_slots) * (8 + kRowWords * 4);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(ingest_pairs_smem_kernel<2, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
-  }
+  // per device (a process may drive several GPUs), so not cached in a static
+  cudaFuncSetAttribute(ingest_pairs_smem_kernel<2, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   ingest_pairs_smem_kernel<2, kThreads><<<grid_for(sms, 1), kThreads, smem, s>>>(recs, n, fwd, rev, ctr, fwd_slots,
                                                                                rev_slots);
 }

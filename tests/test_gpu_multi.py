@@ -37,6 +37,10 @@ def test_ranks_merge_to_the_single_rank_oracle(world):
     idbuf = (C.c_uint8 * abi.COMM_ID_BYTES)()
     assert L.alz_comm_unique_id(idbuf) == 0
     out, errs = [None] * world, []
+    # One process drives all GPUs here, so allocation phases and collective phases are fenced apart:
+    # a cudaMalloc on one thread can wait for the other device's NCCL kernel, which waits for this thread.
+    # (Production runs one process per GPU, where this cannot happen.)
+    bar = threading.Barrier(world, timeout=120)
 
     def run(rank):
         try:
@@ -46,9 +50,12 @@ def test_ranks_merge_to_the_single_rank_oracle(world):
             mine = ev[owner == rank]
             h.submit(mine[: len(mine) // 2])
             h.submit(mine[len(mine) // 2:])
+            h.sync()
+            bar.wait()
             w1 = h.flush()
             w2 = h.flush()           # empty second window on every rank
             out[rank] = (w1, w2, h.stats())
+            bar.wait()
             h.close()
         except Exception as e:   # noqa: BLE001
             errs.append((rank, repr(e)))
