@@ -22,7 +22,7 @@ EXPORTS = [
     "alz_create", "alz_destroy", "alz_strerror", "alz_last_cuda_error", "alz_set_stream", "alz_sync",
     "alz_table_upsert", "alz_table_erase", "alz_table_commit", "alz_submit_l7", "alz_submit_l7_device",
     "alz_submit_l7_raw", "alz_window_flush", "alz_window_flush_device", "alz_get_stats", "alz_gnn_score",
-    "alz_edge_quantiles", "alz_submit_tcp", "alz_sock_lookup", "alz_comm_unique_id", "alz_comm_init",
+    "alz_gnn_score_device", "alz_edge_quantiles", "alz_submit_tcp", "alz_sock_lookup", "alz_comm_unique_id", "alz_comm_init",
     "alz_owner_rank",
 ]
 
@@ -55,6 +55,8 @@ def load(rebuild=False):
         "alz_window_flush_device": ([vp, pp, C.POINTER(sz)], i),
         "alz_get_stats": ([vp, C.POINTER(abi.Stats)], i),
         "alz_gnn_score": ([vp, vp, sz, C.POINTER(sz)], i),
+        "alz_gnn_score_device": ([vp, pp, C.POINTER(sz)], i),
+        "alz_gnn_nodes": ([vp, vp, vp, sz, C.POINTER(sz)], i),
         "alz_edge_quantiles": ([vp, vp, sz, vp], i),
         "alz_submit_tcp": ([vp, vp, sz], i),
         "alz_sock_lookup": ([vp, vp, sz, vp], i),

@@ -1,0 +1,413 @@
+// alz_gnn.cu — GNN anomaly pass over the flushed service graph (docs/SPEC.md §6;
+// not in the reference: north_star's extension). 2-layer GraphSAGE-mean, d = 64,
+// fixed seeded weights, per-edge score.
+//
+//   nodes   : 2 node keys per edge -> sort -> unique (ascending (kind,value))
+//   stats   : per-node in/out count, 5xx, latency sum, degree  (u64 atomics: exact,
+//             order-independent, so the float features are deterministic)
+//   CSR     : in-edges grouped by destination (stable sort by dst index, row
+//             offsets = exclusive scan of the in-degrees)
+//   layer   : warp per node: mean of the in-neighbours' rows (coalesced 256-B
+//             row reads) -> [h_v || m_v] (128) x W (128 x 64) + b, ReLU
+//   score   : sigma(a . [h2_u || h2_v || e_uv] + c), e_uv from the edge's
+//             integers and float64 histogram quantiles
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "alz_handle.h"
+
+using namespace alz;
+
+namespace {
+
+constexpr int D = 64;
+constexpr uint64_t kGnnSeed = 0xA1A26E6Eull;
+
+// ---- weights: pure integer -> double -> float, restated in tests/gnn_ref.py -----
+inline double unit(uint64_t idx) {
+  const uint64_t r = alz_splitmix64(kGnnSeed + idx);
+  return (double)(r >> 11) * (1.0 / 9007199254740992.0) * 2.0 - 1.0;   // [-1, 1)
+}
+
+struct Weights {
+  std::vector<float> W[2], b[2], a;   // W[l][k*64 + j], k in [0,128)
+  float c;
+};
+Weights make_weights() {
+  Weights w;
+  const double sw = 1.0 / std::sqrt(128.0), sa = 1.0 / std::sqrt(132.0);
+  uint64_t idx = 0;
+  for (int l = 0; l < 2; ++l) {
+    w.W[l].resize(128 * D);
+    w.b[l].resize(D);
+    for (int k = 0; k < 128; ++k)
+      for (int j = 0; j < D; ++j) w.W[l][k * D + j] = (float)(unit(idx++) * sw);
+    for (int j = 0; j < D; ++j) w.b[l][j] = (float)(unit(idx++) * 0.01);
+  }
+  w.a.resize(132);
+  for (int k = 0; k < 132; ++k) w.a[k] = (float)(unit(idx++) * sa);
+  w.c = 0.0f;
+  return w;
+}
+
+__device__ __forceinline__ uint64_t node_key(uint32_t kind, uint32_t value) { return ((uint64_t)kind << 32) | value; }
+
+__global__ void edge_node_keys_kernel(const alz_edge_out* __restrict__ e, uint32_t n_e, uint64_t* __restrict__ out) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_e; i += stride) {
+    out[2 * i] = node_key(e[i].from_type, e[i].from);
+    out[2 * i + 1] = node_key(e[i].to_type, e[i].to);
+  }
+}
+__global__ void flag_heads_kernel(const uint64_t* __restrict__ sorted, uint32_t n, uint32_t* __restrict__ flags) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    flags[i] = (i == 0 || sorted[i - 1] != sorted[i]) ? 1u : 0u;
+}
+__global__ void scatter_heads_kernel(const uint64_t* __restrict__ sorted, const uint32_t* __restrict__ flags,
+                                     const uint32_t* __restrict__ pos, uint32_t n, uint64_t* __restrict__ out) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    if (flags[i]) out[pos[i]] = sorted[i];
+}
+__device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t* __restrict__ a, uint32_t n, uint64_t k) {
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (a[mid] < k) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
+// per node: [out_count, in_count, out_err, in_err, out_lat, in_lat, out_deg, in_deg]
+__global__ void edge_stats_kernel(const alz_edge_out* __restrict__ e, uint32_t n_e, const uint64_t* __restrict__ nodes,
+                                  uint32_t n_v, uint32_t* __restrict__ src_idx, uint64_t* __restrict__ dst_key,
+                                  unsigned long long* __restrict__ stats, uint32_t* __restrict__ in_deg) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_e; i += stride) {
+    const uint32_t u = lower_bound_u64(nodes, n_v, node_key(e[i].from_type, e[i].from));
+    const uint32_t v = lower_bound_u64(nodes, n_v, node_key(e[i].to_type, e[i].to));
+    src_idx[i] = u;
+    dst_key[i] = v;
+    atomicAdd(&stats[(size_t)u * 8 + 0], (unsigned long long)e[i].count);
+    atomicAdd(&stats[(size_t)v * 8 + 1], (unsigned long long)e[i].count);
+    if (e[i].err5xx) {
+      atomicAdd(&stats[(size_t)u * 8 + 2], (unsigned long long)e[i].err5xx);
+      atomicAdd(&stats[(size_t)v * 8 + 3], (unsigned long long)e[i].err5xx);
+    }
+    atomicAdd(&stats[(size_t)u * 8 + 4], (unsigned long long)e[i].lat_sum_ns);
+    atomicAdd(&stats[(size_t)v * 8 + 5], (unsigned long long)e[i].lat_sum_ns);
+    atomicAdd(&stats[(size_t)u * 8 + 6], 1ull);
+    atomicAdd(&stats[(size_t)v * 8 + 7], 1ull);
+    atomicAdd(&in_deg[v], 1u);
+  }
+}
+
+__global__ void csr_cols_kernel(const uint32_t* __restrict__ sorted_edge, const uint32_t* __restrict__ src_idx,
+                                uint32_t n_e, uint32_t* __restrict__ col) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_e; i += stride) col[i] = src_idx[sorted_edge[i]];
+}
+
+__device__ __forceinline__ double ratio(uint64_t a, uint64_t b) { return b ? (double)a / (double)b : 0.0; }
+
+__global__ void node_features_kernel(const uint64_t* __restrict__ nodes, const unsigned long long* __restrict__ stats,
+                                     uint32_t n_v, float* __restrict__ h0) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n_v; v += stride) {
+    const unsigned long long* s = stats + (size_t)v * 8;
+    float* o = h0 + (size_t)v * D;
+    const uint32_t kind = (uint32_t)(nodes[v] >> 32);
+    float f[12];
+    f[0] = (float)log1p((double)s[0]);
+    f[1] = (float)log1p((double)s[1]);
+    f[2] = (float)ratio(s[2], s[0]);
+    f[3] = (float)ratio(s[3], s[1]);
+    f[4] = (float)log1p(ratio(s[4], s[0]));
+    f[5] = (float)log1p(ratio(s[5], s[1]));
+    f[6] = (float)log1p((double)s[6]);
+    f[7] = (float)log1p((double)s[7]);
+    f[8] = kind == ALZ_NODE_POD ? 1.f : 0.f;
+    f[9] = kind == ALZ_NODE_SVC ? 1.f : 0.f;
+    f[10] = kind == ALZ_NODE_OUTBOUND ? 1.f : 0.f;
+    f[11] = 1.f;
+    for (int j = 0; j < D; ++j) o[j] = j < 12 ? f[j] : 0.f;
+  }
+}
+
+// one GraphSAGE-mean layer, FP32 SIMT: warp per node, W (32 KB) in shared memory
+__global__ void __launch_bounds__(256) sage_layer_kernel(const float* __restrict__ h_in, float* __restrict__ h_out,
+                                                         const uint32_t* __restrict__ rowptr,
+                                                         const uint32_t* __restrict__ col, const float* __restrict__ W,
+                                                         const float* __restrict__ b, uint32_t n_v) {
+  __shared__ float sW[128 * D];
+  __shared__ float sz[8][128];
+  for (int i = threadIdx.x; i < 128 * D; i += blockDim.x) sW[i] = W[i];
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < n_v; v += warps_per_grid) {
+    const uint32_t beg = rowptr[v], end = rowptr[v + 1];
+    float m0 = 0.f, m1 = 0.f;
+    for (uint32_t p = beg; p < end; ++p) {          // CSR order: deterministic sum
+      const float* hu = h_in + (size_t)col[p] * D;
+      m0 += hu[lane];
+      m1 += hu[32 + lane];
+    }
+    const float inv = end > beg ? 1.0f / (float)(end - beg) : 0.f;
+    const float* hv = h_in + (size_t)v * D;
+    sz[warp][lane] = hv[lane];
+    sz[warp][32 + lane] = hv[32 + lane];
+    sz[warp][64 + lane] = m0 * inv;
+    sz[warp][96 + lane] = m1 * inv;
+    __syncwarp();
+    float a0 = b[lane], a1 = b[32 + lane];
+#pragma unroll 8
+    for (int k = 0; k < 128; ++k) {
+      const float z = sz[warp][k];
+      a0 = fmaf(z, sW[k * D + lane], a0);
+      a1 = fmaf(z, sW[k * D + 32 + lane], a1);
+    }
+    h_out[(size_t)v * D + lane] = fmaxf(a0, 0.f);
+    h_out[(size_t)v * D + 32 + lane] = fmaxf(a1, 0.f);
+    __syncwarp();
+  }
+}
+
+// docs/SPEC.md §4/§5 on the device, float64
+__device__ __forceinline__ double bucket_lo(uint32_t b) {
+  if (b == 0) return 0.0;
+  const double base = (double)(1ull << (8 + b / 2));
+  return (b & 1u) ? base * 1.5 : base;
+}
+__device__ __forceinline__ double bucket_hi(uint32_t b) { return b == ALZ_NB - 1 ? (double)(1ull << 40) : bucket_lo(b + 1); }
+__device__ double hist_quantile(const uint32_t* __restrict__ hist, uint64_t total, double q) {
+  if (total == 0) return 0.0;
+  const double target = q * (double)total;
+  double cum = 0.0;
+  for (uint32_t b = 0; b < ALZ_NB; ++b) {
+    const double c = (double)hist[b];
+    if (c > 0.0 && cum + c >= target) {
+      double f = (target - cum) / c;
+      if (f < 0.0) f = 0.0;
+      return bucket_lo(b) + f * (bucket_hi(b) - bucket_lo(b));
+    }
+    cum += c;
+  }
+  return bucket_hi(ALZ_NB - 1);
+}
+
+__global__ void __launch_bounds__(256) edge_score_kernel(const alz_edge_out* __restrict__ e, uint32_t n_e,
+                                                         const uint32_t* __restrict__ src_idx,
+                                                         const uint64_t* __restrict__ dst_key,
+                                                         const float* __restrict__ h2, const float* __restrict__ a,
+                                                         float c, float* __restrict__ scores) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_e; i += warps_per_grid) {
+    const float* hu = h2 + (size_t)src_idx[i] * D;
+    const float* hv = h2 + (size_t)dst_key[i] * D;
+    float acc = hu[lane] * a[lane] + hu[32 + lane] * a[32 + lane] + hv[lane] * a[64 + lane] +
+                hv[32 + lane] * a[96 + lane];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    if (lane == 0) {
+      uint64_t total = 0;
+      for (int b = 0; b < ALZ_NB; ++b) total += e[i].hist[b];
+      const float f0 = (float)log1p((double)e[i].count);
+      const float f1 = (float)ratio(e[i].err5xx, e[i].count);
+      const float f2 = (float)log1p(hist_quantile(e[i].hist, total, 0.5));
+      const float f3 = (float)log1p(hist_quantile(e[i].hist, total, 0.99));
+      const float z = acc + f0 * a[128] + f1 * a[129] + f2 * a[130] + f3 * a[131] + c;
+      scores[i] = 1.0f / (1.0f + expf(-z));
+    }
+  }
+}
+
+}  // namespace
+
+struct alz_gnn_state {
+  uint32_t cap_e = 0, cap_v = 0;
+  uint64_t *d_nk = nullptr, *d_nk_sorted = nullptr, *d_nodes = nullptr, *d_dst_key = nullptr, *d_dst_sorted = nullptr;
+  uint32_t *d_flags = nullptr, *d_pos = nullptr, *d_iota = nullptr, *d_vals = nullptr, *d_src_idx = nullptr;
+  uint32_t *d_in_deg = nullptr, *d_rowptr = nullptr, *d_col = nullptr, *d_sorted_edge = nullptr;
+  unsigned long long* d_stats = nullptr;
+  float *d_h[3] = {nullptr, nullptr, nullptr}, *d_W[2] = {nullptr, nullptr}, *d_b[2] = {nullptr, nullptr};
+  float *d_a = nullptr, *d_scores = nullptr;
+  float c = 0.f;
+  void* d_tmp = nullptr;
+  size_t tmp_bytes = 0;
+  uint32_t n_v = 0, n_e = 0;
+};
+
+#define CK(expr)                                                                       \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      h->last_err = std::string(#expr) + ": " + cudaGetErrorString(_e);                \
+      return ALZ_E_CUDA;                                                               \
+    }                                                                                  \
+  } while (0)
+
+static int gnn_init(alz_handle* h) {
+  if (h->gnn) return ALZ_OK;
+  alz_gnn_state* g = new alz_gnn_state();
+  h->gnn = g;
+  g->cap_e = h->cfg.max_edges;
+  g->cap_v = 2 * h->cfg.max_edges;
+  const size_t E = g->cap_e, V = g->cap_v;
+  CK(cudaMalloc(&g->d_nk, V * 8));
+  CK(cudaMalloc(&g->d_nk_sorted, V * 8));
+  CK(cudaMalloc(&g->d_nodes, V * 8));
+  CK(cudaMalloc(&g->d_dst_key, E * 8));
+  CK(cudaMalloc(&g->d_dst_sorted, E * 8));
+  CK(cudaMalloc(&g->d_flags, V * 4));
+  CK(cudaMalloc(&g->d_pos, V * 4));
+  CK(cudaMalloc(&g->d_iota, V * 4));
+  CK(cudaMalloc(&g->d_vals, V * 4));
+  CK(cudaMalloc(&g->d_src_idx, E * 4));
+  CK(cudaMalloc(&g->d_in_deg, (V + 1) * 4));
+  CK(cudaMalloc(&g->d_rowptr, (V + 1) * 4));
+  CK(cudaMalloc(&g->d_col, E * 4));
+  CK(cudaMalloc(&g->d_sorted_edge, E * 4));
+  CK(cudaMalloc(&g->d_stats, V * 8 * 8));
+  for (int i = 0; i < 3; ++i) CK(cudaMalloc(&g->d_h[i], V * D * 4));
+  CK(cudaMalloc(&g->d_scores, E * 4));
+  g->tmp_bytes = std::max(sort_pairs_temp_bytes((uint32_t)V), scan_temp_bytes((uint32_t)V + 1));
+  CK(cudaMalloc(&g->d_tmp, g->tmp_bytes));
+  const Weights w = make_weights();
+  for (int l = 0; l < 2; ++l) {
+    CK(cudaMalloc(&g->d_W[l], 128 * D * 4));
+    CK(cudaMalloc(&g->d_b[l], D * 4));
+    CK(cudaMemcpy(g->d_W[l], w.W[l].data(), 128 * D * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(g->d_b[l], w.b[l].data(), D * 4, cudaMemcpyHostToDevice));
+  }
+  CK(cudaMalloc(&g->d_a, 132 * 4));
+  CK(cudaMemcpy(g->d_a, w.a.data(), 132 * 4, cudaMemcpyHostToDevice));
+  g->c = w.c;
+  return ALZ_OK;
+}
+
+void alz_internal_free_gnn(alz_handle* h) {
+  alz_gnn_state* g = h->gnn;
+  if (!g) return;
+  cudaFree(g->d_nk); cudaFree(g->d_nk_sorted); cudaFree(g->d_nodes); cudaFree(g->d_dst_key); cudaFree(g->d_dst_sorted);
+  cudaFree(g->d_flags); cudaFree(g->d_pos); cudaFree(g->d_iota); cudaFree(g->d_vals); cudaFree(g->d_src_idx);
+  cudaFree(g->d_in_deg); cudaFree(g->d_rowptr); cudaFree(g->d_col); cudaFree(g->d_sorted_edge); cudaFree(g->d_stats);
+  for (int i = 0; i < 3; ++i) cudaFree(g->d_h[i]);
+  for (int l = 0; l < 2; ++l) { cudaFree(g->d_W[l]); cudaFree(g->d_b[l]); }
+  cudaFree(g->d_a); cudaFree(g->d_scores); cudaFree(g->d_tmp);
+  delete g;
+  h->gnn = nullptr;
+}
+
+// CSR build + 2 layers + scoring over the last flushed window (h->d_out)
+static int gnn_run(alz_handle* h) {
+  int rc = gnn_init(h);
+  if (rc != ALZ_OK) return rc;
+  alz_gnn_state* g = h->gnn;
+  cudaStream_t s = h->stream;
+  const uint32_t n_e = h->last_n_edges;
+  g->n_e = n_e;
+  g->n_v = 0;
+  if (n_e == 0) return ALZ_OK;
+  if (n_e > g->cap_e) return ALZ_E_CAPACITY;
+  const unsigned grid = (unsigned)h->sms * 4;
+  const uint32_t n2 = 2 * n_e;
+  // nodes
+  edge_node_keys_kernel<<<grid, 256, 0, s>>>(h->d_out, n_e, g->d_nk);
+  launch_iota(g->d_iota, n2, h->sms, s);
+  sort_pairs(g->d_tmp, g->tmp_bytes, g->d_nk, g->d_nk_sorted, g->d_iota, g->d_vals, n2, s);
+  flag_heads_kernel<<<grid, 256, 0, s>>>(g->d_nk_sorted, n2, g->d_flags);
+  exclusive_scan_u32(g->d_tmp, g->tmp_bytes, g->d_flags, g->d_pos, n2, s);
+  scatter_heads_kernel<<<grid, 256, 0, s>>>(g->d_nk_sorted, g->d_flags, g->d_pos, n2, g->d_nodes);
+  uint32_t last[2];
+  CK(cudaMemcpyAsync(&last[0], g->d_pos + (n2 - 1), 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&last[1], g->d_flags + (n2 - 1), 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  const uint32_t n_v = last[0] + last[1];
+  g->n_v = n_v;
+  // stats + CSR by destination
+  CK(cudaMemsetAsync(g->d_stats, 0, (size_t)n_v * 64, s));
+  CK(cudaMemsetAsync(g->d_in_deg, 0, ((size_t)n_v + 1) * 4, s));
+  edge_stats_kernel<<<grid, 256, 0, s>>>(h->d_out, n_e, g->d_nodes, n_v, g->d_src_idx, g->d_dst_key, g->d_stats,
+                                         g->d_in_deg);
+  launch_iota(g->d_iota, n_e, h->sms, s);
+  sort_pairs(g->d_tmp, g->tmp_bytes, g->d_dst_key, g->d_dst_sorted, g->d_iota, g->d_sorted_edge, n_e, s);
+  csr_cols_kernel<<<grid, 256, 0, s>>>(g->d_sorted_edge, g->d_src_idx, n_e, g->d_col);
+  exclusive_scan_u32(g->d_tmp, g->tmp_bytes, g->d_in_deg, g->d_rowptr, n_v + 1, s);
+  // features, layers, scores
+  node_features_kernel<<<grid, 256, 0, s>>>(g->d_nodes, g->d_stats, n_v, g->d_h[0]);
+  sage_layer_kernel<<<grid, 256, 0, s>>>(g->d_h[0], g->d_h[1], g->d_rowptr, g->d_col, g->d_W[0], g->d_b[0], n_v);
+  sage_layer_kernel<<<grid, 256, 0, s>>>(g->d_h[1], g->d_h[2], g->d_rowptr, g->d_col, g->d_W[1], g->d_b[1], n_v);
+  edge_score_kernel<<<grid, 256, 0, s>>>(h->d_out, n_e, g->d_src_idx, g->d_dst_key, g->d_h[2], g->d_a, g->c,
+                                         g->d_scores);
+  CK(cudaGetLastError());
+  return ALZ_OK;
+}
+
+extern "C" int alz_gnn_score_device(alz_handle* h, const float** dev_scores, size_t* n_out) {
+  if (!h || !n_out) return ALZ_E_INVAL;
+  CK(cudaSetDevice(h->device));
+  int rc = gnn_run(h);
+  *n_out = h->gnn ? h->gnn->n_e : 0;
+  if (rc != ALZ_OK) return rc;
+  if (dev_scores) *dev_scores = h->gnn->d_scores;
+  return ALZ_OK;
+}
+
+extern "C" int alz_gnn_score(alz_handle* h, float* edge_scores, size_t cap, size_t* n_out) {
+  if (!h || !n_out || (!edge_scores && cap)) return ALZ_E_INVAL;
+  const float* d = nullptr;
+  int rc = alz_gnn_score_device(h, &d, n_out);
+  if (rc != ALZ_OK) return rc;
+  if (*n_out > cap) return ALZ_E_CAPACITY;
+  if (*n_out) CK(cudaMemcpyAsync(edge_scores, d, *n_out * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return ALZ_OK;
+}
+
+// debug/test: node keys ((kind << 32) | value, ascending) and the layer-2 embeddings of the last alz_gnn_score
+extern "C" int alz_gnn_nodes(alz_handle* h, uint64_t* node_keys, float* h2, size_t cap, size_t* n_out) {
+  if (!h || !n_out) return ALZ_E_INVAL;
+  if (!h->gnn) return ALZ_E_STATE;
+  CK(cudaSetDevice(h->device));
+  *n_out = h->gnn->n_v;
+  if (h->gnn->n_v > cap) return ALZ_E_CAPACITY;
+  if (h->gnn->n_v) {
+    if (node_keys) CK(cudaMemcpyAsync(node_keys, h->gnn->d_nodes, (size_t)h->gnn->n_v * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (h2) CK(cudaMemcpyAsync(h2, h->gnn->d_h[2], (size_t)h->gnn->n_v * D * 4, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return ALZ_OK;
+}
+
+// SPEC §5 on the host: the same interpolation, float64
+extern "C" int alz_edge_quantiles(const alz_edge_out* e, const double* qs, size_t nq, double* out_ns) {
+  if (!e || (!qs && nq) || (!out_ns && nq)) return ALZ_E_INVAL;
+  uint64_t total = 0;
+  for (int b = 0; b < ALZ_NB; ++b) total += e->hist[b];
+  auto lo = [](uint32_t b) -> double {
+    if (b == 0) return 0.0;
+    const double base = (double)(1ull << (8 + b / 2));
+    return (b & 1u) ? base * 1.5 : base;
+  };
+  auto hi = [&](uint32_t b) -> double { return b == ALZ_NB - 1 ? (double)(1ull << 40) : lo(b + 1); };
+  for (size_t i = 0; i < nq; ++i) {
+    double r = total ? hi(ALZ_NB - 1) : 0.0;
+    if (total) {
+      const double target = qs[i] * (double)total;
+      double cum = 0.0;
+      for (uint32_t b = 0; b < ALZ_NB; ++b) {
+        const double c = (double)e->hist[b];
+        if (c > 0.0 && cum + c >= target) {
+          double f = (target - cum) / c;
+          if (f < 0.0) f = 0.0;
+          r = lo(b) + f * (hi(b) - lo(b));
+          break;
+        }
+        cum += c;
+      }
+    }
+    out_ns[i] = r;
+  }
+  return ALZ_OK;
+}

@@ -212,6 +212,8 @@ int alz_get_stats(alz_handle* h, alz_stats* out);
 
 /* ---- GNN anomaly pass over the last flushed window (docs/SPEC.md §6) -------- */
 int alz_gnn_score(alz_handle* h, float* edge_scores, size_t cap, size_t* n_out);
+/* same, scores left on the device (valid until the next call on this handle) */
+int alz_gnn_score_device(alz_handle* h, const float** dev_scores, size_t* n_out);
 /* quantiles from the histogram, the same float64 interpolation the scores use */
 int alz_edge_quantiles(const alz_edge_out* e, const double* qs, size_t nq, double* out_ns);
 

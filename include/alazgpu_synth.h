@@ -23,6 +23,9 @@ int alz_memcpy_d2h(alz_handle* h, void* dst, const void* src, size_t bytes);
 /* fold pending socket pairs into the edge accumulators now (flush does it anyway) */
 int alz_fold(alz_handle* h);
 
+/* test/debug: node keys ((kind << 32) | value, ascending) and layer-2 embeddings [n x 64] of the last GNN pass */
+int alz_gnn_nodes(alz_handle* h, uint64_t* node_keys, float* h2, size_t cap, size_t* n_out);
+
 typedef struct alz_synth_dev alz_synth_dev;
 int alz_synth_dev_create(alz_handle* h, const alz_synth_topo* topo, alz_synth_dev** out);
 int alz_synth_dev_fill(alz_handle* h, alz_synth_dev* d, uint64_t first, uint64_t n, alz_l7_rec* dev_out);
