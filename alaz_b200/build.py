@@ -9,7 +9,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libalazgpu.so")
 
 # alz_ext_stubs.cu only provides the entry points whose real file is absent
-SOURCES = ["alz_api.cu", "alz_kernels.cu", "alz_sort.cu", "alz_comm.cu", "alz_gnn.cu", "alz_sock.cu",
+SOURCES = ["alz_api.cu", "alz_kernels.cu", "alz_ingest.cu", "alz_sort.cu", "alz_comm.cu", "alz_gnn.cu", "alz_sock.cu",
            "alz_ext_stubs.cu"]
 EXTRA = [os.path.join(HERE, "synth", "alz_synth_topo.c")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -56,7 +56,9 @@ static int alloc_table(alz_handle* h, AccTable* t, uint32_t max_rows, uint32_t* 
   CK(cudaMalloc(&t->lat_sum, rows * 8));
   CK(cudaMalloc(&t->err5xx, rows * 8));
   t->count = nullptr;
+  t->row_cnt = nullptr;
   if (with_count) CK(cudaMalloc(&t->count, rows * 8));
+  else { CK(cudaMalloc(&t->row_cnt, rows * 4)); CK(cudaMemsetAsync(t->row_cnt, 0, rows * 4, h->stream)); }
   CK(cudaMalloc(&t->hist, rows * ALZ_NB * 4));
   CK(cudaMemsetAsync(t->dict, 0xFF, (size_t)dict_cap * sizeof(DictEnt), h->stream));
   CK(cudaMemsetAsync(t->lat_sum, 0, rows * 8, h->stream));
@@ -67,6 +69,7 @@ static int alloc_table(alz_handle* h, AccTable* t, uint32_t max_rows, uint32_t* 
 }
 static void free_table(AccTable* t) {
   cudaFree(t->dict); cudaFree(t->row_key); cudaFree(t->lat_sum); cudaFree(t->err5xx); cudaFree(t->count);
+  cudaFree(t->row_cnt);
   cudaFree(t->hist);
   memset(t, 0, sizeof(*t));
 }
@@ -134,6 +137,8 @@ extern "C" int alz_create(const alz_config* cfg, alz_handle** out) {
   CKC(cudaMemsetAsync(h->d_ep, 0, (size_t)h->ep_cap * sizeof(EpEntry), h->stream));
   CKC(cudaMalloc(&h->d_ctr, sizeof(Counters)));
   CKC(cudaMemsetAsync(h->d_ctr, 0, sizeof(Counters), h->stream));
+  CKC(cudaMalloc(&h->d_hot, 2 * sizeof(HotState)));
+  CKC(cudaMemsetAsync(h->d_hot, 0, 2 * sizeof(HotState), h->stream));
   int rc;
   if (!(h->cfg.flags & ALZ_CFG_EAGER_JOIN)) {
     if ((rc = alloc_table(h, &h->pairs_fwd, h->cfg.max_pairs, &h->d_ctr->fwd_rows, false)) != ALZ_OK) return fail(rc);
@@ -161,7 +166,7 @@ extern "C" int alz_destroy(alz_handle* h) {
   cudaDeviceSynchronize();
   alz_internal_free_extensions(h);
   free_table(&h->pairs_fwd); free_table(&h->pairs_rev); free_table(&h->edges);
-  cudaFree(h->d_ep); cudaFree(h->d_ctr);
+  cudaFree(h->d_ep); cudaFree(h->d_ctr); cudaFree(h->d_hot);
   if (h->h_ctr) cudaFreeHost(h->h_ctr);
   for (int b = 0; b < 2; ++b) {
     cudaFree(h->d_keys[b]); cudaFree(h->d_rows[b]);
@@ -238,8 +243,14 @@ extern "C" int alz_table_erase(alz_handle* h, int table, uint32_t ip) {
 int alz_internal_fold(alz_handle* h) {
   if (h->cfg.flags & ALZ_CFG_EAGER_JOIN) return ALZ_OK;
   if (h->pending_since_fold == 0) return ALZ_OK;
-  launch_fold_pairs(h->pairs_fwd, false, h->d_ep, h->ep_cap - 1, h->edges, h->d_ctr, h->sms, h->stream);
-  launch_fold_pairs(h->pairs_rev, true, h->d_ep, h->ep_cap - 1, h->edges, h->d_ctr, h->sms, h->stream);
+  // the join on distinct pairs; it also leaves per-pair counts behind, from which the next
+  // ingest launches learn which pairs are hot (alz_ingest.cu)
+  CK(cudaMemsetAsync(h->d_hot[0].bins, 0, sizeof(h->d_hot[0].bins), h->stream));
+  CK(cudaMemsetAsync(h->d_hot[1].bins, 0, sizeof(h->d_hot[1].bins), h->stream));
+  launch_fold_pairs(h->pairs_fwd, false, h->d_ep, h->ep_cap - 1, h->edges, h->d_ctr, h->d_hot[0].bins, h->sms, h->stream);
+  launch_fold_pairs(h->pairs_rev, true, h->d_ep, h->ep_cap - 1, h->edges, h->d_ctr, h->d_hot[1].bins, h->sms, h->stream);
+  launch_hot_select(h->pairs_fwd, &h->d_hot[0], false, h->sms, h->stream);
+  launch_hot_select(h->pairs_rev, &h->d_hot[1], true, h->sms, h->stream);
   CK(cudaGetLastError());
   int rc = clear_dict(h, &h->pairs_fwd);
   if (rc == ALZ_OK) rc = clear_dict(h, &h->pairs_rev);
@@ -277,8 +288,13 @@ static int ingest_device(alz_handle* h, const alz_l7_rec* d, uint64_t n) {
   if (h->cfg.flags & ALZ_CFG_EAGER_JOIN)
     launch_ingest_eager(d, n, h->d_ep, h->ep_cap - 1, h->edges, h->d_ctr, h->sms, h->stream);
   else
-    launch_ingest_pairs(d, n, h->pairs_fwd, h->pairs_rev, h->d_ctr, h->sms, h->stream,
-                        (h->cfg.flags & ALZ_CFG_NO_SMEM_CACHE) ? 0 : 1);
+  {
+    if (h->cfg.flags & ALZ_CFG_NO_SMEM_CACHE)
+      launch_ingest_pairs_v1(d, n, h->pairs_fwd, h->pairs_rev, h->d_ctr, h->sms, h->stream);
+    else
+      launch_ingest_pairs_v4(d, n, h->pairs_fwd, h->pairs_rev, h->d_ctr, &h->d_hot[0], &h->d_hot[1], h->d_ep,
+                             h->ep_cap - 1, h->sms, h->stream);
+  }
   CK(cudaGetLastError());
   h->events_in += n;
   h->pending_since_fold += n;

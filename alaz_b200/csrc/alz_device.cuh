@@ -120,6 +120,7 @@ struct AccTable {
   uint64_t* lat_sum;  // [max_rows + 1]
   uint64_t* err5xx;   // [max_rows + 1]
   uint64_t* count;    // [max_rows + 1] (edge table only; pair tables derive it from hist)
+  uint32_t* row_cnt;  // [max_rows + 1] (pair tables only) events of the row at the last fold, saturated
   uint32_t* hist;     // [(max_rows + 1) * ALZ_NB]
 };
 
@@ -165,6 +166,49 @@ __device__ __forceinline__ uint32_t ep_lookup(const EpEntry* __restrict__ tab, u
   }
 }
 
+// Pair-dictionary insert with the drop rule applied at admission: a NEW socket pair is only
+// inserted if its source address is a pod right now (setFromToV2's first test, data.go:829-832).
+// Unresolvable traffic is often high-cardinality (every event a new pair); letting it into the
+// dictionary cost a CAS, a row and two DRAM-missing reductions per event
+// (profiles/r1_v4_ingest_ncu.txt: 890k row allocations per 100M events, 190k of them real).
+// Existing pairs are found without touching the endpoint table. Returns kDropRow for a rejected pair.
+constexpr uint32_t kDropRow = 0xFFFFFFFDu;
+__device__ __forceinline__ uint32_t find_or_insert_pair(const AccTable& t, uint64_t key,
+                                                        const EpEntry* __restrict__ ep, uint32_t ep_mask) {
+  if (key == kEmptyKey) return t.max_rows;
+  uint32_t slot = (uint32_t)hash64(key) & t.dict_mask;
+  bool checked = false;
+#pragma unroll 1
+  for (uint32_t p = 0; p < kMaxProbe; ++p) {
+    const uint4 e = __ldcg(reinterpret_cast<const uint4*>(&t.dict[slot]));
+    uint64_t k = ((uint64_t)e.y << 32) | e.x;
+    uint32_t row = e.z;
+    if (k == kEmptyKey) {
+      if (!checked) {
+        uint32_t pod, svc;
+        if ((ep_lookup(ep, ep_mask, (uint32_t)(key >> 32), &pod, &svc) & kEpPod) == 0u) return kDropRow;
+        checked = true;
+      }
+      const uint64_t old = atomicCAS((unsigned long long*)&t.dict[slot].key, (unsigned long long)kEmptyKey,
+                                     (unsigned long long)key);
+      if (old == kEmptyKey) {
+        row = atomicAdd(t.n_rows, 1u);
+        if (row >= t.max_rows) row = kLostRow; else t.row_key[row] = key;
+        *reinterpret_cast<volatile uint32_t*>(&t.dict[slot].row) = row;
+        return row;
+      }
+      k = old;
+      row = kNoRow;
+    }
+    if (k == key) {
+      while (row == kNoRow) row = *reinterpret_cast<volatile uint32_t*>(&t.dict[slot].row);
+      return row;
+    }
+    slot = (slot + 1u) & t.dict_mask;
+  }
+  return kLostRow;
+}
+
 // setFromToV2 on integers: false = "error finding pod with sockets saddr" (drop)
 __device__ __forceinline__ bool resolve_edge(const EpEntry* __restrict__ tab, uint32_t mask, uint32_t saddr,
                                              uint32_t daddr, bool rev, uint64_t* edge_key) {
@@ -198,6 +242,23 @@ __device__ __forceinline__ uint32_t rec_status(const Rec& r) { return r.w[3] & 0
 __device__ __forceinline__ uint32_t rec_protocol(const Rec& r) { return (r.w[3] >> 16) & 0xFFu; }
 __device__ __forceinline__ uint32_t rec_mflags(const Rec& r) { return r.w[3] >> 24; }
 __device__ __forceinline__ uint64_t rec_duration(const Rec& r) { return ((uint64_t)r.w[5] << 32) | r.w[4]; }
+
+// ---- hot-pair feedback (alz_ingest.cu): which socket pairs took the most events last fold ----
+constexpr int kHotA = 64;     // tier A: inserted into the per-CTA table first
+constexpr int kHotB = 1024;   // tier B capacity
+struct HotState {
+  uint32_t bins[128];          // quarter-octave histogram of per-pair event counts
+  uint32_t thr_a, thr_b;       // lowest bin of tier A / of tier B
+  uint32_t n_a, n_b;
+  uint64_t keys_a[kHotA];
+  uint64_t keys_b[kHotB];
+};
+// monotone bin of a count >= 1: 4 bins per octave
+__device__ __forceinline__ uint32_t count_bin(uint32_t c) {
+  const uint32_t o = 31u - (uint32_t)__clz((int)c);
+  const uint32_t sub = o >= 2u ? (c >> (o - 2u)) & 3u : (c << (2u - o)) & 3u;
+  return o * 4u + sub;
+}
 
 // device-side counters (per handle)
 struct Counters {

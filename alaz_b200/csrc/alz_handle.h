@@ -35,6 +35,7 @@ struct alz_handle {
   alz::AccTable pairs_fwd{}, pairs_rev{}, edges{};
   alz::Counters* d_ctr = nullptr;
   alz::Counters* h_ctr = nullptr;  // pinned
+  alz::HotState* d_hot = nullptr;  // [2]: forward pairs, reversed pairs
 
   // flush scratch
   uint64_t* d_keys[2] = {nullptr, nullptr};

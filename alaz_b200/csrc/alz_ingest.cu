@@ -1,0 +1,304 @@
+// alz_ingest.cu — the dominant kernel: l7 events -> per-socket-pair accumulators
+// (DESIGN.md §3 step 1, §5). One persistent CTA of 1024 threads per SM.
+//
+// Each CTA keeps a private table of hot socket pairs in shared memory (the stream
+// is Zipf-skewed; without it the hottest pairs serialise in one L2 slice):
+//   * 4-way buckets: a lookup is two LDS.128 and four compares, no probe loop, so
+//     every lane of a warp walks the same instructions;
+//   * which pairs are hot is fed back from the previous fold (hot_select kernels
+//     below): tier A = the ~64 hottest, inserted first so they cannot lose a
+//     bucket race, tier B = the rest up to the table size. With no history (first
+//     window) pairs are admitted first-come while buckets have room;
+//   * racing admissions may duplicate a key inside a bucket: harmless, both rows
+//     are added into the global table when the CTA drains.
+// Cold pairs go to the global dictionary: the home slot of all events of a thread
+// is fetched before any is consumed (memory-level parallelism), the probe loop is
+// only the slow path. Control flow between the stages meets at __syncwarp().
+#include "alz_kernels.cuh"
+
+namespace alz {
+
+namespace {
+
+constexpr int kRowWords = ALZ_NB + 3;   // 64 hist cells, lat_lo, lat_hi, err5xx (odd stride: bank spread)
+constexpr uint32_t kFwdBuckets = 128, kRevBuckets = 16, kWays = 4;
+constexpr uint32_t kSlots = (kFwdBuckets + kRevBuckets) * kWays;
+constexpr int kThreads = 1024;
+constexpr int kUnroll = 2;
+
+struct Smem {
+  uint64_t* keys;   // [kSlots]  bucket-major, 4 keys per bucket (32 B)
+  uint32_t* fill;   // [kFwdBuckets + kRevBuckets]
+  uint32_t* rows;   // [kSlots * kRowWords]
+};
+
+__device__ __forceinline__ uint32_t bucket_of(uint64_t key, bool rv) {
+  const uint32_t hb = (uint32_t)(hash64(key) >> 40);
+  return rv ? kFwdBuckets + (hb & (kRevBuckets - 1u)) : (hb & (kFwdBuckets - 1u));
+}
+
+// slot of key in its bucket or -1; two 16-byte shared loads
+__device__ __forceinline__ int smem_lookup(const Smem& s, uint32_t bucket, uint64_t key) {
+  const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(&s.keys[bucket * kWays]);
+  const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(&s.keys[bucket * kWays + 2]);
+  int w = -1;
+  w = (b.y == key) ? 3 : w;
+  w = (b.x == key) ? 2 : w;
+  w = (a.y == key) ? 1 : w;
+  w = (a.x == key) ? 0 : w;
+  return w < 0 ? -1 : (int)(bucket * kWays) + w;
+}
+
+// claim a free way of the bucket for key; -1 if the bucket is full
+__device__ __forceinline__ int smem_admit(const Smem& s, uint32_t bucket, uint64_t key) {
+  if (*reinterpret_cast<volatile uint32_t*>(&s.fill[bucket]) >= kWays) return -1;
+  const uint32_t w = atomicAdd(&s.fill[bucket], 1u);
+  if (w >= kWays) return -1;
+  s.keys[bucket * kWays + w] = key;
+  return (int)(bucket * kWays + w);
+}
+
+__device__ __forceinline__ void smem_accumulate(const Smem& s, int slot, uint32_t bucket, uint64_t dur, bool err) {
+  uint32_t* row = s.rows + (size_t)slot * kRowWords;
+  atomicAdd(&row[bucket], 1u);
+  const uint32_t lo = (uint32_t)dur;
+  const uint32_t old = atomicAdd(&row[ALZ_NB], lo);
+  const uint32_t hi = (uint32_t)(dur >> 32) + ((old + lo < old) ? 1u : 0u);
+  if (hi) atomicAdd(&row[ALZ_NB + 1], hi);
+  if (err) atomicAdd(&row[ALZ_NB + 2], 1u);
+}
+
+struct Ev {
+  uint64_t key, dur;
+  uint32_t bucket;
+  bool act, rev, err;
+};
+// processL7's switch as bit tests (aggregator/data.go:1364-1383): request rows for
+// HTTP(1) AMQP(2) POSTGRES(3) REDIS(5) MYSQL(7) MONGO(8); the SQL/Mongo ones unless rejected
+__device__ __forceinline__ Ev decode(const Rec& r, bool live) {
+  Ev e;
+  const uint32_t p = rec_protocol(r), mf = rec_mflags(r);
+  const bool row = p <= 8u && ((0x1AEu >> p) & 1u);
+  const bool sql = p <= 8u && ((0x188u >> p) & 1u);
+  e.act = live && row && !(sql && (mf & ALZ_MF_PAYLOAD_REJECT));
+  e.rev = (mf & ALZ_MF_METHOD_MASK) == 2u && (p == ALZ_PROTO_AMQP || p == ALZ_PROTO_REDIS);  // DELIVER / PUSHED_EVENT
+  e.key = ((uint64_t)rec_saddr(r) << 32) | rec_daddr(r);
+  e.dur = rec_duration(r);
+  e.bucket = latency_bucket(e.dur);
+  e.err = is_5xx(p, rec_status(r));
+  return e;
+}
+
+// streaming load: read once, keep it out of L1 and first in line for L2 eviction so the
+// accumulator rows stay resident
+__device__ __forceinline__ Rec load_rec_stream(const alz_l7_rec* p, uint64_t policy) {
+  Rec r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+               : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]),
+                 "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+               : "l"(p), "l"(policy));
+  return r;
+}
+
+// tier A then tier B of one table's hot list into its buckets
+__device__ __forceinline__ void preload_hot(const Smem& s, const HotState* hot, bool rv) {
+  if (hot == nullptr) return;
+  const uint32_t na = min(hot->n_a, (uint32_t)kHotA), nb = min(hot->n_b, (uint32_t)kHotB);
+  for (uint32_t i = threadIdx.x; i < na; i += blockDim.x) {
+    const uint64_t k = hot->keys_a[i];
+    if (k != kEmptyKey) smem_admit(s, bucket_of(k, rv), k);
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
+    const uint64_t k = hot->keys_b[i];
+    if (k != kEmptyKey) smem_admit(s, bucket_of(k, rv), k);
+  }
+}
+
+// private rows [first, first + count) into global table g; a warp per slot
+__device__ __forceinline__ void smem_drain(const Smem& s, uint32_t first, uint32_t count, const AccTable& g,
+                                           const EpEntry* __restrict__ ep, uint32_t ep_mask, uint32_t* lost,
+                                           uint32_t* unresolved) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (uint32_t i = warp; i < count; i += nwarps) {
+    const uint32_t slot = first + i;
+    const uint64_t key = s.keys[slot];
+    if (key == kEmptyKey) continue;   // warp-uniform
+    const uint32_t* row = s.rows + (size_t)slot * kRowWords;
+    const uint32_t h0 = row[lane], h1 = row[32u + lane];
+    uint32_t c = h0 + h1;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+    if (c == 0u) continue;            // preloaded but never hit in this launch: no global row needed
+    uint32_t grow = 0;
+    if (lane == 0) grow = find_or_insert_pair(g, key, ep, ep_mask);
+    grow = __shfl_sync(0xFFFFFFFFu, grow, 0);
+    if (grow >= kDropRow) {   // source is not a pod (dropped like the reference does) or capacity
+      if (lane == 0) { if (grow == kDropRow) *unresolved += c; else *lost += c; }
+      continue;
+    }
+    if (h0) atomicAdd(&g.hist[(size_t)grow * ALZ_NB + lane], h0);
+    if (h1) atomicAdd(&g.hist[(size_t)grow * ALZ_NB + 32u + lane], h1);
+    if (lane == 0) {
+      const uint64_t lat = ((uint64_t)row[ALZ_NB + 1] << 32) + row[ALZ_NB];
+      if (lat) atomicAdd((unsigned long long*)&g.lat_sum[grow], (unsigned long long)lat);
+      if (row[ALZ_NB + 2]) atomicAdd((unsigned long long*)&g.err5xx[grow], (unsigned long long)row[ALZ_NB + 2]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) ingest_pairs_v4_kernel(const alz_l7_rec* __restrict__ recs, uint64_t n,
+                                                                      AccTable fwd, AccTable rev, Counters* ctr,
+                                                                      const HotState* hot_fwd, const HotState* hot_rev,
+                                                                      const EpEntry* __restrict__ ep, uint32_t ep_mask) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  Smem s;
+  s.keys = reinterpret_cast<uint64_t*>(smem_raw);
+  s.fill = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kSlots * 8);
+  s.rows = s.fill + (kFwdBuckets + kRevBuckets);
+  for (uint32_t i = threadIdx.x; i < kSlots; i += kThreads) s.keys[i] = kEmptyKey;
+  for (uint32_t i = threadIdx.x; i < kFwdBuckets + kRevBuckets; i += kThreads) s.fill[i] = 0u;
+  for (uint32_t i = threadIdx.x; i < kSlots * kRowWords; i += kThreads) s.rows[i] = 0u;
+  __syncthreads();
+  preload_hot(s, hot_fwd, false);
+  preload_hot(s, hot_rev, true);
+  __syncthreads();
+
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+
+  uint32_t not_request = 0, lost = 0, unresolved = 0;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t stride = (uint64_t)gridDim.x * kThreads;
+  for (uint64_t base = (uint64_t)blockIdx.x * kThreads + (threadIdx.x & ~31u); base < n; base += stride * kUnroll) {
+    __syncwarp();   // lanes that took the slow path last iteration rejoin here
+    Rec r[kUnroll];
+    bool live[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint64_t j = base + (uint64_t)u * stride + lane;
+      live[u] = j < n;
+      r[u] = Rec{};
+      if (live[u]) r[u] = load_rec_stream(recs + j, policy);
+    }
+    Ev e[kUnroll];
+    int ss[kUnroll];
+    uint32_t sb[kUnroll];
+    // stage 1: decode, shared-memory lookup (no loop, no divergence)
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      e[u] = decode(r[u], live[u]);
+      not_request += (live[u] && !e[u].act) ? 1u : 0u;
+      sb[u] = bucket_of(e[u].key, e[u].rev);
+      ss[u] = smem_lookup(s, sb[u], e[u].key);
+      if (!e[u].act || e[u].key == kEmptyKey) ss[u] = -1;
+    }
+    // stage 2: first-come admission of misses while their bucket has room (rare once warm)
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+      if (e[u].act && ss[u] < 0 && e[u].key != kEmptyKey) ss[u] = smem_admit(s, sb[u], e[u].key);
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+      if (ss[u] >= 0) smem_accumulate(s, ss[u], e[u].bucket, e[u].dur, e[u].err);
+    // stage 3: the rest goes to the global dictionary; fetch every home slot first
+    bool g[kUnroll];
+    uint4 ent[kUnroll];
+    uint32_t home[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      g[u] = e[u].act && ss[u] < 0;
+      const AccTable& t = e[u].rev ? rev : fwd;
+      home[u] = (uint32_t)hash64(e[u].key) & t.dict_mask;
+      ent[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (g[u]) ent[u] = __ldcg(reinterpret_cast<const uint4*>(&t.dict[home[u]]));
+    }
+    uint32_t row[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      row[u] = kLostRow;
+      if (g[u]) {
+        const uint64_t k = ((uint64_t)ent[u].y << 32) | ent[u].x;
+        if (k == e[u].key && ent[u].z != kNoRow && e[u].key != kEmptyKey) row[u] = ent[u].z;   // fast path
+        else row[u] = find_or_insert_pair(e[u].rev ? rev : fwd, e[u].key, ep, ep_mask);        // new pair / collision
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      if (g[u]) {
+        if (row[u] >= kDropRow) { if (row[u] == kDropRow) ++unresolved; else ++lost; continue; }
+        const AccTable& t = e[u].rev ? rev : fwd;
+        atomicAdd(&t.hist[(size_t)row[u] * ALZ_NB + e[u].bucket], 1u);
+        atomicAdd((unsigned long long*)&t.lat_sum[row[u]], (unsigned long long)e[u].dur);
+        if (e[u].err) atomicAdd((unsigned long long*)&t.err5xx[row[u]], 1ull);
+      }
+    }
+  }
+  __syncthreads();
+  smem_drain(s, 0u, kFwdBuckets * kWays, fwd, ep, ep_mask, &lost, &unresolved);
+  smem_drain(s, kFwdBuckets * kWays, kRevBuckets * kWays, rev, ep, ep_mask, &lost, &unresolved);
+  for (int o = 16; o > 0; o >>= 1) {
+    not_request += __shfl_xor_sync(0xFFFFFFFFu, not_request, o);
+    lost += __shfl_xor_sync(0xFFFFFFFFu, lost, o);
+    unresolved += __shfl_xor_sync(0xFFFFFFFFu, unresolved, o);
+  }
+  if (lane == 0) {
+    if (not_request) atomicAdd(&ctr->not_request, (unsigned long long)not_request);
+    if (lost) atomicAdd(&ctr->capacity_events, (unsigned long long)lost);
+    if (unresolved) atomicAdd(&ctr->src_unresolved, (unsigned long long)unresolved);
+  }
+}
+
+// ---- hot-pair feedback: after a fold, pick the pairs that took the most events -----
+// fold_pairs_kernel left row_cnt[row] and a 128-bin (quarter-octave) histogram of the
+// counts; thresholds = the lowest bins that keep tier A <= kHotA and A+B <= target.
+__global__ void hot_pick_kernel(HotState* hot, uint32_t target_total) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  uint32_t cum = 0, thr_a = 128, thr_b = 128;
+  for (int b = 127; b >= 0; --b) {
+    cum += hot->bins[b];
+    if (cum <= (uint32_t)kHotA) thr_a = (uint32_t)b;
+    if (cum <= target_total) thr_b = (uint32_t)b;
+  }
+  hot->thr_a = thr_a;
+  hot->thr_b = thr_b;
+  hot->n_a = 0;
+  hot->n_b = 0;
+}
+__global__ void __launch_bounds__(256) hot_emit_kernel(AccTable pairs, HotState* hot) {
+  const uint32_t n_rows = min(*pairs.n_rows, pairs.max_rows);
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t row = blockIdx.x * blockDim.x + threadIdx.x; row < n_rows; row += stride) {
+    const uint32_t c = pairs.row_cnt[row];
+    if (c == 0u) continue;
+    const uint32_t b = count_bin(c);
+    if (b >= hot->thr_a) {
+      const uint32_t p = atomicAdd(&hot->n_a, 1u);
+      if (p < (uint32_t)kHotA) hot->keys_a[p] = pairs.row_key[row];
+    } else if (b >= hot->thr_b) {
+      const uint32_t p = atomicAdd(&hot->n_b, 1u);
+      if (p < (uint32_t)kHotB) hot->keys_b[p] = pairs.row_key[row];
+    }
+  }
+}
+
+}  // namespace
+
+void launch_ingest_pairs_v4(const alz_l7_rec* recs, uint64_t n, const AccTable& fwd, const AccTable& rev,
+                            Counters* ctr, const HotState* hot_fwd, const HotState* hot_rev, const EpEntry* ep,
+                            uint32_t ep_mask, int sms, cudaStream_t s) {
+  if (n == 0) return;
+  const size_t smem = (size_t)kSlots * 8 + (size_t)(kFwdBuckets + kRevBuckets) * 4 + (size_t)kSlots * kRowWords * 4;
+  // per device (a process may drive several GPUs), so not cached in a static
+  cudaFuncSetAttribute(ingest_pairs_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  ingest_pairs_v4_kernel<<<(unsigned)sms, kThreads, smem, s>>>(recs, n, fwd, rev, ctr, hot_fwd, hot_rev, ep, ep_mask);
+}
+
+// after fold_pairs_kernel(pairs, ..., hot->bins): choose next window's hot list
+void launch_hot_select(const AccTable& pairs, HotState* hot, bool rev, int sms, cudaStream_t s) {
+  const uint32_t target = rev ? (kRevBuckets * kWays * 7u) / 8u : (kFwdBuckets * kWays * 7u) / 8u;
+  hot_pick_kernel<<<1, 32, 0, s>>>(hot, target);
+  hot_emit_kernel<<<(unsigned)sms * 4, 256, 0, s>>>(pairs, hot);
+}
+
+}  // namespace alz

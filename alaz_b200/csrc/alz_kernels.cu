@@ -95,147 +95,6 @@ __global__ void __launch_bounds__(256) ingest_pairs_kernel(const alz_l7_rec* __r
 }
 
 // ---------------------------------------------------------------------------
-// ingest v2 (default): per-CTA shared-memory cache of hot socket pairs.
-// The stream is Zipf-skewed: a handful of pairs take most events, and their
-// global reductions serialise in one L2 slice (v1: 17 ms / 100M events, all of
-// it same-address atomics, profiles/r1_v1_launches.csv). Each CTA admits the
-// first pairs it sees into an open-addressed table in shared memory
-// (first-come is hot-biased under Zipf) and reduces them there; cold pairs go
-// straight to the global dictionary. At the end the CTA adds its private rows
-// into the global table, one reduction per non-zero cell.
-//
-// smem row = 64 hist cells + lat_lo + lat_hi + err5xx = 67 words: the odd
-// stride spreads equal buckets of different pairs over the banks.
-// ---------------------------------------------------------------------------
-constexpr int kRowWords = ALZ_NB + 3;
-// One shared array holds both private tables (forward pairs, then reversed pairs); a
-// table is selected by integer offsets so every access stays a shared-space LDS/ATOMS
-// (selecting between two structs of pointers made them generic loads: long-scoreboard
-// stalls on the probe, profiles/r1_v3_ingest_ncu.txt).
-struct SmemView {
-  uint64_t* keys;   // [fwd_slots + rev_slots]
-  uint32_t* rows;   // [(fwd_slots + rev_slots) * kRowWords]
-  uint32_t* used;   // [2] admitted pairs per table
-  uint32_t fwd_slots, rev_slots;
-};
-
-// slot (global index into keys/rows) of `key` in table `rv`, admitting it while the table is open; -1 = not cached
-__device__ __forceinline__ int smem_find_or_admit(const SmemView& v, bool rv, uint64_t key) {
-  const uint32_t base = rv ? v.fwd_slots : 0u;
-  const uint32_t mask = (rv ? v.rev_slots : v.fwd_slots) - 1u;
-  const uint32_t limit = (mask + 1u) - ((mask + 1u) >> 2);
-  if (key == kEmptyKey) return -1;
-  uint32_t slot = (uint32_t)(hash64(key) >> 32) & mask;
-#pragma unroll 1
-  for (int p = 0; p < 6; ++p) {
-    const uint64_t k = v.keys[base + slot];
-    if (k == key) return (int)(base + slot);
-    if (k == kEmptyKey) {
-      if (*reinterpret_cast<volatile uint32_t*>(&v.used[rv ? 1 : 0]) >= limit) return -1;
-      const uint64_t old = atomicCAS((unsigned long long*)&v.keys[base + slot], (unsigned long long)kEmptyKey,
-                                     (unsigned long long)key);
-      if (old == kEmptyKey) { atomicAdd(&v.used[rv ? 1 : 0], 1u); return (int)(base + slot); }
-      if (old == key) return (int)(base + slot);
-    }
-    slot = (slot + 1u) & mask;
-  }
-  return -1;
-}
-
-__device__ __forceinline__ void smem_accumulate(const SmemView& v, int slot, uint32_t bucket, uint64_t dur, bool err) {
-  uint32_t* row = v.rows + (size_t)slot * kRowWords;
-  atomicAdd(&row[bucket], 1u);
-  const uint32_t lo = (uint32_t)dur;
-  const uint32_t old = atomicAdd(&row[ALZ_NB], lo);
-  const uint32_t hi = (uint32_t)(dur >> 32) + ((old + lo < old) ? 1u : 0u);
-  if (hi) atomicAdd(&row[ALZ_NB + 1], hi);
-  if (err) atomicAdd(&row[ALZ_NB + 2], 1u);
-}
-
-// add the private slots [first, first + count) into global table g; a warp per slot
-__device__ __forceinline__ void smem_drain(const SmemView& v, uint32_t first, uint32_t count, const AccTable& g,
-                                           uint32_t* lost) {
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (uint32_t i = warp; i < count; i += nwarps) {
-    const uint32_t slot = first + i;
-    const uint64_t key = v.keys[slot];
-    if (key == kEmptyKey) continue;   // warp-uniform
-    const uint32_t* row = v.rows + (size_t)slot * kRowWords;
-    uint32_t grow = 0;
-    if (lane == 0) grow = find_or_insert(g, key);
-    grow = __shfl_sync(0xFFFFFFFFu, grow, 0);
-    const uint32_t h0 = row[lane], h1 = row[32u + lane];
-    if (grow >= kLostRow) {
-      uint32_t c = h0 + h1;
-      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
-      if (lane == 0) *lost += c;
-      continue;
-    }
-    if (h0) atomicAdd(&g.hist[(size_t)grow * ALZ_NB + lane], h0);
-    if (h1) atomicAdd(&g.hist[(size_t)grow * ALZ_NB + 32u + lane], h1);
-    if (lane == 0) {
-      const uint64_t lat = ((uint64_t)row[ALZ_NB + 1] << 32) + row[ALZ_NB];
-      if (lat) atomicAdd((unsigned long long*)&g.lat_sum[grow], (unsigned long long)lat);
-      if (row[ALZ_NB + 2]) atomicAdd((unsigned long long*)&g.err5xx[grow], (unsigned long long)row[ALZ_NB + 2]);
-    }
-  }
-}
-
-template <int UNROLL, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1) ingest_pairs_smem_kernel(const alz_l7_rec* __restrict__ recs, uint64_t n,
-                                                                        AccTable fwd, AccTable rev, Counters* ctr,
-                                                                        uint32_t fwd_slots, uint32_t rev_slots) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  __shared__ uint32_t s_used[2];
-  SmemView sv;
-  sv.keys = reinterpret_cast<uint64_t*>(smem_raw);
-  sv.rows = reinterpret_cast<uint32_t*>(smem_raw + (size_t)(fwd_slots + rev_slots) * 8);
-  sv.used = s_used;
-  sv.fwd_slots = fwd_slots; sv.rev_slots = rev_slots;
-  for (uint32_t i = threadIdx.x; i < fwd_slots + rev_slots; i += THREADS) sv.keys[i] = kEmptyKey;
-  for (uint32_t i = threadIdx.x; i < (fwd_slots + rev_slots) * kRowWords; i += THREADS) sv.rows[i] = 0u;
-  if (threadIdx.x < 2) s_used[threadIdx.x] = 0u;
-  __syncthreads();
-
-  uint32_t not_request = 0, lost = 0;
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint64_t stride = (uint64_t)gridDim.x * THREADS;
-  for (uint64_t base = (uint64_t)blockIdx.x * THREADS + (threadIdx.x & ~31u); base < n; base += stride * UNROLL) {
-    Rec r[UNROLL];
-    bool live[UNROLL];
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const uint64_t j = base + (uint64_t)u * stride + lane;
-      live[u] = j < n;
-      if (live[u]) r[u] = load_rec(recs + j);
-    }
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const Ev e = decode(r[u], live[u]);
-      not_request += (live[u] && !e.act) ? 1u : 0u;
-      // 1) shared-memory table
-      int ss = -1;
-      if (e.act) ss = smem_find_or_admit(sv, e.rev, e.key);
-      __syncwarp();
-      if (ss >= 0) smem_accumulate(sv, ss, e.bucket, e.dur, e.err);
-      // 2) the rest: global dictionary
-      const bool g = e.act && ss < 0;
-      uint32_t row = kLostRow;
-      if (g) row = find_or_insert(e.rev ? rev : fwd, e.key);
-      __syncwarp();
-      if (g) {
-        if (row >= kLostRow) ++lost;
-        else global_accumulate(e.rev ? rev : fwd, row, e.bucket, e.dur, e.err);
-      }
-    }
-  }
-  __syncthreads();
-  smem_drain(sv, 0u, fwd_slots, fwd, &lost);
-  smem_drain(sv, fwd_slots, rev_slots, rev, &lost);
-  flush_thread_counters(ctr, not_request, 0u, lost);
-}
-
-// ---------------------------------------------------------------------------
 // ingest, eager plan: join every event, then reduce per edge
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ingest_eager_kernel(const alz_l7_rec* __restrict__ recs, uint64_t n,
@@ -276,7 +135,8 @@ __global__ void __launch_bounds__(256) ingest_eager_kernel(const alz_l7_rec* __r
 // zero it. The caller clears the pair dictionary afterwards.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fold_pairs_kernel(AccTable pairs, bool rev, const EpEntry* __restrict__ ep,
-                                                         uint32_t ep_mask, AccTable edges, Counters* ctr) {
+                                                         uint32_t ep_mask, AccTable edges, Counters* ctr,
+                                                         uint32_t* __restrict__ hot_bins) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warps_per_grid = (gridDim.x * blockDim.x) >> 5;
   const uint32_t n_rows = min(*pairs.n_rows, pairs.max_rows);
@@ -288,6 +148,11 @@ __global__ void __launch_bounds__(256) fold_pairs_kernel(AccTable pairs, bool re
     uint64_t cnt = (uint64_t)h0 + h1;
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
     if (cnt == 0) continue;  // unused sentinel row (allocated rows always hold >= 1 event)
+    if (lane == 0 && row != pairs.max_rows && pairs.row_cnt != nullptr) {   // feedback for the next ingest
+      const uint32_t c32 = cnt > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)cnt;
+      pairs.row_cnt[row] = c32;
+      if (hot_bins != nullptr) atomicAdd(&hot_bins[count_bin(c32)], 1u);
+    }
     const uint64_t key = (row == pairs.max_rows) ? kEmptyKey : pairs.row_key[row];
     uint64_t ekey = 0;
     uint32_t erow = kLostRow;
@@ -428,20 +293,10 @@ __global__ void __launch_bounds__(256) synth_owned_kernel(alz_synth_view v, uint
 // ---------------------------------------------------------------------------
 static inline unsigned grid_for(int sms, int per_sm) { return (unsigned)(sms * per_sm); }
 
-void launch_ingest_pairs(const alz_l7_rec* recs, uint64_t n, const AccTable& fwd, const AccTable& rev,
-                         Counters* ctr, int sms, cudaStream_t s, int variant) {
-  if (n == 0) return;
-  if (variant == 0) {  // v1: global reductions only (kept for the ncu comparison)
-    ingest_pairs_kernel<4><<<grid_for(sms, 8), 256, 0, s>>>(recs, n, fwd, rev, ctr);
-    return;
-  }
-  constexpr int kThreads = 1024;
-  const uint32_t fwd_slots = 512, rev_slots = 64;
-  const size_t smem = (size_t)(fwd_slots + rev_slots) * (8 + kRowWords * 4);
-  // per device (a process may drive several GPUs), so not cached in a static
-  cudaFuncSetAttribute(ingest_pairs_smem_kernel<2, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  ingest_pairs_smem_kernel<2, kThreads><<<grid_for(sms, 1), kThreads, smem, s>>>(recs, n, fwd, rev, ctr, fwd_slots,
-                                                                               rev_slots);
+void launch_ingest_pairs_v1(const alz_l7_rec* recs, uint64_t n, const AccTable& fwd, const AccTable& rev,
+                            Counters* ctr, int sms, cudaStream_t s) {
+  if (n == 0) return;   // global reductions only (ALZ_CFG_NO_SMEM_CACHE; kept for the ncu comparison)
+  ingest_pairs_kernel<4><<<grid_for(sms, 8), 256, 0, s>>>(recs, n, fwd, rev, ctr);
 }
 void launch_ingest_eager(const alz_l7_rec* recs, uint64_t n, const EpEntry* ep, uint32_t ep_mask,
                          const AccTable& edges, Counters* ctr, int sms, cudaStream_t s) {
@@ -449,8 +304,8 @@ void launch_ingest_eager(const alz_l7_rec* recs, uint64_t n, const EpEntry* ep, 
   ingest_eager_kernel<<<grid_for(sms, 8), 256, 0, s>>>(recs, n, ep, ep_mask, edges, ctr);
 }
 void launch_fold_pairs(const AccTable& pairs, bool rev, const EpEntry* ep, uint32_t ep_mask,
-                       const AccTable& edges, Counters* ctr, int sms, cudaStream_t s) {
-  fold_pairs_kernel<<<grid_for(sms, 8), 256, 0, s>>>(pairs, rev, ep, ep_mask, edges, ctr);
+                       const AccTable& edges, Counters* ctr, uint32_t* hot_bins, int sms, cudaStream_t s) {
+  fold_pairs_kernel<<<grid_for(sms, 8), 256, 0, s>>>(pairs, rev, ep, ep_mask, edges, ctr, hot_bins);
 }
 void launch_iota(uint32_t* out, uint32_t n, int sms, cudaStream_t s) {
   if (n == 0) return;

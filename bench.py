@@ -253,7 +253,7 @@ def main():
                 "parallelism": f"dp{world} by alz_owner_rank(saddr)" if world > 1 else "single GPU",
                 "live_edges": int(n_edges), "rows_emitted_per_step": int(st["rows_emitted"] // max(1, st["events_in"] // N)),
             },
-            "roofline": {"bound": "hbm", "kernel": "ingest_pairs_kernel" if not args.eager else "ingest_eager_kernel",
+            "roofline": {"bound": "hbm", "kernel": "ingest_eager_kernel" if args.eager else ("ingest_pairs_kernel(v1)" if args.no_smem_cache else "ingest_pairs_v4_kernel"),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": None,
                          "kernel_ms": ingest_ms_max, "flush_ms": flush_ms,
