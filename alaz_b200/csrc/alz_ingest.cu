@@ -12,8 +12,14 @@
 //   * racing admissions may duplicate a key inside a bucket: harmless, both rows
 //     are added into the global table when the CTA drains.
 // Cold pairs go to the global dictionary: the home slot of all events of a thread
-// is fetched before any is consumed (memory-level parallelism), the probe loop is
-// only the slow path. Control flow between the stages meets at __syncwarp().
+// is fetched before any is consumed (memory-level parallelism) and a hit there is
+// reduced at once. Everything else — a new pair, a collision, an unresolvable
+// source — is rare (~4 % of events) and loop-shaped, so it is NOT run inline: the
+// lane pushes the event onto its warp's queue in shared memory (ballot-compacted,
+// no atomics) and the warp runs the slow path for 32 queued events at a time.
+// The main loop therefore stays converged: with the slow path inline, lanes
+// came back from it in separate groups and the whole loop body issued ~1.55x
+// (profiles/r1_v4b_ingest_ncu.txt: 20 of 32 lanes active on the loop's own code).
 #include "alz_kernels.cuh"
 
 namespace alz {
@@ -25,6 +31,7 @@ constexpr uint32_t kFwdBuckets = 128, kRevBuckets = 16, kWays = 4;
 constexpr uint32_t kSlots = (kFwdBuckets + kRevBuckets) * kWays;
 constexpr int kThreads = 1024;
 constexpr int kUnroll = 2;
+constexpr uint32_t kQueue = 64;          // slow-path queue entries per warp (ring)
 
 struct Smem {
   uint64_t* keys;   // [kSlots]  bucket-major, 4 keys per bucket (32 B)
@@ -146,6 +153,32 @@ __device__ __forceinline__ void smem_drain(const Smem& s, uint32_t first, uint32
   }
 }
 
+// the warp's slow path: lane i takes queue entry (head + i) for i < count
+__device__ __forceinline__ void slow_path_32(const uint64_t* q_key, const uint64_t* q_dur, const uint32_t* q_meta,
+                                             uint32_t head, uint32_t count, const AccTable& fwd, const AccTable& rev,
+                                             const EpEntry* __restrict__ ep, uint32_t ep_mask, uint32_t* lost,
+                                             uint32_t* unresolved) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const bool mine = lane < count;
+  const uint32_t pos = (head + lane) & (kQueue - 1u);
+  uint64_t key = 0, dur = 0;
+  uint32_t meta = 0, row = kLostRow;
+  if (mine) { key = q_key[pos]; dur = q_dur[pos]; meta = q_meta[pos]; }
+  const bool rv = (meta & 0x100u) != 0u;
+  if (mine) row = find_or_insert_pair(rv ? rev : fwd, key, ep, ep_mask);
+  __syncwarp();
+  if (mine) {
+    if (row >= kDropRow) { if (row == kDropRow) *unresolved += 1u; else *lost += 1u; }
+    else {
+      const AccTable& t = rv ? rev : fwd;
+      atomicAdd(&t.hist[(size_t)row * ALZ_NB + (meta & 0xFFu)], 1u);
+      atomicAdd((unsigned long long*)&t.lat_sum[row], (unsigned long long)dur);
+      if (meta & 0x200u) atomicAdd((unsigned long long*)&t.err5xx[row], 1ull);
+    }
+  }
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(kThreads, 1) ingest_pairs_v4_kernel(const alz_l7_rec* __restrict__ recs, uint64_t n,
                                                                       AccTable fwd, AccTable rev, Counters* ctr,
                                                                       const HotState* hot_fwd, const HotState* hot_rev,
@@ -155,6 +188,12 @@ __global__ void __launch_bounds__(kThreads, 1) ingest_pairs_v4_kernel(const alz_
   s.keys = reinterpret_cast<uint64_t*>(smem_raw);
   s.fill = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kSlots * 8);
   s.rows = s.fill + (kFwdBuckets + kRevBuckets);
+  // per-warp slow-path queues behind the table
+  uint8_t* qbase = reinterpret_cast<uint8_t*>(s.rows + (size_t)kSlots * kRowWords) + (size_t)(threadIdx.x >> 5) * kQueue * 20;
+  uint64_t* q_key = reinterpret_cast<uint64_t*>(qbase);
+  uint64_t* q_dur = q_key + kQueue;
+  uint32_t* q_meta = reinterpret_cast<uint32_t*>(q_dur + kQueue);
+  uint32_t q_head = 0, q_count = 0;
   for (uint32_t i = threadIdx.x; i < kSlots; i += kThreads) s.keys[i] = kEmptyKey;
   for (uint32_t i = threadIdx.x; i < kFwdBuckets + kRevBuckets; i += kThreads) s.fill[i] = 0u;
   for (uint32_t i = threadIdx.x; i < kSlots * kRowWords; i += kThreads) s.rows[i] = 0u;
@@ -203,37 +242,43 @@ __global__ void __launch_bounds__(kThreads, 1) ingest_pairs_v4_kernel(const alz_
     // stage 3: the rest goes to the global dictionary; fetch every home slot first
     bool g[kUnroll];
     uint4 ent[kUnroll];
-    uint32_t home[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       g[u] = e[u].act && ss[u] < 0;
       const AccTable& t = e[u].rev ? rev : fwd;
-      home[u] = (uint32_t)hash64(e[u].key) & t.dict_mask;
+      const uint32_t home = (uint32_t)hash64(e[u].key) & t.dict_mask;
       ent[u] = make_uint4(0u, 0u, 0u, 0u);
-      if (g[u]) ent[u] = __ldcg(reinterpret_cast<const uint4*>(&t.dict[home[u]]));
+      if (g[u]) ent[u] = __ldcg(reinterpret_cast<const uint4*>(&t.dict[home]));
     }
-    uint32_t row[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-      row[u] = kLostRow;
-      if (g[u]) {
-        const uint64_t k = ((uint64_t)ent[u].y << 32) | ent[u].x;
-        if (k == e[u].key && ent[u].z != kNoRow && e[u].key != kEmptyKey) row[u] = ent[u].z;   // fast path
-        else row[u] = find_or_insert_pair(e[u].rev ? rev : fwd, e[u].key, ep, ep_mask);        // new pair / collision
-      }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      if (g[u]) {
-        if (row[u] >= kDropRow) { if (row[u] == kDropRow) ++unresolved; else ++lost; continue; }
+      const uint64_t k = ((uint64_t)ent[u].y << 32) | ent[u].x;
+      const bool hit = g[u] && k == e[u].key && ent[u].z < kDropRow && e[u].key != kEmptyKey;
+      if (hit) {
         const AccTable& t = e[u].rev ? rev : fwd;
-        atomicAdd(&t.hist[(size_t)row[u] * ALZ_NB + e[u].bucket], 1u);
-        atomicAdd((unsigned long long*)&t.lat_sum[row[u]], (unsigned long long)e[u].dur);
-        if (e[u].err) atomicAdd((unsigned long long*)&t.err5xx[row[u]], 1ull);
+        atomicAdd(&t.hist[(size_t)ent[u].z * ALZ_NB + e[u].bucket], 1u);
+        atomicAdd((unsigned long long*)&t.lat_sum[ent[u].z], (unsigned long long)e[u].dur);
+        if (e[u].err) atomicAdd((unsigned long long*)&t.err5xx[ent[u].z], 1ull);
+      }
+      // everything else waits in the warp's queue
+      const bool slow = g[u] && !hit;
+      const uint32_t m = __ballot_sync(0xFFFFFFFFu, slow);
+      if (slow) {
+        const uint32_t pos = (q_head + q_count + __popc(m & ((1u << lane) - 1u))) & (kQueue - 1u);
+        q_key[pos] = e[u].key;
+        q_dur[pos] = e[u].dur;
+        q_meta[pos] = e[u].bucket | (e[u].rev ? 0x100u : 0u) | (e[u].err ? 0x200u : 0u);
+      }
+      q_count += __popc(m);
+      __syncwarp();
+      if (q_count >= 32u) {
+        slow_path_32(q_key, q_dur, q_meta, q_head, 32u, fwd, rev, ep, ep_mask, &lost, &unresolved);
+        q_head = (q_head + 32u) & (kQueue - 1u);
+        q_count -= 32u;
       }
     }
   }
+  if (q_count) slow_path_32(q_key, q_dur, q_meta, q_head, q_count, fwd, rev, ep, ep_mask, &lost, &unresolved);
   __syncthreads();
   smem_drain(s, 0u, kFwdBuckets * kWays, fwd, ep, ep_mask, &lost, &unresolved);
   smem_drain(s, kFwdBuckets * kWays, kRevBuckets * kWays, rev, ep, ep_mask, &lost, &unresolved);
@@ -288,7 +333,8 @@ void launch_ingest_pairs_v4(const alz_l7_rec* recs, uint64_t n, const AccTable& 
                             Counters* ctr, const HotState* hot_fwd, const HotState* hot_rev, const EpEntry* ep,
                             uint32_t ep_mask, int sms, cudaStream_t s) {
   if (n == 0) return;
-  const size_t smem = (size_t)kSlots * 8 + (size_t)(kFwdBuckets + kRevBuckets) * 4 + (size_t)kSlots * kRowWords * 4;
+  const size_t smem = (size_t)kSlots * 8 + (size_t)(kFwdBuckets + kRevBuckets) * 4 + (size_t)kSlots * kRowWords * 4 +
+                      (size_t)(kThreads / 32) * kQueue * 20;
   // per device (a process may drive several GPUs), so not cached in a static
   cudaFuncSetAttribute(ingest_pairs_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   ingest_pairs_v4_kernel<<<(unsigned)sms, kThreads, smem, s>>>(recs, n, fwd, rev, ctr, hot_fwd, hot_rev, ep, ep_mask);
