@@ -20,6 +20,8 @@
 // The main loop therefore stays converged: with the slow path inline, lanes
 // came back from it in separate groups and the whole loop body issued ~1.55x
 // (profiles/r1_v4b_ingest_ncu.txt: 20 of 32 lanes active on the loop's own code).
+#include <cstdlib>
+
 #include "alz_kernels.cuh"
 
 namespace alz {
@@ -29,8 +31,6 @@ namespace {
 constexpr int kRowWords = ALZ_NB + 3;   // 64 hist cells, lat_lo, lat_hi, err5xx (odd stride: bank spread)
 constexpr uint32_t kFwdBuckets = 128, kRevBuckets = 16, kWays = 4;
 constexpr uint32_t kSlots = (kFwdBuckets + kRevBuckets) * kWays;
-constexpr int kThreads = 1024;
-constexpr int kUnroll = 2;
 constexpr uint32_t kQueue = 64;          // slow-path queue entries per warp (ring)
 
 struct Smem {
@@ -179,6 +179,7 @@ __device__ __forceinline__ void slow_path_32(const uint64_t* q_key, const uint64
   __syncwarp();
 }
 
+template <int kThreads, int kUnroll, bool kPrefetch>
 __global__ void __launch_bounds__(kThreads, 1) ingest_pairs_v4_kernel(const alz_l7_rec* __restrict__ recs, uint64_t n,
                                                                       AccTable fwd, AccTable rev, Counters* ctr,
                                                                       const HotState* hot_fwd, const HotState* hot_rev,
@@ -208,16 +209,41 @@ __global__ void __launch_bounds__(kThreads, 1) ingest_pairs_v4_kernel(const alz_
   uint32_t not_request = 0, lost = 0, unresolved = 0;
   const uint32_t lane = threadIdx.x & 31u;
   const uint64_t stride = (uint64_t)gridDim.x * kThreads;
-  for (uint64_t base = (uint64_t)blockIdx.x * kThreads + (threadIdx.x & ~31u); base < n; base += stride * kUnroll) {
-    __syncwarp();   // lanes that took the slow path last iteration rejoin here
-    Rec r[kUnroll];
-    bool live[kUnroll];
+  const uint64_t first = (uint64_t)blockIdx.x * kThreads + (threadIdx.x & ~31u);
+  Rec nxt[kUnroll];
+  bool nlive[kUnroll];
+  if (kPrefetch) {   // records of the first iteration
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-      const uint64_t j = base + (uint64_t)u * stride + lane;
-      live[u] = j < n;
-      r[u] = Rec{};
-      if (live[u]) r[u] = load_rec_stream(recs + j, policy);
+      const uint64_t j = first + (uint64_t)u * stride + lane;
+      nlive[u] = j < n;
+      nxt[u] = Rec{};
+      if (nlive[u]) nxt[u] = load_rec_stream(recs + j, policy);
+    }
+  }
+  for (uint64_t base = first; base < n; base += stride * kUnroll) {
+    __syncwarp();
+    Rec r[kUnroll];
+    bool live[kUnroll];
+    if (kPrefetch) {
+      // take this iteration's records, put the next iteration's loads in flight before any processing
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) { r[u] = nxt[u]; live[u] = nlive[u]; }
+      const uint64_t nb = base + stride * kUnroll;
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const uint64_t j = nb + (uint64_t)u * stride + lane;
+        nlive[u] = j < n;
+        if (nlive[u]) nxt[u] = load_rec_stream(recs + j, policy);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const uint64_t j = base + (uint64_t)u * stride + lane;
+        live[u] = j < n;
+        r[u] = Rec{};
+        if (live[u]) r[u] = load_rec_stream(recs + j, policy);
+      }
     }
     Ev e[kUnroll];
     int ss[kUnroll];
@@ -329,15 +355,32 @@ __global__ void __launch_bounds__(256) hot_emit_kernel(AccTable pairs, HotState*
 
 }  // namespace
 
+template <int kThreads, int kUnroll, bool kPrefetch>
+static void launch_variant(const alz_l7_rec* recs, uint64_t n, const AccTable& fwd, const AccTable& rev, Counters* ctr,
+                           const HotState* hot_fwd, const HotState* hot_rev, const EpEntry* ep, uint32_t ep_mask,
+                           int sms, cudaStream_t s) {
+  const size_t smem = (size_t)kSlots * 8 + (size_t)(kFwdBuckets + kRevBuckets) * 4 + (size_t)kSlots * kRowWords * 4 +
+                      (size_t)(kThreads / 32) * kQueue * 20;
+  // per device (a process may drive several GPUs), so not cached in a static
+  cudaFuncSetAttribute(ingest_pairs_v4_kernel<kThreads, kUnroll, kPrefetch>,
+                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  ingest_pairs_v4_kernel<kThreads, kUnroll, kPrefetch><<<(unsigned)sms, kThreads, smem, s>>>(
+      recs, n, fwd, rev, ctr, hot_fwd, hot_rev, ep, ep_mask);
+}
+
 void launch_ingest_pairs_v4(const alz_l7_rec* recs, uint64_t n, const AccTable& fwd, const AccTable& rev,
                             Counters* ctr, const HotState* hot_fwd, const HotState* hot_rev, const EpEntry* ep,
                             uint32_t ep_mask, int sms, cudaStream_t s) {
   if (n == 0) return;
-  const size_t smem = (size_t)kSlots * 8 + (size_t)(kFwdBuckets + kRevBuckets) * 4 + (size_t)kSlots * kRowWords * 4 +
-                      (size_t)(kThreads / 32) * kQueue * 20;
-  // per device (a process may drive several GPUs), so not cached in a static
-  cudaFuncSetAttribute(ingest_pairs_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  ingest_pairs_v4_kernel<<<(unsigned)sms, kThreads, smem, s>>>(recs, n, fwd, rev, ctr, hot_fwd, hot_rev, ep, ep_mask);
+  // ALZ_INGEST_VARIANT: tuning knob for profiling runs (default = the measured best)
+  static const int variant = [] { const char* v = getenv("ALZ_INGEST_VARIANT"); return v ? atoi(v) : 0; }();
+  switch (variant) {
+    case 1: launch_variant<512, 4, true>(recs, n, fwd, rev, ctr, hot_fwd, hot_rev, ep, ep_mask, sms, s); break;
+    case 2: launch_variant<768, 2, true>(recs, n, fwd, rev, ctr, hot_fwd, hot_rev, ep, ep_mask, sms, s); break;
+    case 3: launch_variant<512, 4, false>(recs, n, fwd, rev, ctr, hot_fwd, hot_rev, ep, ep_mask, sms, s); break;
+    case 4: launch_variant<1024, 2, true>(recs, n, fwd, rev, ctr, hot_fwd, hot_rev, ep, ep_mask, sms, s); break;
+    default: launch_variant<1024, 2, false>(recs, n, fwd, rev, ctr, hot_fwd, hot_rev, ep, ep_mask, sms, s); break;
+  }
 }
 
 // after fold_pairs_kernel(pairs, ..., hot->bins): choose next window's hot list

@@ -84,6 +84,7 @@ static const char* POD = "pod";
 static const char* SVC = "service";
 static const char* OUTBOUND = "outbound";
 
+#define NSHARD 64
 typedef struct acc {
   uint64_t count, err5xx, lat_sum;
   uint32_t hist[ALZ_NB];
@@ -92,7 +93,8 @@ typedef struct acc {
 struct orc {
   smap pod_ip_to_uid; /* ClusterInfo.PodIPToPodUid, cluster.go:15 */
   smap svc_ip_to_uid; /* ClusterInfo.ServiceIPToServiceUid, cluster.go:16 */
-  smap groups;        /* "ftype|fuid|ttype|tuid" -> acc* */
+  smap groups[NSHARD]; /* "ftype|fuid|ttype|tuid" -> acc*, sharded by key hash so that the
+                          multi-threaded merge can run one shard per thread */
   alz_stats st;
 };
 
@@ -100,14 +102,14 @@ orc* orc_create(void) {
   orc* o = (orc*)calloc(1, sizeof(*o));
   smap_init(&o->pod_ip_to_uid, 1024);
   smap_init(&o->svc_ip_to_uid, 1024);
-  smap_init(&o->groups, 1024);
+  for (int i = 0; i < NSHARD; i++) smap_init(&o->groups[i], 256);
   return o;
 }
 void orc_destroy(orc* o) {
   if (!o) return;
   smap_free(&o->pod_ip_to_uid, 1);
   smap_free(&o->svc_ip_to_uid, 1);
-  smap_free(&o->groups, 1);
+  for (int i = 0; i < NSHARD; i++) smap_free(&o->groups[i], 1);
   free(o);
 }
 
@@ -218,9 +220,10 @@ uint32_t orc_bucket(uint64_t d) {
 }
 
 /* PersistRequest stand-in: fold the emitted row into its (From,To) group */
-static void persist_request(smap* groups, const request* r, alz_stats* st) {
+static void persist_request(smap* shards, const request* r, alz_stats* st) {
   char key[96];
   snprintf(key, sizeof key, "%s|%s|%s|%s", r->from_type, r->from_uid, r->to_type, r->to_uid);
+  smap* groups = &shards[str_hash(key) % NSHARD];
   smap_ent* g = smap_find(groups, key);
   acc* a;
   if (g) a = (acc*)g->val;
@@ -279,15 +282,36 @@ static void process_l7(const orc* o, const alz_l7_rec* d, smap* groups, alz_stat
 }
 
 typedef struct worker {
-  const orc* o;
+  orc* o;
   const alz_l7_rec* recs;
   size_t n;
-  smap groups;
+  smap groups[NSHARD];
   alz_stats st;
+  struct worker* all;
+  int nworkers, id;
 } worker;
 static void* worker_main(void* p) {
   worker* w = (worker*)p;
-  for (size_t i = 0; i < w->n; i++) process_l7(w->o, &w->recs[i], &w->groups, &w->st);
+  for (size_t i = 0; i < w->n; i++) process_l7(w->o, &w->recs[i], w->groups, &w->st);
+  return NULL;
+}
+static void merge_acc(acc* dst, const acc* src);
+/* phase 2: thread `id` folds shards id, id+T, ... of every worker into the shared result */
+static void* merge_main(void* p) {
+  worker* w = (worker*)p;
+  for (int sh = w->id; sh < NSHARD; sh += w->nworkers) {
+    smap* dst = &w->o->groups[sh];
+    for (int t = 0; t < w->nworkers; t++) {
+      smap* src = &w->all[t].groups[sh];
+      for (size_t i = 0; i < src->cap; i++) {
+        smap_ent* e = &src->e[i];
+        if (!e->key || e->key == TOMB) continue;
+        smap_ent* g = smap_find(dst, e->key);
+        if (g) { merge_acc((acc*)g->val, (acc*)e->val); free(e->val); }
+        else smap_put(dst, e->key, e->val, 0);
+      }
+    }
+  }
   return NULL;
 }
 static void merge_acc(acc* dst, const acc* src) {
@@ -297,7 +321,7 @@ static void merge_acc(acc* dst, const acc* src) {
 
 void orc_process_l7(orc* o, const alz_l7_rec* recs, size_t n, int nthreads) {
   if (nthreads <= 1) {
-    for (size_t i = 0; i < n; i++) process_l7(o, &recs[i], &o->groups, &o->st);
+    for (size_t i = 0; i < n; i++) process_l7(o, &recs[i], o->groups, &o->st);
     return;
   }
   worker* w = (worker*)calloc((size_t)nthreads, sizeof(worker));
@@ -305,20 +329,15 @@ void orc_process_l7(orc* o, const alz_l7_rec* recs, size_t n, int nthreads) {
   size_t per = (n + (size_t)nthreads - 1) / (size_t)nthreads;
   for (int t = 0; t < nthreads; t++) {
     size_t b = per * (size_t)t, e = b + per; if (b > n) b = n; if (e > n) e = n;
-    w[t].o = o; w[t].recs = recs + b; w[t].n = e - b;
-    smap_init(&w[t].groups, 1024);
+    w[t].o = o; w[t].recs = recs + b; w[t].n = e - b; w[t].all = w; w[t].nworkers = nthreads; w[t].id = t;
+    for (int i = 0; i < NSHARD; i++) smap_init(&w[t].groups[i], 64);
     pthread_create(&th[t], NULL, worker_main, &w[t]);
   }
+  for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+  for (int t = 0; t < nthreads; t++) pthread_create(&th[t], NULL, merge_main, &w[t]);
+  for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
   for (int t = 0; t < nthreads; t++) {
-    pthread_join(th[t], NULL);
-    for (size_t i = 0; i < w[t].groups.cap; i++) {
-      smap_ent* e = &w[t].groups.e[i];
-      if (!e->key || e->key == TOMB) continue;
-      smap_ent* g = smap_find(&o->groups, e->key);
-      if (g) { merge_acc((acc*)g->val, (acc*)e->val); free(e->val); }
-      else smap_put(&o->groups, e->key, e->val, 0);
-    }
-    smap_free(&w[t].groups, 0);
+    for (int i = 0; i < NSHARD; i++) smap_free(&w[t].groups[i], 0);
     o->st.events_in += w[t].st.events_in; o->st.rows_emitted += w[t].st.rows_emitted;
     o->st.not_request += w[t].st.not_request; o->st.src_unresolved += w[t].st.src_unresolved;
   }
@@ -343,8 +362,9 @@ static int edge_cmp(const void* pa, const void* pb) {
 }
 size_t orc_edges(orc* o, alz_edge_out* out, size_t cap) {
   size_t n = 0;
-  for (size_t i = 0; i < o->groups.cap; i++) {
-    smap_ent* e = &o->groups.e[i];
+  for (int sh = 0; sh < NSHARD; sh++)
+  for (size_t i = 0; i < o->groups[sh].cap; i++) {
+    smap_ent* e = &o->groups[sh].e[i];
     if (!e->key || e->key == TOMB) continue;
     if (n < cap) {
       char k[96]; snprintf(k, sizeof k, "%s", e->key);
@@ -363,12 +383,12 @@ size_t orc_edges(orc* o, alz_edge_out* out, size_t cap) {
   return n;
 }
 void orc_window_reset(orc* o) {
-  smap_free(&o->groups, 1);
-  smap_init(&o->groups, 1024);
+  for (int i = 0; i < NSHARD; i++) { smap_free(&o->groups[i], 1); smap_init(&o->groups[i], 256); }
 }
 void orc_stats(orc* o, alz_stats* st) {
   *st = o->st;
-  st->edges_live = o->groups.len;
+  st->edges_live = 0;
+  for (int i = 0; i < NSHARD; i++) st->edges_live += o->groups[i].len;
 }
 
 /* docs/SPEC.md §5 */
