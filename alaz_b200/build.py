@@ -50,5 +50,25 @@ def build(force=False, verbose=False):
     return LIB
 
 
+SIM_TEST = os.path.join(LIB_DIR, "alaz_sim_test")
+
+
+def build_sim_test(force=False):
+    """g++ build of the C++ host adapter + the reference's simulation scenario (tests/cpp/sim_test.cc)."""
+    root = os.path.dirname(HERE)
+    srcs = [os.path.join(root, "tests", "cpp", "sim_test.cc"), os.path.join(HERE, "host", "alaz_aggregator.cc")]
+    deps = srcs + [os.path.join(HERE, "host", "alaz_aggregator.hpp"), LIB]
+    build()
+    if not force and os.path.exists(SIM_TEST) and all(os.path.getmtime(d) <= os.path.getmtime(SIM_TEST) for d in deps):
+        return SIM_TEST
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall"] + srcs + ["-L" + LIB_DIR, "-lalazgpu", "-Wl,-rpath," + LIB_DIR,
+                                                           "-Wl,-rpath,$ORIGIN", "-o", SIM_TEST]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building alaz_sim_test")
+    return SIM_TEST
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -183,3 +183,32 @@ class Topo:
 
     def __del__(self):
         self.close()
+
+
+class SockMaps:
+    """processTcpConnect + SocketLine lookups, restated (oracle/alz_oracle.c)."""
+
+    def __init__(self):
+        self.L = lib()
+        self.h = self.L.orc_sockmaps_create()
+        self.localhost_dropped = 0
+
+    def process(self, recs):
+        recs = np.ascontiguousarray(recs, dtype=abi.TCP_REC)
+        d = C.c_uint64(0)
+        self.L.orc_sockmaps_process_tcp(self.h, _ptr(recs), len(recs), C.byref(d))
+        self.localhost_dropped += d.value
+
+    def lookup(self, q):
+        q = np.ascontiguousarray(q, dtype=abi.SOCK_QUERY)
+        out = np.zeros(len(q), dtype=abi.SOCK_RESULT)
+        self.L.orc_sockmaps_lookup(self.h, _ptr(q), len(q), _ptr(out))
+        return out
+
+    def close(self):
+        if self.h:
+            self.L.orc_sockmaps_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
