@@ -11,7 +11,9 @@
 //             row reads) -> [h_v || m_v] (128) x W (128 x 64) + b, ReLU
 //   score   : sigma(a . [h2_u || h2_v || e_uv] + c), e_uv from the edge's
 //             integers and float64 histogram quantiles
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -50,6 +52,16 @@ Weights make_weights() {
   for (int k = 0; k < 132; ++k) w.a[k] = (float)(unit(idx++) * sa);
   w.c = 0.0f;
   return w;
+}
+
+// host-side cvt.rna.tf32.f32: round to nearest (ties away) on the 13 dropped mantissa bits
+inline float tf32_round(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  u = (u + 0x1000u) & 0xFFFFE000u;
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
 }
 
 __device__ __forceinline__ uint64_t node_key(uint32_t kind, uint32_t value) { return ((uint64_t)kind << 32) | value; }
@@ -173,6 +185,172 @@ __global__ void __launch_bounds__(256) sage_layer_kernel(const float* __restrict
   }
 }
 
+// ---------------------------------------------------------------------------
+// The same layer on the 5th-gen tensor cores: the feature update
+//   [h_v || mean_{u in N_in(v)} h_u]  (128 nodes x 128)  x  W (128 x 64)
+// is the path's one dense contraction. One persistent CTA per SM, tile = 128 nodes:
+//   gather   8 warps build the tile's 128 x 128 operand directly in shared memory in
+//            the UMMA K-major / no-swizzle layout (8 x 16-byte core matrices)
+//   MMA      one thread issues tcgen05.mma.cta_group::1.kind::tf32, M=128 N=64 K=8,
+//            accumulator in TMEM (64 columns)
+//   epilogue 4 warps tcgen05.ld their 32 lanes, add bias, ReLU, store rows
+// Precision: kind::tf32 keeps 10 mantissa bits, which would miss the 1e-5 bound, so
+// both operands are split x = hi + lo (hi = cvt.rna.tf32, lo = x - hi, exact) and
+// the product is accumulated as hi*hi + hi*lo + lo*hi (3xTF32): 48 MMAs per tile.
+// ---------------------------------------------------------------------------
+namespace tc {
+constexpr uint32_t TM = 128, TK = 128, TN = 64;
+constexpr uint32_t A_BYTES = TM * TK * 4, B_BYTES = TN * TK * 4;
+constexpr uint32_t A_LBO = (TM / 8) * 128, A_SBO = 128;   // K-adjacent cores TM/8 cores apart; row groups adjacent
+constexpr uint32_t B_LBO = (TN / 8) * 128, B_SBO = 128;
+constexpr uint32_t SMEM_BYTES = 2 * A_BYTES + 2 * B_BYTES + 64;
+
+// byte offset of element (row r, k) in a K-major no-swizzle operand with R rows:
+// core matrix = 8 rows x 16 B; cores of one K-slice are contiguous over the row groups
+__host__ __device__ inline uint32_t op_off(uint32_t r, uint32_t k, uint32_t rows) {
+  return (k >> 2) * (rows / 8) * 128 + (r >> 3) * 128 + (r & 7) * 16 + (k & 3) * 4;
+}
+// UMMA shared-memory descriptor (sm_100): start >> 4, LBO >> 4 at bit 16, SBO >> 4 at bit 32,
+// version 1 at bit 46, layout type 0 (no swizzle) at bit 61
+__device__ __forceinline__ uint64_t smem_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+         (1ull << 46);
+}
+// instruction descriptor: D = F32 (bit 4), A = B = TF32 (2 << 7, 2 << 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((TN >> 3) << 17) | ((TM >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return u;
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+      :: "r"(tmem_d), "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "r"(taddr) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 1) sage_layer_tc_kernel(const float* __restrict__ h_in, float* __restrict__ h_out,
+                                                               const uint32_t* __restrict__ rowptr,
+                                                               const uint32_t* __restrict__ col,
+                                                               const uint8_t* __restrict__ Wcan,   // B_hi then B_lo
+                                                               const float* __restrict__ bias, uint32_t n_v) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA_hi = smem;
+  uint8_t* sA_lo = smem + A_BYTES;
+  uint8_t* sB = smem + 2 * A_BYTES;                      // B_hi, then B_lo
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + 2 * A_BYTES + 2 * B_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+
+  for (uint32_t i = tid; i < 2 * B_BYTES / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(sB)[i] = reinterpret_cast<const uint4*>(Wcan)[i];
+  if (warp == 0) {   // TMEM: 64 columns for the 128 x 64 fp32 accumulator
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" :: "r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(mbar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  uint32_t parity = 0;
+
+  for (uint32_t tile = blockIdx.x; tile * TM < n_v; tile += gridDim.x) {
+    // ---- gather: warp w builds rows 16w .. 16w+15 of the operand (hi and lo parts)
+    for (uint32_t rr = 0; rr < 16; ++rr) {
+      const uint32_t r = warp * 16 + rr, v = tile * TM + r;
+      float z[4] = {0.f, 0.f, 0.f, 0.f};
+      if (v < n_v) {
+        const uint32_t beg = rowptr[v], end = rowptr[v + 1];
+        float m0 = 0.f, m1 = 0.f;
+        for (uint32_t p = beg; p < end; ++p) {          // CSR order: deterministic sum
+          const float* hu = h_in + (size_t)col[p] * D;
+          m0 += hu[lane];
+          m1 += hu[32 + lane];
+        }
+        const float inv = end > beg ? 1.0f / (float)(end - beg) : 0.f;
+        const float* hv = h_in + (size_t)v * D;
+        z[0] = hv[lane]; z[1] = hv[32 + lane]; z[2] = m0 * inv; z[3] = m1 * inv;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t k = (uint32_t)q * 32 + lane;
+        const uint32_t hi = to_tf32(z[q]);
+        const uint32_t lo = to_tf32(z[q] - __uint_as_float(hi));
+        const uint32_t off = op_off(r, k, TM);
+        *reinterpret_cast<uint32_t*>(sA_hi + off) = hi;
+        *reinterpret_cast<uint32_t*>(sA_lo + off) = lo;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor-core (async proxy) reads
+    __syncthreads();
+    // ---- MMA: one thread, 3 passes x 16 K-steps of M128 N64 K8
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_hi = smem_u32(sA_hi), a_lo = smem_u32(sA_lo), b_hi = smem_u32(sB), b_lo = smem_u32(sB + B_BYTES);
+      const uint32_t pa[3] = {a_hi, a_hi, a_lo}, pb[3] = {b_hi, b_lo, b_hi};
+      uint32_t acc = 0;
+#pragma unroll
+      for (int ps = 0; ps < 3; ++ps) {
+        for (uint32_t ks = 0; ks < TK / 8; ++ks) {
+          const uint64_t da = smem_desc(pa[ps] + ks * 2 * A_LBO, A_LBO, A_SBO);
+          const uint64_t db = smem_desc(pb[ps] + ks * 2 * B_LBO, B_LBO, B_SBO);
+          mma_tf32(tmem_base, da, db, acc);
+          acc = 1;
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                   :: "r"(smem_u32(mbar)) : "memory");
+    }
+    // ---- epilogue: warps 0..3 own TMEM lanes 32w .. 32w+31
+    if (warp < 4) {
+      uint32_t done = 0;
+      while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(smem_u32(mbar)), "r"(parity) : "memory");
+      }
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t v = tile * TM + warp * 32 + lane;
+      float* orow = h_out + (size_t)v * D;
+#pragma unroll
+      for (uint32_t c = 0; c < TN; c += 16) {
+        uint32_t acc[16];
+        tmem_ld16(tmem_base + ((warp * 32u) << 16) + c, acc);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (v < n_v) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 o;
+            o.x = fmaxf(__uint_as_float(acc[j + 0]) + bias[c + j + 0], 0.f);
+            o.y = fmaxf(__uint_as_float(acc[j + 1]) + bias[c + j + 1], 0.f);
+            o.z = fmaxf(__uint_as_float(acc[j + 2]) + bias[c + j + 2], 0.f);
+            o.w = fmaxf(__uint_as_float(acc[j + 3]) + bias[c + j + 3], 0.f);
+            *reinterpret_cast<float4*>(orow + c + j) = o;
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    parity ^= 1u;
+    __syncthreads();   // operand tile and accumulator are free again
+  }
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" :: "r"(tmem_base) : "memory");
+}
+}  // namespace tc
+
 // docs/SPEC.md §4/§5 on the device, float64
 __device__ __forceinline__ double bucket_lo(uint32_t b) {
   if (b == 0) return 0.0;
@@ -232,6 +410,8 @@ struct alz_gnn_state {
   unsigned long long* d_stats = nullptr;
   float *d_h[3] = {nullptr, nullptr, nullptr}, *d_W[2] = {nullptr, nullptr}, *d_b[2] = {nullptr, nullptr};
   float *d_a = nullptr, *d_scores = nullptr;
+  uint8_t* d_Wcan[2] = {nullptr, nullptr};   // per layer: W^T split hi/lo in the UMMA operand layout (64 KB)
+  bool use_tc = true;
   float c = 0.f;
   void* d_tmp = nullptr;
   size_t tmp_bytes = 0;
@@ -280,6 +460,24 @@ static int gnn_init(alz_handle* h) {
     CK(cudaMemcpy(g->d_W[l], w.W[l].data(), 128 * D * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(g->d_b[l], w.b[l].data(), D * 4, cudaMemcpyHostToDevice));
   }
+  {
+    const char* simt = getenv("ALZ_GNN_SIMT");   // comparison knob: FP32 FFMA layer instead of tcgen05
+    g->use_tc = !(simt && simt[0] == '1');
+    std::vector<float> can(2 * tc::TN * tc::TK);
+    for (int l = 0; l < 2; ++l) {
+      for (uint32_t n = 0; n < tc::TN; ++n)
+        for (uint32_t k = 0; k < tc::TK; ++k) {
+          const float x = w.W[l][k * D + n];               // B[n][k] = W[k][n]
+          const float hi = tf32_round(x), lo = tf32_round(x - hi);
+          const uint32_t off = tc::op_off(n, k, tc::TN) / 4;
+          can[off] = hi;
+          can[tc::TN * tc::TK + off] = lo;
+        }
+      CK(cudaMalloc(&g->d_Wcan[l], 2 * tc::B_BYTES));
+      CK(cudaMemcpy(g->d_Wcan[l], can.data(), 2 * tc::B_BYTES, cudaMemcpyHostToDevice));
+    }
+    CK(cudaFuncSetAttribute(tc::sage_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+  }
   CK(cudaMalloc(&g->d_a, 132 * 4));
   CK(cudaMemcpy(g->d_a, w.a.data(), 132 * 4, cudaMemcpyHostToDevice));
   g->c = w.c;
@@ -293,7 +491,7 @@ void alz_internal_free_gnn(alz_handle* h) {
   cudaFree(g->d_flags); cudaFree(g->d_pos); cudaFree(g->d_iota); cudaFree(g->d_vals); cudaFree(g->d_src_idx);
   cudaFree(g->d_in_deg); cudaFree(g->d_rowptr); cudaFree(g->d_col); cudaFree(g->d_sorted_edge); cudaFree(g->d_stats);
   for (int i = 0; i < 3; ++i) cudaFree(g->d_h[i]);
-  for (int l = 0; l < 2; ++l) { cudaFree(g->d_W[l]); cudaFree(g->d_b[l]); }
+  for (int l = 0; l < 2; ++l) { cudaFree(g->d_W[l]); cudaFree(g->d_b[l]); cudaFree(g->d_Wcan[l]); }
   cudaFree(g->d_a); cudaFree(g->d_scores); cudaFree(g->d_tmp);
   delete g;
   h->gnn = nullptr;
@@ -336,8 +534,15 @@ static int gnn_run(alz_handle* h) {
   exclusive_scan_u32(g->d_tmp, g->tmp_bytes, g->d_in_deg, g->d_rowptr, n_v + 1, s);
   // features, layers, scores
   node_features_kernel<<<grid, 256, 0, s>>>(g->d_nodes, g->d_stats, n_v, g->d_h[0]);
-  sage_layer_kernel<<<grid, 256, 0, s>>>(g->d_h[0], g->d_h[1], g->d_rowptr, g->d_col, g->d_W[0], g->d_b[0], n_v);
-  sage_layer_kernel<<<grid, 256, 0, s>>>(g->d_h[1], g->d_h[2], g->d_rowptr, g->d_col, g->d_W[1], g->d_b[1], n_v);
+  for (int l = 0; l < 2; ++l) {
+    if (g->use_tc) {
+      const unsigned tiles = (n_v + tc::TM - 1) / tc::TM;
+      tc::sage_layer_tc_kernel<<<std::min<unsigned>(tiles, (unsigned)h->sms), 256, tc::SMEM_BYTES, s>>>(
+          g->d_h[l], g->d_h[l + 1], g->d_rowptr, g->d_col, g->d_Wcan[l], g->d_b[l], n_v);
+    } else {
+      sage_layer_kernel<<<grid, 256, 0, s>>>(g->d_h[l], g->d_h[l + 1], g->d_rowptr, g->d_col, g->d_W[l], g->d_b[l], n_v);
+    }
+  }
   edge_score_kernel<<<grid, 256, 0, s>>>(h->d_out, n_e, g->d_src_idx, g->d_dst_key, g->d_h[2], g->d_a, g->c,
                                          g->d_scores);
   CK(cudaGetLastError());
