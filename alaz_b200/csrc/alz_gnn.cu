@@ -321,6 +321,7 @@ __global__ void __launch_bounds__(256, 1) sage_layer_tc_kernel(const float* __re
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                      : "=r"(done) : "r"(smem_u32(mbar)), "r"(parity) : "memory");
       }
+      __syncwarp();   // lane 0 of warp 0 comes from the MMA issue: .sync.aligned loads need the whole warp together
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t v = tile * TM + warp * 32 + lane;
       float* orow = h_out + (size_t)v * D;
