@@ -57,8 +57,12 @@ static int alloc_table(alz_handle* h, AccTable* t, uint32_t max_rows, uint32_t* 
   CK(cudaMalloc(&t->err5xx, rows * 8));
   t->count = nullptr;
   t->row_cnt = nullptr;
+  t->row_aux = nullptr;
   if (with_count) CK(cudaMalloc(&t->count, rows * 8));
-  else { CK(cudaMalloc(&t->row_cnt, rows * 4)); CK(cudaMemsetAsync(t->row_cnt, 0, rows * 4, h->stream)); }
+  else {
+    CK(cudaMalloc(&t->row_cnt, rows * 4)); CK(cudaMemsetAsync(t->row_cnt, 0, rows * 4, h->stream));
+    CK(cudaMalloc(&t->row_aux, rows * 4));
+  }
   CK(cudaMalloc(&t->hist, rows * ALZ_NB * 4));
   CK(cudaMemsetAsync(t->dict, 0xFF, (size_t)dict_cap * sizeof(DictEnt), h->stream));
   CK(cudaMemsetAsync(t->lat_sum, 0, rows * 8, h->stream));
@@ -69,7 +73,7 @@ static int alloc_table(alz_handle* h, AccTable* t, uint32_t max_rows, uint32_t* 
 }
 static void free_table(AccTable* t) {
   cudaFree(t->dict); cudaFree(t->row_key); cudaFree(t->lat_sum); cudaFree(t->err5xx); cudaFree(t->count);
-  cudaFree(t->row_cnt);
+  cudaFree(t->row_cnt); cudaFree(t->row_aux);
   cudaFree(t->hist);
   memset(t, 0, sizeof(*t));
 }

@@ -121,6 +121,7 @@ struct AccTable {
   uint64_t* err5xx;   // [max_rows + 1]
   uint64_t* count;    // [max_rows + 1] (edge table only; pair tables derive it from hist)
   uint32_t* row_cnt;  // [max_rows + 1] (pair tables only) events of the row at the last fold, saturated
+  uint32_t* row_aux;  // [max_rows + 1] (pair tables only) edge row found by fold_resolve_kernel
   uint32_t* hist;     // [(max_rows + 1) * ALZ_NB]
 };
 

@@ -388,13 +388,42 @@ __global__ void __launch_bounds__(256) edge_score_kernel(const alz_edge_out* __r
     float acc = hu[lane] * a[lane] + hu[32 + lane] * a[32 + lane] + hv[lane] * a[64 + lane] +
                 hv[32 + lane] * a[96 + lane];
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    // quantiles with the whole warp: lane l owns buckets 2l and 2l+1; an inclusive scan of the
+    // (exactly representable) counts finds the bucket each quantile falls into, then the one
+    // lane that owns it interpolates exactly like hist_quantile() / SPEC §5
+    const double c0 = (double)e[i].hist[2 * lane], c1 = (double)e[i].hist[2 * lane + 1];
+    double incl = c0 + c1;
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if ((int)lane >= o) incl += t;
+    }
+    const double total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    const double before = incl - (c0 + c1);
+    double qv[2];
+#pragma unroll
+    for (int qi = 0; qi < 2; ++qi) {
+      const double target = (qi == 0 ? 0.5 : 0.99) * total;
+      // first bucket with c > 0 and cum + c >= target
+      const bool h0 = c0 > 0.0 && before + c0 >= target;
+      const bool h1 = c1 > 0.0 && before + c0 + c1 >= target;
+      const uint32_t m = __ballot_sync(0xFFFFFFFFu, h0 || h1);
+      double val = total > 0.0 ? bucket_hi(ALZ_NB - 1) : 0.0;
+      const int owner = m ? __ffs(m) - 1 : 0;
+      if (m && (int)lane == owner) {
+        const uint32_t b = h0 ? 2u * lane : 2u * lane + 1u;
+        const double cum = h0 ? before : before + c0;
+        const double cb = h0 ? c0 : c1;
+        double f = (target - cum) / cb;
+        if (f < 0.0) f = 0.0;
+        val = bucket_lo(b) + f * (bucket_hi(b) - bucket_lo(b));
+      }
+      qv[qi] = __shfl_sync(0xFFFFFFFFu, val, owner);
+    }
     if (lane == 0) {
-      uint64_t total = 0;
-      for (int b = 0; b < ALZ_NB; ++b) total += e[i].hist[b];
       const float f0 = (float)log1p((double)e[i].count);
       const float f1 = (float)ratio(e[i].err5xx, e[i].count);
-      const float f2 = (float)log1p(hist_quantile(e[i].hist, total, 0.5));
-      const float f3 = (float)log1p(hist_quantile(e[i].hist, total, 0.99));
+      const float f2 = (float)log1p(qv[0]);
+      const float f3 = (float)log1p(qv[1]);
       const float z = acc + f0 * a[128] + f1 * a[129] + f2 * a[130] + f3 * a[131] + c;
       scores[i] = 1.0f / (1.0f + expf(-z));
     }

@@ -134,8 +134,30 @@ __global__ void __launch_bounds__(256) ingest_eager_kernel(const alz_l7_rec* __r
 // resolve (saddr,daddr) -> edge, add the row into the edge accumulators and
 // zero it. The caller clears the pair dictionary afterwards.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) fold_pairs_kernel(AccTable pairs, bool rev, const EpEntry* __restrict__ ep,
-                                                         uint32_t ep_mask, AccTable edges, Counters* ctr,
+// pass 1, a thread per pair row: resolve and find the edge row. All the dependent
+// table/dictionary probes of a pair sit in one thread, 32 pairs per warp in flight
+// (the one-warp-per-row version spent its time in lane 0's probe chain).
+__global__ void __launch_bounds__(256) fold_resolve_kernel(AccTable pairs, bool rev, const EpEntry* __restrict__ ep,
+                                                           uint32_t ep_mask, AccTable edges) {
+  const uint32_t n_rows = min(*pairs.n_rows, pairs.max_rows);
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= n_rows; i += stride) {
+    const uint32_t row = (i == n_rows) ? pairs.max_rows : i;
+    const uint64_t key = (row == pairs.max_rows) ? kEmptyKey : pairs.row_key[row];
+    if (row == pairs.max_rows) {                               // the sentinel row exists even when unused
+      uint32_t any = 0;
+      for (int b = 0; b < ALZ_NB; ++b) any |= pairs.hist[(size_t)row * ALZ_NB + b];
+      if (any == 0u) { pairs.row_aux[row] = kDropRow; continue; }
+    }
+    uint64_t ekey = 0;
+    uint32_t erow = kDropRow;                                  // source is not a pod: data.go:829-832
+    if (resolve_edge(ep, ep_mask, (uint32_t)(key >> 32), (uint32_t)key, rev, &ekey)) erow = find_or_insert(edges, ekey);
+    pairs.row_aux[row] = erow;
+  }
+}
+
+// pass 2, a warp per pair row: add the row into its edge row and zero it
+__global__ void __launch_bounds__(256) fold_pairs_kernel(AccTable pairs, AccTable edges, Counters* ctr,
                                                          uint32_t* __restrict__ hot_bins) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warps_per_grid = (gridDim.x * blockDim.x) >> 5;
@@ -153,22 +175,8 @@ __global__ void __launch_bounds__(256) fold_pairs_kernel(AccTable pairs, bool re
       pairs.row_cnt[row] = c32;
       if (hot_bins != nullptr) atomicAdd(&hot_bins[count_bin(c32)], 1u);
     }
-    const uint64_t key = (row == pairs.max_rows) ? kEmptyKey : pairs.row_key[row];
-    uint64_t ekey = 0;
-    uint32_t erow = kLostRow;
-    int ok = 0;
-    if (lane == 0) {
-      ok = resolve_edge(ep, ep_mask, (uint32_t)(key >> 32), (uint32_t)key, rev, &ekey) ? 1 : 0;
-      if (ok) {
-        erow = find_or_insert(edges, ekey);
-        if (erow >= kLostRow) atomicAdd(&ctr->capacity_events, (unsigned long long)cnt);
-      } else {
-        atomicAdd(&ctr->src_unresolved, (unsigned long long)cnt);   // data.go:829-832
-      }
-    }
-    ok = __shfl_sync(0xFFFFFFFFu, ok, 0);
-    erow = __shfl_sync(0xFFFFFFFFu, erow, 0);
-    if (ok && erow < kLostRow) {
+    const uint32_t erow = pairs.row_aux[row];
+    if (erow < kDropRow) {
       if (h0) atomicAdd(&edges.hist[(size_t)erow * ALZ_NB + lane], h0);
       if (h1) atomicAdd(&edges.hist[(size_t)erow * ALZ_NB + 32u + lane], h1);
       if (lane == 0) {
@@ -177,6 +185,9 @@ __global__ void __launch_bounds__(256) fold_pairs_kernel(AccTable pairs, bool re
         const uint64_t e = pairs.err5xx[row];
         if (e) atomicAdd((unsigned long long*)&edges.err5xx[erow], (unsigned long long)e);
       }
+    } else if (lane == 0) {
+      if (erow == kDropRow) atomicAdd(&ctr->src_unresolved, (unsigned long long)cnt);
+      else atomicAdd(&ctr->capacity_events, (unsigned long long)cnt);
     }
     pairs.hist[(size_t)row * ALZ_NB + lane] = 0u;
     pairs.hist[(size_t)row * ALZ_NB + 32u + lane] = 0u;
@@ -305,7 +316,8 @@ void launch_ingest_eager(const alz_l7_rec* recs, uint64_t n, const EpEntry* ep, 
 }
 void launch_fold_pairs(const AccTable& pairs, bool rev, const EpEntry* ep, uint32_t ep_mask,
                        const AccTable& edges, Counters* ctr, uint32_t* hot_bins, int sms, cudaStream_t s) {
-  fold_pairs_kernel<<<grid_for(sms, 8), 256, 0, s>>>(pairs, rev, ep, ep_mask, edges, ctr, hot_bins);
+  fold_resolve_kernel<<<grid_for(sms, 4), 256, 0, s>>>(pairs, rev, ep, ep_mask, edges);
+  fold_pairs_kernel<<<grid_for(sms, 8), 256, 0, s>>>(pairs, edges, ctr, hot_bins);
 }
 void launch_iota(uint32_t* out, uint32_t n, int sms, cudaStream_t s) {
   if (n == 0) return;
