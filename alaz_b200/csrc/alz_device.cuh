@@ -43,6 +43,14 @@ __host__ __device__ __forceinline__ uint32_t owner_rank(uint32_t saddr, uint32_t
   return (uint32_t)(((uint64_t)hash32(saddr ^ 0xA1A2B200u) * nranks) >> 32);
 }
 
+// cheap 32-bit hash of a socket pair for the pair dictionaries and the per-CTA table (the per-event
+// path pays for this once; hash64 costs two 64-bit multiplies)
+__host__ __device__ __forceinline__ uint32_t pair_hash(uint64_t key) {
+  uint32_t h = (uint32_t)(key >> 32) * 0x9E3779B1u ^ (uint32_t)key * 0x85EBCA6Bu;
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 13;
+  return h;
+}
+
 // ---- packed edge key (docs/SPEC.md §3) -----------------------------------------
 // One end of every edge is the pod that setFromToV2 resolved from saddr.
 //   bit 63      rev: 0 = pod is From, 1 = pod is To (row was reversed)
@@ -177,7 +185,7 @@ constexpr uint32_t kDropRow = 0xFFFFFFFDu;
 __device__ __forceinline__ uint32_t find_or_insert_pair(const AccTable& t, uint64_t key,
                                                         const EpEntry* __restrict__ ep, uint32_t ep_mask) {
   if (key == kEmptyKey) return t.max_rows;
-  uint32_t slot = (uint32_t)hash64(key) & t.dict_mask;
+  uint32_t slot = pair_hash(key) & t.dict_mask;
   bool checked = false;
 #pragma unroll 1
   for (uint32_t p = 0; p < kMaxProbe; ++p) {

@@ -40,7 +40,7 @@ struct Smem {
 };
 
 __device__ __forceinline__ uint32_t bucket_of(uint64_t key, bool rv) {
-  const uint32_t hb = (uint32_t)(hash64(key) >> 40);
+  const uint32_t hb = pair_hash(key) >> 20;   // high bits: independent of the dictionary's low-bit slot
   return rv ? kFwdBuckets + (hb & (kRevBuckets - 1u)) : (hb & (kFwdBuckets - 1u));
 }
 
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(kThreads, 1) ingest_pairs_v4_kernel(const alz_
     for (int u = 0; u < kUnroll; ++u) {
       g[u] = e[u].act && ss[u] < 0;
       const AccTable& t = e[u].rev ? rev : fwd;
-      const uint32_t home = (uint32_t)hash64(e[u].key) & t.dict_mask;
+      const uint32_t home = pair_hash(e[u].key) & t.dict_mask;
       ent[u] = make_uint4(0u, 0u, 0u, 0u);
       if (g[u]) ent[u] = __ldcg(reinterpret_cast<const uint4*>(&t.dict[home]));
     }
