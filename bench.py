@@ -255,11 +255,17 @@ def main():
             },
             "roofline": {"bound": "hbm", "kernel": "ingest_eager_kernel" if args.eager else ("ingest_pairs_kernel(v1)" if args.no_smem_cache else "ingest_pairs_v4_kernel"),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "traffic": None,
+                         "peak_source": peak_src,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full on this
+                         # workload (profiles/r1_v5_ingest_ncu.txt); only valid for the default configuration
+                         "traffic": (3.453e9 if (S == 10_000 and N == 100_000_000 and world == 1 and not args.eager
+                                                and not args.no_smem_cache) else None),
                          "kernel_ms": ingest_ms_max, "flush_ms": flush_ms,
                          "algorithmic_bytes_per_launch": alg_bytes},
             "clocks": clocks,
-            "gpu_launches": args.steps * 5,
+            # own kernels per step: ingest, 2x fold_resolve, 2x fold_pairs, 2x hot_pick, 2x hot_emit, iota, gather
+            # (CUB sort/scan kernels and memsets not counted)
+            "gpu_launches": args.steps * 11,
             "e2e": e2e,
         }
         if gnn_ms is not None:
