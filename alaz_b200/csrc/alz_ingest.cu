@@ -28,7 +28,9 @@ namespace alz {
 
 namespace {
 
-constexpr int kRowWords = ALZ_NB + 3;   // 64 hist cells, lat_lo, lat_hi, err5xx (odd stride: bank spread)
+constexpr int kLatSub = 4;              // latency sub-accumulators per row, picked by lane: every event of a pair adds to
+                                        // its latency sum, so a hot pair's lanes would all serialise on one word
+constexpr int kRowWords = ALZ_NB + 2 * kLatSub + 1;   // 64 hist cells, 4 x (lat_lo, lat_hi), err5xx = 73 (odd stride)
 constexpr uint32_t kFwdBuckets = 128, kRevBuckets = 16, kWays = 4;
 constexpr uint32_t kSlots = (kFwdBuckets + kRevBuckets) * kWays;
 constexpr uint32_t kQueue = 64;          // slow-path queue entries per warp (ring)
@@ -68,11 +70,12 @@ __device__ __forceinline__ int smem_admit(const Smem& s, uint32_t bucket, uint64
 __device__ __forceinline__ void smem_accumulate(const Smem& s, int slot, uint32_t bucket, uint64_t dur, bool err) {
   uint32_t* row = s.rows + (size_t)slot * kRowWords;
   atomicAdd(&row[bucket], 1u);
+  uint32_t* lat = row + ALZ_NB + 2 * (threadIdx.x & (kLatSub - 1));
   const uint32_t lo = (uint32_t)dur;
-  const uint32_t old = atomicAdd(&row[ALZ_NB], lo);
+  const uint32_t old = atomicAdd(&lat[0], lo);
   const uint32_t hi = (uint32_t)(dur >> 32) + ((old + lo < old) ? 1u : 0u);
-  if (hi) atomicAdd(&row[ALZ_NB + 1], hi);
-  if (err) atomicAdd(&row[ALZ_NB + 2], 1u);
+  if (hi) atomicAdd(&lat[1], hi);
+  if (err) atomicAdd(&row[ALZ_NB + 2 * kLatSub], 1u);
 }
 
 struct Ev {
@@ -146,9 +149,11 @@ __device__ __forceinline__ void smem_drain(const Smem& s, uint32_t first, uint32
     if (h0) atomicAdd(&g.hist[(size_t)grow * ALZ_NB + lane], h0);
     if (h1) atomicAdd(&g.hist[(size_t)grow * ALZ_NB + 32u + lane], h1);
     if (lane == 0) {
-      const uint64_t lat = ((uint64_t)row[ALZ_NB + 1] << 32) + row[ALZ_NB];
+      uint64_t lat = 0;
+      for (int q = 0; q < kLatSub; ++q) lat += ((uint64_t)row[ALZ_NB + 2 * q + 1] << 32) + row[ALZ_NB + 2 * q];
       if (lat) atomicAdd((unsigned long long*)&g.lat_sum[grow], (unsigned long long)lat);
-      if (row[ALZ_NB + 2]) atomicAdd((unsigned long long*)&g.err5xx[grow], (unsigned long long)row[ALZ_NB + 2]);
+      const uint32_t er = row[ALZ_NB + 2 * kLatSub];
+      if (er) atomicAdd((unsigned long long*)&g.err5xx[grow], (unsigned long long)er);
     }
   }
 }

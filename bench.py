@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--services", type=int, default=10_000)
     ap.add_argument("--events", type=int, default=100_000_000, help="events per GPU per step")
-    ap.add_argument("--cpu-sample", type=int, default=8_000_000, help="events timed on the CPU arm")
+    ap.add_argument("--cpu-sample", type=int, default=32_000_000, help="events timed on the CPU arm")
     ap.add_argument("--eager", action="store_true", help="ALZ_CFG_EAGER_JOIN plan")
     ap.add_argument("--no-smem-cache", action="store_true", help="ingest v1: global reductions only")
     ap.add_argument("--no-e2e", action="store_true")
