@@ -32,7 +32,7 @@ def load(rebuild=False):
     global _lib
     if _lib is not None and not rebuild:
         return _lib
-    path = _build.LIB
+    path = os.environ.get("ALZ_LIB_PATH") or _build.LIB   # ALZ_LIB_PATH: A/B runs of two builds on one box
     if rebuild or not os.path.exists(path):
         path = _build.build(force=rebuild)
     L = C.CDLL(path, mode=C.RTLD_GLOBAL)

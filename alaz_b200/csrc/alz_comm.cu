@@ -90,6 +90,28 @@ __device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t* __restrict__
   return lo;
 }
 
+// union of R sorted, pairwise disjoint key lists (segment r = gathered[r * pad .. + counts[r])):
+// out[sum of lower bounds] = key. *dup is set if a key occurs in two lists.
+__global__ void __launch_bounds__(256) merge_disjoint_kernel(const uint64_t* __restrict__ gathered, uint32_t pad,
+                                                             uint32_t R, const uint32_t* __restrict__ counts,
+                                                             uint64_t* __restrict__ out, uint32_t* __restrict__ dup) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < pad * R; t += stride) {
+    const uint32_t r = t / pad, i = t - r * pad;
+    if (i >= counts[r]) continue;
+    const uint64_t k = gathered[t];
+    uint32_t pos = i;
+    for (uint32_t q = 0; q < R; ++q) {
+      if (q == r) continue;
+      const uint64_t* seg = gathered + (size_t)q * pad;
+      const uint32_t lb = lower_bound_u64(seg, counts[q], k);
+      if (lb < counts[q] && seg[lb] == k) *dup = 1u;
+      pos += lb;
+    }
+    out[pos] = k;
+  }
+}
+
 // local live rows -> canonical array (zeroed beforehand); a warp per local edge; rows are zeroed
 __global__ void __launch_bounds__(256) scatter_canonical_kernel(AccTable edges, const uint64_t* __restrict__ keys,
                                                                 const uint32_t* __restrict__ rows, uint32_t n_local,
@@ -251,19 +273,30 @@ int alz_internal_merge_ranks(alz_handle* h) {
   if ((uint64_t)pad * R > c->gather_cap) return ALZ_E_CAPACITY;
   const uint32_t n_g = pad * (uint32_t)R;
 
-  // 2. keys: pad, all-gather, sort, unique
+  // 2. keys: pad, all-gather, merge. Each rank's list is sorted and, when the caller partitioned by
+  //    alz_owner_rank, the lists are disjoint: a key's place in the union is then the sum of its lower
+  //    bounds in the R lists - no sort. A key found on two ranks (caller routed one source to two ranks)
+  //    raises a flag and the general path (sort + unique) runs instead; the sums are right either way.
   pad_keys_kernel<<<grid, 256, 0, s>>>(h->d_keys[1], h->n_live, c->d_sorted, pad);
   NK(g_nccl.AllGather(c->d_sorted, c->d_gather, pad, ncclUint64, c->comm, s));
-  launch_iota(c->d_iota, n_g, h->sms, s);
-  sort_pairs(c->d_tmp, c->tmp_bytes, c->d_gather, c->d_sorted, c->d_iota, c->d_vals, n_g, s);
-  flag_heads_kernel<<<grid, 256, 0, s>>>(c->d_sorted, n_g, c->d_flags);
-  exclusive_scan_u32(c->d_tmp, c->tmp_bytes, c->d_flags, c->d_pos, n_g, s);
-  scatter_heads_kernel<<<grid, 256, 0, s>>>(c->d_sorted, c->d_flags, c->d_pos, n_g, c->d_can_keys);
-  uint32_t last[2];
-  CK(cudaMemcpyAsync(&last[0], c->d_pos + (n_g - 1), 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(&last[1], c->d_flags + (n_g - 1), 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemsetAsync(c->d_flags, 0, 4, s));
+  merge_disjoint_kernel<<<grid, 256, 0, s>>>(c->d_gather, pad, (uint32_t)R, c->d_counts, c->d_can_keys, c->d_flags);
+  uint32_t dup = 0;
+  CK(cudaMemcpyAsync(&dup, c->d_flags, 4, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
-  const uint32_t n_can = last[0] + last[1];
+  uint32_t n_can = (uint32_t)total;
+  if (dup) {
+    launch_iota(c->d_iota, n_g, h->sms, s);
+    sort_pairs(c->d_tmp, c->tmp_bytes, c->d_gather, c->d_sorted, c->d_iota, c->d_vals, n_g, s);
+    flag_heads_kernel<<<grid, 256, 0, s>>>(c->d_sorted, n_g, c->d_flags);
+    exclusive_scan_u32(c->d_tmp, c->tmp_bytes, c->d_flags, c->d_pos, n_g, s);
+    scatter_heads_kernel<<<grid, 256, 0, s>>>(c->d_sorted, c->d_flags, c->d_pos, n_g, c->d_can_keys);
+    uint32_t last[2];
+    CK(cudaMemcpyAsync(&last[0], c->d_pos + (n_g - 1), 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&last[1], c->d_flags + (n_g - 1), 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    n_can = last[0] + last[1];
+  }
   if (n_can > h->cfg.max_edges) return ALZ_E_CAPACITY;
 
   // 3. scatter local rows into the zeroed canonical array

@@ -3,8 +3,9 @@
 //
 // Each CTA keeps a private table of hot socket pairs in shared memory (the stream
 // is Zipf-skewed; without it the hottest pairs serialise in one L2 slice):
-//   * 4-way buckets: a lookup is two LDS.128 and four compares, no probe loop, so
-//     every lane of a warp walks the same instructions;
+//   * 4-way buckets with 16-bit tags: a lookup is one 8-byte load of the four tags and one
+//     key load for the lanes whose tag matched (two random LDS.128 per lane made the shared-
+//     memory pipe the limiter), no probe loop, every lane walks the same instructions;
 //   * which pairs are hot is fed back from the previous fold (hot_select kernels
 //     below): tier A = the ~64 hottest, inserted first so they cannot lose a
 //     bucket race, tier B = the rest up to the table size. With no history (first
@@ -36,34 +37,44 @@ constexpr uint32_t kSlots = (kFwdBuckets + kRevBuckets) * kWays;
 constexpr uint32_t kQueue = 64;          // slow-path queue entries per warp (ring)
 
 struct Smem {
-  uint64_t* keys;   // [kSlots]  bucket-major, 4 keys per bucket (32 B)
-  uint32_t* fill;   // [kFwdBuckets + kRevBuckets]
+  uint64_t* keys;   // [kSlots]  bucket-major, 4 keys per bucket
+  uint16_t* tags;   // [kSlots]  16 hash bits per way (0 = free): a lookup reads these 8 bytes, then one key
+  uint32_t* fill;   // [kFwdBuckets + kRevBuckets] ways handed out
   uint32_t* rows;   // [kSlots * kRowWords]
 };
 
-__device__ __forceinline__ uint32_t bucket_of(uint64_t key, bool rv) {
-  const uint32_t hb = pair_hash(key) >> 20;   // high bits: independent of the dictionary's low-bit slot
+__device__ __forceinline__ uint32_t bucket_of(uint32_t h, bool rv) {
+  const uint32_t hb = h >> 20;   // high bits: independent of the dictionary's low-bit slot
   return rv ? kFwdBuckets + (hb & (kRevBuckets - 1u)) : (hb & (kFwdBuckets - 1u));
 }
+__device__ __forceinline__ uint32_t tag_of(uint32_t h) { return (h & 0xFFFFu) | 1u; }
 
-// slot of key in its bucket or -1; two 16-byte shared loads
-__device__ __forceinline__ int smem_lookup(const Smem& s, uint32_t bucket, uint64_t key) {
-  const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(&s.keys[bucket * kWays]);
-  const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(&s.keys[bucket * kWays + 2]);
+// slot of key in its bucket or -1. One 8-byte load of the four tags, then the key of the first way whose
+// tag matches (only lanes with a match load it). A second way with an equal tag, or a tag that is visible
+// before its key, reads as a miss: the event then takes the global path, which is always correct.
+// *room = the bucket still has a free way.
+__device__ __forceinline__ int smem_lookup(const Smem& s, uint32_t bucket, uint64_t key, uint32_t tag, bool* room) {
+  const uint2 t = *reinterpret_cast<const uint2*>(&s.tags[bucket * kWays]);
+  const uint32_t t0 = t.x & 0xFFFFu, t1 = t.x >> 16, t2 = t.y & 0xFFFFu, t3 = t.y >> 16;
+  *room = t3 == 0u;              // ways fill in order 0..3
   int w = -1;
-  w = (b.y == key) ? 3 : w;
-  w = (b.x == key) ? 2 : w;
-  w = (a.y == key) ? 1 : w;
-  w = (a.x == key) ? 0 : w;
+  w = (t3 == tag) ? 3 : w;
+  w = (t2 == tag) ? 2 : w;
+  w = (t1 == tag) ? 1 : w;
+  w = (t0 == tag) ? 0 : w;
+  if (w >= 0 && s.keys[bucket * kWays + (uint32_t)w] != key) w = -1;
   return w < 0 ? -1 : (int)(bucket * kWays) + w;
 }
 
 // claim a free way of the bucket for key; -1 if the bucket is full
-__device__ __forceinline__ int smem_admit(const Smem& s, uint32_t bucket, uint64_t key) {
-  if (*reinterpret_cast<volatile uint32_t*>(&s.fill[bucket]) >= kWays) return -1;
+__device__ __forceinline__ int smem_admit(const Smem& s, uint32_t bucket, uint64_t key, uint32_t tag) {
   const uint32_t w = atomicAdd(&s.fill[bucket], 1u);
   if (w >= kWays) return -1;
   s.keys[bucket * kWays + w] = key;
+  // no fence here on purpose: a reader that sees the tag before the key takes it for a miss (still correct),
+  // and a __threadfence_block() anywhere in this kernel makes nvcc emit every global reduction as ATOMG
+  // (with return) instead of REDG: +70 % kernel time (profiles/r1_v6_tagfence_ncu.txt)
+  *reinterpret_cast<volatile uint16_t*>(&s.tags[bucket * kWays + w]) = (uint16_t)tag;
   return (int)(bucket * kWays + w);
 }
 
@@ -116,12 +127,12 @@ __device__ __forceinline__ void preload_hot(const Smem& s, const HotState* hot, 
   const uint32_t na = min(hot->n_a, (uint32_t)kHotA), nb = min(hot->n_b, (uint32_t)kHotB);
   for (uint32_t i = threadIdx.x; i < na; i += blockDim.x) {
     const uint64_t k = hot->keys_a[i];
-    if (k != kEmptyKey) smem_admit(s, bucket_of(k, rv), k);
+    if (k != kEmptyKey) { const uint32_t hh = pair_hash(k); smem_admit(s, bucket_of(hh, rv), k, tag_of(hh)); }
   }
   __syncthreads();
   for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
     const uint64_t k = hot->keys_b[i];
-    if (k != kEmptyKey) smem_admit(s, bucket_of(k, rv), k);
+    if (k != kEmptyKey) { const uint32_t hh = pair_hash(k); smem_admit(s, bucket_of(hh, rv), k, tag_of(hh)); }
   }
 }
 
@@ -184,7 +195,51 @@ __device__ __forceinline__ void slow_path_32(const uint64_t* q_key, const uint64
   __syncwarp();
 }
 
-template <int kThreads, int kUnroll, bool kPrefetch>
+// a fetched dictionary home slot waiting to be used
+struct Pend {
+  uint4 ent;       // the 16-byte DictEnt as loaded
+  uint64_t key, dur;
+  uint32_t meta;   // bit 31 valid, bit 9 5xx, bit 8 reversed, bits 0..7 latency bucket
+};
+
+// use the probes: a hit reduces into its row at once, anything else joins the warp's slow-path queue
+template <int kUnroll>
+__device__ __forceinline__ void consume_probes(const Pend* p, const AccTable& fwd, const AccTable& rev,
+                                               const EpEntry* __restrict__ ep, uint32_t ep_mask, uint64_t* q_key,
+                                               uint64_t* q_dur, uint32_t* q_meta, uint32_t& q_head, uint32_t& q_count,
+                                               uint32_t* lost, uint32_t* unresolved) {
+  const uint32_t lane = threadIdx.x & 31u;
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    const bool g = (p[u].meta & 0x80000000u) != 0u;
+    const bool rv = (p[u].meta & 0x100u) != 0u;
+    const uint64_t k = ((uint64_t)p[u].ent.y << 32) | p[u].ent.x;
+    const bool hit = g && k == p[u].key && p[u].ent.z < kDropRow && p[u].key != kEmptyKey;
+    if (hit) {
+      const AccTable& t = rv ? rev : fwd;
+      atomicAdd(&t.hist[(size_t)p[u].ent.z * ALZ_NB + (p[u].meta & 0xFFu)], 1u);
+      atomicAdd((unsigned long long*)&t.lat_sum[p[u].ent.z], (unsigned long long)p[u].dur);
+      if (p[u].meta & 0x200u) atomicAdd((unsigned long long*)&t.err5xx[p[u].ent.z], 1ull);
+    }
+    const bool slow = g && !hit;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, slow);
+    if (slow) {
+      const uint32_t pos = (q_head + q_count + __popc(m & ((1u << lane) - 1u))) & (kQueue - 1u);
+      q_key[pos] = p[u].key;
+      q_dur[pos] = p[u].dur;
+      q_meta[pos] = p[u].meta & 0x3FFu;
+    }
+    q_count += __popc(m);
+    __syncwarp();
+    if (q_count >= 32u) {
+      slow_path_32(q_key, q_dur, q_meta, q_head, 32u, fwd, rev, ep, ep_mask, lost, unresolved);
+      q_head = (q_head + 32u) & (kQueue - 1u);
+      q_count -= 32u;
+    }
+  }
+}
+
+template <int kThreads, int kUnroll, bool kPrefetch, bool kPipe>
 __global__ void __launch_bounds__(kThreads, 1) ingest_pairs_v4_kernel(const alz_l7_rec* __restrict__ recs, uint64_t n,
                                                                       AccTable fwd, AccTable rev, Counters* ctr,
                                                                       const HotState* hot_fwd, const HotState* hot_rev,
@@ -192,7 +247,8 @@ __global__ void __launch_bounds__(kThreads, 1) ingest_pairs_v4_kernel(const alz_
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Smem s;
   s.keys = reinterpret_cast<uint64_t*>(smem_raw);
-  s.fill = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kSlots * 8);
+  s.tags = reinterpret_cast<uint16_t*>(smem_raw + (size_t)kSlots * 8);
+  s.fill = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kSlots * 10);
   s.rows = s.fill + (kFwdBuckets + kRevBuckets);
   // per-warp slow-path queues behind the table
   uint8_t* qbase = reinterpret_cast<uint8_t*>(s.rows + (size_t)kSlots * kRowWords) + (size_t)(threadIdx.x >> 5) * kQueue * 20;
@@ -200,7 +256,7 @@ __global__ void __launch_bounds__(kThreads, 1) ingest_pairs_v4_kernel(const alz_
   uint64_t* q_dur = q_key + kQueue;
   uint32_t* q_meta = reinterpret_cast<uint32_t*>(q_dur + kQueue);
   uint32_t q_head = 0, q_count = 0;
-  for (uint32_t i = threadIdx.x; i < kSlots; i += kThreads) s.keys[i] = kEmptyKey;
+  for (uint32_t i = threadIdx.x; i < kSlots; i += kThreads) { s.keys[i] = kEmptyKey; s.tags[i] = 0; }
   for (uint32_t i = threadIdx.x; i < kFwdBuckets + kRevBuckets; i += kThreads) s.fill[i] = 0u;
   for (uint32_t i = threadIdx.x; i < kSlots * kRowWords; i += kThreads) s.rows[i] = 0u;
   __syncthreads();
@@ -212,6 +268,9 @@ __global__ void __launch_bounds__(kThreads, 1) ingest_pairs_v4_kernel(const alz_
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
 
   uint32_t not_request = 0, lost = 0, unresolved = 0;
+  Pend pend[kUnroll];
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) { pend[u].ent = make_uint4(0u, 0u, 0u, 0u); pend[u].key = 0; pend[u].dur = 0; pend[u].meta = 0u; }
   const uint32_t lane = threadIdx.x & 31u;
   const uint64_t stride = (uint64_t)gridDim.x * kThreads;
   const uint64_t first = (uint64_t)blockIdx.x * kThreads + (threadIdx.x & ~31u);
@@ -252,63 +311,50 @@ __global__ void __launch_bounds__(kThreads, 1) ingest_pairs_v4_kernel(const alz_
     }
     Ev e[kUnroll];
     int ss[kUnroll];
-    uint32_t sb[kUnroll];
+    uint32_t sb[kUnroll], hh[kUnroll];
+    bool room[kUnroll];
     // stage 1: decode, shared-memory lookup (no loop, no divergence)
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       e[u] = decode(r[u], live[u]);
       not_request += (live[u] && !e[u].act) ? 1u : 0u;
-      sb[u] = bucket_of(e[u].key, e[u].rev);
-      ss[u] = smem_lookup(s, sb[u], e[u].key);
+      hh[u] = pair_hash(e[u].key);
+      sb[u] = bucket_of(hh[u], e[u].rev);
+      ss[u] = smem_lookup(s, sb[u], e[u].key, tag_of(hh[u]), &room[u]);
       if (!e[u].act || e[u].key == kEmptyKey) ss[u] = -1;
     }
     // stage 2: first-come admission of misses while their bucket has room (rare once warm)
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u)
-      if (e[u].act && ss[u] < 0 && e[u].key != kEmptyKey) ss[u] = smem_admit(s, sb[u], e[u].key);
+      if (room[u] && e[u].act && ss[u] < 0 && e[u].key != kEmptyKey)
+        ss[u] = smem_admit(s, sb[u], e[u].key, tag_of(hh[u]));
     __syncwarp();
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u)
       if (ss[u] >= 0) smem_accumulate(s, ss[u], e[u].bucket, e[u].dur, e[u].err);
-    // stage 3: the rest goes to the global dictionary; fetch every home slot first
-    bool g[kUnroll];
-    uint4 ent[kUnroll];
+    // stage 3: the rest goes to the global dictionary. The home slots are fetched now and, with kPipe,
+    // consumed one iteration later, so the L2 round trip of the probe hides behind a whole iteration
+    Pend cur[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-      g[u] = e[u].act && ss[u] < 0;
+      const bool g = e[u].act && ss[u] < 0;
       const AccTable& t = e[u].rev ? rev : fwd;
-      const uint32_t home = pair_hash(e[u].key) & t.dict_mask;
-      ent[u] = make_uint4(0u, 0u, 0u, 0u);
-      if (g[u]) ent[u] = __ldcg(reinterpret_cast<const uint4*>(&t.dict[home]));
+      const uint32_t home = hh[u] & t.dict_mask;
+      cur[u].key = e[u].key;
+      cur[u].dur = e[u].dur;
+      cur[u].meta = g ? (0x80000000u | e[u].bucket | (e[u].rev ? 0x100u : 0u) | (e[u].err ? 0x200u : 0u)) : 0u;
+      cur[u].ent = make_uint4(0u, 0u, 0u, 0u);
+      if (g) cur[u].ent = __ldcg(reinterpret_cast<const uint4*>(&t.dict[home]));
     }
+    if (kPipe) {
+      consume_probes<kUnroll>(pend, fwd, rev, ep, ep_mask, q_key, q_dur, q_meta, q_head, q_count, &lost, &unresolved);
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const uint64_t k = ((uint64_t)ent[u].y << 32) | ent[u].x;
-      const bool hit = g[u] && k == e[u].key && ent[u].z < kDropRow && e[u].key != kEmptyKey;
-      if (hit) {
-        const AccTable& t = e[u].rev ? rev : fwd;
-        atomicAdd(&t.hist[(size_t)ent[u].z * ALZ_NB + e[u].bucket], 1u);
-        atomicAdd((unsigned long long*)&t.lat_sum[ent[u].z], (unsigned long long)e[u].dur);
-        if (e[u].err) atomicAdd((unsigned long long*)&t.err5xx[ent[u].z], 1ull);
-      }
-      // everything else waits in the warp's queue
-      const bool slow = g[u] && !hit;
-      const uint32_t m = __ballot_sync(0xFFFFFFFFu, slow);
-      if (slow) {
-        const uint32_t pos = (q_head + q_count + __popc(m & ((1u << lane) - 1u))) & (kQueue - 1u);
-        q_key[pos] = e[u].key;
-        q_dur[pos] = e[u].dur;
-        q_meta[pos] = e[u].bucket | (e[u].rev ? 0x100u : 0u) | (e[u].err ? 0x200u : 0u);
-      }
-      q_count += __popc(m);
-      __syncwarp();
-      if (q_count >= 32u) {
-        slow_path_32(q_key, q_dur, q_meta, q_head, 32u, fwd, rev, ep, ep_mask, &lost, &unresolved);
-        q_head = (q_head + 32u) & (kQueue - 1u);
-        q_count -= 32u;
-      }
+      for (int u = 0; u < kUnroll; ++u) pend[u] = cur[u];
+    } else {
+      consume_probes<kUnroll>(cur, fwd, rev, ep, ep_mask, q_key, q_dur, q_meta, q_head, q_count, &lost, &unresolved);
     }
   }
+  if (kPipe) consume_probes<kUnroll>(pend, fwd, rev, ep, ep_mask, q_key, q_dur, q_meta, q_head, q_count, &lost, &unresolved);
   if (q_count) slow_path_32(q_key, q_dur, q_meta, q_head, q_count, fwd, rev, ep, ep_mask, &lost, &unresolved);
   __syncthreads();
   smem_drain(s, 0u, kFwdBuckets * kWays, fwd, ep, ep_mask, &lost, &unresolved);
@@ -360,16 +406,16 @@ __global__ void __launch_bounds__(256) hot_emit_kernel(AccTable pairs, HotState*
 
 }  // namespace
 
-template <int kThreads, int kUnroll, bool kPrefetch>
+template <int kThreads, int kUnroll, bool kPrefetch, bool kPipe>
 static void launch_variant(const alz_l7_rec* recs, uint64_t n, const AccTable& fwd, const AccTable& rev, Counters* ctr,
                            const HotState* hot_fwd, const HotState* hot_rev, const EpEntry* ep, uint32_t ep_mask,
                            int sms, cudaStream_t s) {
-  const size_t smem = (size_t)kSlots * 8 + (size_t)(kFwdBuckets + kRevBuckets) * 4 + (size_t)kSlots * kRowWords * 4 +
+  const size_t smem = (size_t)kSlots * 10 + (size_t)(kFwdBuckets + kRevBuckets) * 4 + (size_t)kSlots * kRowWords * 4 +
                       (size_t)(kThreads / 32) * kQueue * 20;
   // per device (a process may drive several GPUs), so not cached in a static
-  cudaFuncSetAttribute(ingest_pairs_v4_kernel<kThreads, kUnroll, kPrefetch>,
+  cudaFuncSetAttribute(ingest_pairs_v4_kernel<kThreads, kUnroll, kPrefetch, kPipe>,
                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  ingest_pairs_v4_kernel<kThreads, kUnroll, kPrefetch><<<(unsigned)sms, kThreads, smem, s>>>(
+  ingest_pairs_v4_kernel<kThreads, kUnroll, kPrefetch, kPipe><<<(unsigned)sms, kThreads, smem, s>>>(
       recs, n, fwd, rev, ctr, hot_fwd, hot_rev, ep, ep_mask);
 }
 
@@ -380,11 +426,12 @@ void launch_ingest_pairs_v4(const alz_l7_rec* recs, uint64_t n, const AccTable& 
   // ALZ_INGEST_VARIANT: tuning knob for profiling runs (default = the measured best)
   static const int variant = [] { const char* v = getenv("ALZ_INGEST_VARIANT"); return v ? atoi(v) : 0; }();
   switch (variant) {
-    case 1: launch_variant<512, 4, true>(recs, n, fwd, rev, ctr, hot_fwd, hot_rev, ep, ep_mask, sms, s); break;
-    case 2: launch_variant<768, 2, true>(recs, n, fwd, rev, ctr, hot_fwd, hot_rev, ep, ep_mask, sms, s); break;
-    case 3: launch_variant<512, 4, false>(recs, n, fwd, rev, ctr, hot_fwd, hot_rev, ep, ep_mask, sms, s); break;
-    case 4: launch_variant<1024, 2, true>(recs, n, fwd, rev, ctr, hot_fwd, hot_rev, ep, ep_mask, sms, s); break;
-    default: launch_variant<1024, 2, false>(recs, n, fwd, rev, ctr, hot_fwd, hot_rev, ep, ep_mask, sms, s); break;
+    case 1: launch_variant<1024, 2, false, true>(recs, n, fwd, rev, ctr, hot_fwd, hot_rev, ep, ep_mask, sms, s); break;
+    case 2: launch_variant<768, 2, true, true>(recs, n, fwd, rev, ctr, hot_fwd, hot_rev, ep, ep_mask, sms, s); break;
+    case 3: launch_variant<768, 2, false, true>(recs, n, fwd, rev, ctr, hot_fwd, hot_rev, ep, ep_mask, sms, s); break;
+    case 4: launch_variant<1024, 2, true, false>(recs, n, fwd, rev, ctr, hot_fwd, hot_rev, ep, ep_mask, sms, s); break;
+    case 5: launch_variant<1024, 2, true, true>(recs, n, fwd, rev, ctr, hot_fwd, hot_rev, ep, ep_mask, sms, s); break;
+    default: launch_variant<1024, 2, false, false>(recs, n, fwd, rev, ctr, hot_fwd, hot_rev, ep, ep_mask, sms, s); break;
   }
 }
 

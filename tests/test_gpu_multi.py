@@ -19,8 +19,9 @@ def _ngpu():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
+@pytest.mark.parametrize("overlap", [False, True])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_ranks_merge_to_the_single_rank_oracle(world):
+def test_ranks_merge_to_the_single_rank_oracle(world, overlap):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     L = capi.load()
@@ -30,6 +31,11 @@ def test_ranks_merge_to_the_single_rank_oracle(world):
     o = ol.Oracle()
     o.load_tables(t.pod_ip, t.svc_ip)
     o.process(ev, 4)
+    if overlap:
+        # a caller that does NOT partition cleanly: the first 20k events reach every rank. The merge must
+        # notice keys present on several ranks and still return exact sums (general sort+unique path).
+        for _ in range(world - 1):
+            o.process(ev[:20_000])
     exp = o.edges()
     us = np.unique(ev["saddr"])
     own_of = dict(zip(us.tolist(), [L.alz_owner_rank(int(s), world) for s in us]))
@@ -48,6 +54,8 @@ def test_ranks_merge_to_the_single_rank_oracle(world):
             h._ck(L.alz_comm_init(h.h, world, rank, idbuf), "alz_comm_init")
             h.load_tables(t.pod_ip, t.svc_ip)
             mine = ev[owner == rank]
+            if overlap:
+                mine = np.concatenate([mine, ev[:20_000][owner[:20_000] != rank]])
             h.submit(mine[: len(mine) // 2])
             h.submit(mine[len(mine) // 2:])
             h.sync()
@@ -72,5 +80,5 @@ def test_ranks_merge_to_the_single_rank_oracle(world):
         assert len(w2) == 0
         # canonical order is the same on every rank
         assert w1.tobytes() == out[0][0].tobytes()
-    assert sum(out[r][2]["events_in"] for r in range(world)) == N
+    assert sum(out[r][2]["events_in"] for r in range(world)) == N + (20_000 * (world - 1) if overlap else 0)
     assert sum(out[r][2]["rows_emitted"] for r in range(world)) == int(exp["count"].sum())
