@@ -359,22 +359,6 @@ __device__ __forceinline__ double bucket_lo(uint32_t b) {
   return (b & 1u) ? base * 1.5 : base;
 }
 __device__ __forceinline__ double bucket_hi(uint32_t b) { return b == ALZ_NB - 1 ? (double)(1ull << 40) : bucket_lo(b + 1); }
-__device__ double hist_quantile(const uint32_t* __restrict__ hist, uint64_t total, double q) {
-  if (total == 0) return 0.0;
-  const double target = q * (double)total;
-  double cum = 0.0;
-  for (uint32_t b = 0; b < ALZ_NB; ++b) {
-    const double c = (double)hist[b];
-    if (c > 0.0 && cum + c >= target) {
-      double f = (target - cum) / c;
-      if (f < 0.0) f = 0.0;
-      return bucket_lo(b) + f * (bucket_hi(b) - bucket_lo(b));
-    }
-    cum += c;
-  }
-  return bucket_hi(ALZ_NB - 1);
-}
-
 __global__ void __launch_bounds__(256) edge_score_kernel(const alz_edge_out* __restrict__ e, uint32_t n_e,
                                                          const uint32_t* __restrict__ src_idx,
                                                          const uint64_t* __restrict__ dst_key,
