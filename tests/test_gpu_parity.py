@@ -256,3 +256,20 @@ def test_full_size_properties_config2():
     h.dev_free(d)
     t.close()
     h.close()
+
+
+@pytest.mark.parametrize("flags", PLANS)
+def test_committed_golden_fixture(flags):
+    """tests/golden/synth_small.npz: fixed vectors, independent of today's oracle build."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "synth_small.npz"))
+    h = capi.Handle(max_endpoints=1024, max_pairs=1 << 14, flags=flags)
+    h.load_tables(z["pod_ip"], z["svc_ip"])
+    ev = z["events"].view(abi.L7_REC)
+    h.submit(ev[:7777]); h.submit(ev[7777:])
+    got = h.flush()
+    exp = z["edges"].view(abi.EDGE_OUT)
+    assert edges_equal(got, exp), explain_diff(got, exp)
+    st = h.stats()
+    assert [st["events_in"], st["rows_emitted"], st["not_request"], st["src_unresolved"]] == z["stats"].tolist()
+    h.close()

@@ -236,3 +236,19 @@ def test_sockline_closed_last_entry_rules():
     ln2 = _Line()
     ln2.add(100, None)
     assert ln2.get(50) is None                         # :117-118 first entry is a close
+
+
+def test_committed_synthetic_fixture_still_matches_the_oracle():
+    # tests/golden/synth_small.npz (made by tests/golden/make_synth_golden.py)
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "synth_small.npz"))
+    o = ol.Oracle()
+    o.load_tables(z["pod_ip"], z["svc_ip"])
+    o.process(z["events"].view(abi.L7_REC))
+    assert edges_equal(o.edges(), z["edges"].view(abi.EDGE_OUT))
+    a = _py_oracle({int(ip): k for k, ip in enumerate(z["pod_ip"])}, {int(ip): k for k, ip in enumerate(z["svc_ip"])})
+    for r in z["events"].view(abi.L7_REC):
+        a.process_l7(r)
+    assert edges_equal(pyref_edges(a), z["edges"].view(abi.EDGE_OUT))
+    st = o.stats()
+    assert [st["events_in"], st["rows_emitted"], st["not_request"], st["src_unresolved"]] == z["stats"].tolist()
