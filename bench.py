@@ -38,8 +38,8 @@ ALG_BYTES_PER_EDGE = 296      # each live edge row written once per window (alz_
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--services", type=int, default=10_000)
     ap.add_argument("--events", type=int, default=100_000_000, help="events per GPU per step")
@@ -71,7 +71,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -80,7 +80,11 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.p.stdout:
-            self.rows.append([x.strip() for x in ln.strip().split(",")])
+            self.rows.append([time.perf_counter()] + [x.strip() for x in ln.strip().split(",")])
+
+    def mark(self):
+        """Samples from here on are 'under load' (the timed regions); earlier ones are kept as a fallback."""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if not self.p:
@@ -90,19 +94,23 @@ class ClockSampler:
             self.p.wait(timeout=2)
         except Exception:
             self.p.kill()
-        sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t_mark = getattr(self, "t_mark", 0.0)
+        loaded = [r for r in self.rows if r[0] >= t_mark]
+        rows, scope = (loaded, "timed regions (device-resident steps + e2e steps)") if loaded else \
+                      (self.rows, "whole run incl. warm-up (timed regions shorter than the sampling period)")
+        sm, mx, reasons = [], None, set()
+        for r in rows:
             try:
-                sm.append(float(r[0]))
-                mx = float(r[1])
-                for n, v in zip(names, r[2:6]):
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for n, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "scope": scope}
 
 
 def cpu_arm(services, n_events, seed, nthreads, steps=1, warmup=0):
@@ -196,12 +204,13 @@ def main():
         h.submit_device(d_ev, N)
         return h.flush_device()
 
-    for _ in range(args.warmup):
-        _, n_edges = step()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        _, n_edges = step()
+    barrier()
+    sampler.mark()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_all0.record(stream)
@@ -213,7 +222,6 @@ def main():
         ev[k][2].record(stream)
     t_all1.record(stream)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     total_ms = t_all0.elapsed_time(t_all1)
     ingest_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
     flush_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
@@ -233,6 +241,7 @@ def main():
     if not args.no_e2e:
         e2e = run_e2e(h, capi, abi, d_ev, N, n_edges, args, world, dist if world > 1 else None, torch)
 
+    clocks = sampler.stop() if rank == 0 else None
     gnn_ms = None
     if not args.no_gnn:
         gnn_ms = run_gnn(h, step, args, torch)
