@@ -70,5 +70,21 @@ def build_sim_test(force=False):
     return SIM_TEST
 
 
+HOST_UNIT = os.path.join(LIB_DIR, "alaz_host_unit_test")
+
+
+def build_host_unit_test():
+    root = os.path.dirname(HERE)
+    srcs = [os.path.join(root, "tests", "cpp", "host_unit_test.cc"), os.path.join(HERE, "host", "alaz_aggregator.cc")]
+    build()
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall"] + srcs + ["-L" + LIB_DIR, "-lalazgpu", "-Wl,-rpath," + LIB_DIR,
+                                                           "-Wl,-rpath,$ORIGIN", "-o", HOST_UNIT]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building alaz_host_unit_test")
+    return HOST_UNIT
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

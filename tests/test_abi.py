@@ -99,3 +99,10 @@ def test_product_never_references_the_oracle():
                     if re.search(r"oracle_lib|alz_oracle|liboracle|orc_process|ref_py", s):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_cpp_host_adapter_conversions_and_loud_failure():
+    exe = build.build_host_unit_test()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "host unit ok" in r.stdout
