@@ -178,7 +178,7 @@ def main():
     seed = 0xA1A20001
     topo = capi.Topo(S, seed=seed)
     flags = (abi.CFG_EAGER_JOIN if args.eager else 0) | (abi.CFG_NO_SMEM_CACHE if args.no_smem_cache else 0)
-    h = capi.Handle(device=local_rank, max_endpoints=4 * S, max_pairs=max(1 << 20, 16 * S),
+    h = capi.Handle(device=local_rank, max_endpoints=4 * S, max_pairs=max(1 << 20, 40 * S),
                     max_batch=1 << 22, flags=flags)
     stream = torch.cuda.Stream()          # a real stream: handle 0 would mean "library's own"
     torch.cuda.set_stream(stream)
