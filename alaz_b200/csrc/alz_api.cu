@@ -146,7 +146,7 @@ extern "C" int alz_create(const alz_config* cfg, alz_handle** out) {
   int rc;
   if (!(h->cfg.flags & ALZ_CFG_EAGER_JOIN)) {
     if ((rc = alloc_table(h, &h->pairs_fwd, h->cfg.max_pairs, &h->d_ctr->fwd_rows, false)) != ALZ_OK) return fail(rc);
-    if ((rc = alloc_table(h, &h->pairs_rev, std::max<uint32_t>(1024u, h->cfg.max_pairs >> 3), &h->d_ctr->rev_rows,
+    if ((rc = alloc_table(h, &h->pairs_rev, std::max<uint32_t>(1024u, h->cfg.max_pairs >> 1), &h->d_ctr->rev_rows,
                           false)) != ALZ_OK) return fail(rc);
   }
   if ((rc = alloc_table(h, &h->edges, h->cfg.max_edges, &h->d_ctr->edge_rows, true)) != ALZ_OK) return fail(rc);
