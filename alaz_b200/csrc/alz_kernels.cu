@@ -156,42 +156,57 @@ __global__ void __launch_bounds__(256) fold_resolve_kernel(AccTable pairs, bool 
   }
 }
 
-// pass 2, a warp per pair row: add the row into its edge row and zero it
+// pass 2, eight lanes per pair row (four rows per warp in flight): add the row into its edge row and
+// zero it. Each lane owns 8 histogram cells = two 16-byte loads; the one-warp-per-row version was bound
+// by its chain of dependent L2 round trips (profiles/r1_final_launches.csv: 0.15 ms per launch).
 __global__ void __launch_bounds__(256) fold_pairs_kernel(AccTable pairs, AccTable edges, Counters* ctr,
                                                          uint32_t* __restrict__ hot_bins) {
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31u, sl = lane & 7u;
+  const uint32_t groups_per_grid = (gridDim.x * blockDim.x) >> 3;
   const uint32_t n_rows = min(*pairs.n_rows, pairs.max_rows);
+  const uint32_t n_iter = (n_rows + 1u + groups_per_grid - 1u) / groups_per_grid;   // same trip count for every lane
+  uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
   // rows [0, n_rows) plus the sentinel row (index n_rows stands for row max_rows)
-  for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i <= n_rows; i += warps_per_grid) {
-    const uint32_t row = (i == n_rows) ? pairs.max_rows : i;
-    const uint32_t h0 = pairs.hist[(size_t)row * ALZ_NB + lane];
-    const uint32_t h1 = pairs.hist[(size_t)row * ALZ_NB + 32u + lane];
-    uint64_t cnt = (uint64_t)h0 + h1;
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
-    if (cnt == 0) continue;  // unused sentinel row (allocated rows always hold >= 1 event)
-    if (lane == 0 && row != pairs.max_rows && pairs.row_cnt != nullptr) {   // feedback for the next ingest
+  for (uint32_t it = 0; it < n_iter; ++it, i += groups_per_grid) {
+    const bool valid = i <= n_rows;
+    const uint32_t row = !valid ? 0u : (i == n_rows) ? pairs.max_rows : i;
+    uint4* cells = reinterpret_cast<uint4*>(pairs.hist + (size_t)row * ALZ_NB + sl * 8u);
+    uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
+    if (valid) { a = cells[0]; b = cells[1]; }
+    uint64_t cnt = (uint64_t)a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+    cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 1);
+    cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 2);
+    cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 4);
+    if (!valid || cnt == 0) continue;  // unused sentinel row (allocated rows always hold >= 1 event)
+    if (sl == 0 && row != pairs.max_rows && pairs.row_cnt != nullptr) {   // feedback for the next ingest
       const uint32_t c32 = cnt > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)cnt;
       pairs.row_cnt[row] = c32;
       if (hot_bins != nullptr) atomicAdd(&hot_bins[count_bin(c32)], 1u);
     }
     const uint32_t erow = pairs.row_aux[row];
     if (erow < kDropRow) {
-      if (h0) atomicAdd(&edges.hist[(size_t)erow * ALZ_NB + lane], h0);
-      if (h1) atomicAdd(&edges.hist[(size_t)erow * ALZ_NB + 32u + lane], h1);
-      if (lane == 0) {
+      uint32_t* dst = edges.hist + (size_t)erow * ALZ_NB + sl * 8u;
+      if (a.x) atomicAdd(dst + 0, a.x);
+      if (a.y) atomicAdd(dst + 1, a.y);
+      if (a.z) atomicAdd(dst + 2, a.z);
+      if (a.w) atomicAdd(dst + 3, a.w);
+      if (b.x) atomicAdd(dst + 4, b.x);
+      if (b.y) atomicAdd(dst + 5, b.y);
+      if (b.z) atomicAdd(dst + 6, b.z);
+      if (b.w) atomicAdd(dst + 7, b.w);
+      if (sl == 0) {
         atomicAdd((unsigned long long*)&edges.count[erow], (unsigned long long)cnt);
         atomicAdd((unsigned long long*)&edges.lat_sum[erow], (unsigned long long)pairs.lat_sum[row]);
         const uint64_t e = pairs.err5xx[row];
         if (e) atomicAdd((unsigned long long*)&edges.err5xx[erow], (unsigned long long)e);
       }
-    } else if (lane == 0) {
+    } else if (sl == 0) {
       if (erow == kDropRow) atomicAdd(&ctr->src_unresolved, (unsigned long long)cnt);
       else atomicAdd(&ctr->capacity_events, (unsigned long long)cnt);
     }
-    pairs.hist[(size_t)row * ALZ_NB + lane] = 0u;
-    pairs.hist[(size_t)row * ALZ_NB + 32u + lane] = 0u;
-    if (lane == 0) { pairs.lat_sum[row] = 0ull; pairs.err5xx[row] = 0ull; }
+    cells[0] = make_uint4(0u, 0u, 0u, 0u);
+    cells[1] = make_uint4(0u, 0u, 0u, 0u);
+    if (sl == 0) { pairs.lat_sum[row] = 0ull; pairs.err5xx[row] = 0ull; }
   }
 }
 
