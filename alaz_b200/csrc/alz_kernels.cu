@@ -222,14 +222,19 @@ __global__ void __launch_bounds__(256) iota_kernel(uint32_t* out, uint32_t n) {
 __global__ void __launch_bounds__(256) gather_edges_kernel(AccTable edges, const uint64_t* __restrict__ keys,
                                                            const uint32_t* __restrict__ rows, uint32_t n_live,
                                                            alz_edge_out* __restrict__ out, bool reset) {
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t warps_per_grid = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_live; i += warps_per_grid) {
+  // eight lanes per edge, four edges per warp in flight; a lane moves 8 histogram cells (2 x 16 bytes)
+  const uint32_t sl = threadIdx.x & 7u;
+  const uint32_t groups_per_grid = (gridDim.x * blockDim.x) >> 3;
+  for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; i < n_live; i += groups_per_grid) {
     const uint32_t row = rows[i];
     alz_edge_out* o = &out[i];
-    o->hist[lane] = edges.hist[(size_t)row * ALZ_NB + lane];
-    o->hist[32u + lane] = edges.hist[(size_t)row * ALZ_NB + 32u + lane];
-    if (lane == 0) {
+    uint4* cells = reinterpret_cast<uint4*>(edges.hist + (size_t)row * ALZ_NB + sl * 8u);
+    uint4* dst = reinterpret_cast<uint4*>(&o->hist[sl * 8u]);   // hist sits at byte 40 of a 296-byte row: 8-byte aligned only
+    const uint4 a = cells[0], b = cells[1];
+    uint2* d2 = reinterpret_cast<uint2*>(dst);
+    d2[0] = make_uint2(a.x, a.y); d2[1] = make_uint2(a.z, a.w);
+    d2[2] = make_uint2(b.x, b.y); d2[3] = make_uint2(b.z, b.w);
+    if (sl == 0) {
       uint8_t ft, tt; uint32_t f, t;
       unpack_edge_key(keys[i], &ft, &f, &tt, &t);
       o->from_type = ft; o->to_type = tt;
@@ -240,9 +245,9 @@ __global__ void __launch_bounds__(256) gather_edges_kernel(AccTable edges, const
       o->lat_sum_ns = edges.lat_sum[row];
     }
     if (reset) {
-      edges.hist[(size_t)row * ALZ_NB + lane] = 0u;
-      edges.hist[(size_t)row * ALZ_NB + 32u + lane] = 0u;
-      if (lane == 0) { edges.count[row] = 0ull; edges.err5xx[row] = 0ull; edges.lat_sum[row] = 0ull; }
+      cells[0] = make_uint4(0u, 0u, 0u, 0u);
+      cells[1] = make_uint4(0u, 0u, 0u, 0u);
+      if (sl == 0) { edges.count[row] = 0ull; edges.err5xx[row] = 0ull; edges.lat_sum[row] = 0ull; }
     }
   }
 }
