@@ -43,7 +43,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--services", type=int, default=10_000)
     ap.add_argument("--events", type=int, default=100_000_000, help="events per GPU per step")
-    ap.add_argument("--cpu-sample", type=int, default=32_000_000, help="events timed on the CPU arm")
+    ap.add_argument("--cpu-sample", type=int, default=None,
+                    help="events per step timed on the CPU arm (default: 32M, or less so that --impl reference ends in ~1-2 min)")
     ap.add_argument("--eager", action="store_true", help="ALZ_CFG_EAGER_JOIN plan")
     ap.add_argument("--no-smem-cache", action="store_true", help="ingest v1: global reductions only")
     ap.add_argument("--no-e2e", action="store_true")
@@ -136,6 +137,8 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
+    if args.cpu_sample is None:   # bounded: ~400M events in total over all steps, 2M..32M per step
+        args.cpu_sample = max(2_000_000, min(32_000_000, 400_000_000 // max(1, args.steps + args.warmup)))
     v, n_edges, sec = cpu_arm(args.services, args.cpu_sample, 0xA1A20001, cores, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
@@ -162,6 +165,8 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return 0
+    if args.cpu_sample is None:
+        args.cpu_sample = 32_000_000
 
     import torch
     import torch.distributed as dist
