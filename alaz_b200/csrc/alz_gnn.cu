@@ -7,8 +7,9 @@
 //             order-independent, so the float features are deterministic)
 //   CSR     : in-edges grouped by destination (stable sort by dst index, row
 //             offsets = exclusive scan of the in-degrees)
-//   layer   : warp per node: mean of the in-neighbours' rows (coalesced 256-B
-//             row reads) -> [h_v || m_v] (128) x W (128 x 64) + b, ReLU
+//   layer   : mean of the in-neighbours' rows (coalesced 256-B row reads) ->
+//             [h_v || m_v] (128) x W (128 x 64) + b, ReLU; the GEMM runs on tcgen05
+//             (sage_layer_tc_kernel, 3xTF32), an FP32 FFMA version is kept for comparison
 //   score   : sigma(a . [h2_u || h2_v || e_uv] + c), e_uv from the edge's
 //             integers and float64 histogram quantiles
 #include <algorithm>

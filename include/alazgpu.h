@@ -201,8 +201,8 @@ int alz_submit_l7_raw(alz_handle* h, const void* host_bpf_l7_events, size_t n);
 
 /* ---- window result: the grouped rows ----------------------------------------
  * Folds pending pairs, (multi-GPU: merges all ranks, one all-reduce on the
- * accumulators), writes the live edges sorted by (from_type,from,to_type,to)
- * and resets the window. n_out is always set to the number of live edges; if
+ * accumulators), writes the live edges in ascending packed-key order
+ * (docs/SPEC.md §3; the same order on every rank) and resets the window. n_out is always set to the number of live edges; if
  * cap is too small returns ALZ_E_CAPACITY and keeps the window. */
 int alz_window_flush(alz_handle* h, alz_edge_out* out, size_t cap, size_t* n_out);
 /* as above but leaves the result on the device for alz_gnn_score / peers;
