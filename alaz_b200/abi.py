@@ -4,10 +4,11 @@ Pure data definitions (numpy dtypes + ctypes structs); no compute. The sizes
 are asserted against the C header in tests/test_abi.py.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = int(os.environ.get("ALZ_ABI_VERSION", "2"))   # override only to drive an older build for A/B timing
 NB = 64
 BPF_L7_EVENT_SIZE = 1096
 COMM_ID_BYTES = 128
@@ -34,6 +35,13 @@ L7_REC = np.dtype([
     ("duration_ns", "<u8"), ("write_time_ns", "<u8"),
 ])
 assert L7_REC.itemsize == 32
+
+L7_REC16 = np.dtype([
+    ("saddr", "<u4"), ("daddr", "<u4"), ("status", "<u2"), ("protocol", "u1"), ("method_flags", "u1"),
+    ("duration_ns", "<u4"),
+])
+assert L7_REC16.itemsize == 16
+REC16_DUR_OVERFLOW = 0x80
 
 TCP_REC = np.dtype([
     ("fd", "<u8"), ("timestamp_ns", "<u8"), ("pid", "<u4"), ("saddr", "<u4"),
@@ -71,7 +79,8 @@ class Stats(C.Structure):
         ("not_request", C.c_uint64), ("src_unresolved", C.c_uint64),
         ("pairs_live", C.c_uint64), ("edges_live", C.c_uint64),
         ("tcp_events_in", C.c_uint64), ("tcp_localhost_dropped", C.c_uint64),
-        ("_reserved", C.c_uint64 * 8),
+        ("capacity_events", C.c_uint64), ("windows", C.c_uint64),
+        ("_reserved", C.c_uint64 * 6),
     ]
 
     def as_dict(self):

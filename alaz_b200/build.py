@@ -8,9 +8,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libalazgpu.so")
 
-# alz_ext_stubs.cu only provides the entry points whose real file is absent
-SOURCES = ["alz_api.cu", "alz_kernels.cu", "alz_ingest.cu", "alz_sort.cu", "alz_comm.cu", "alz_gnn.cu", "alz_sock.cu",
-           "alz_ext_stubs.cu"]
+SOURCES = ["alz_api.cu", "alz_kernels.cu", "alz_ingest.cu", "alz_sort.cu", "alz_comm.cu", "alz_gnn.cu", "alz_sock.cu"]
 EXTRA = [os.path.join(HERE, "synth", "alz_synth_topo.c")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -37,10 +35,8 @@ def build(force=False, verbose=False):
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
-    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))] + EXTRA
-    defs = ["-DALZ_HAVE_" + os.path.splitext(s)[0].upper().replace("ALZ_", "")
-            for s in ("alz_comm.cu", "alz_gnn.cu", "alz_sock.cu") if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [nvcc] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + srcs + ["-o", LIB, "-ldl"]
+    srcs = [os.path.join(CSRC, s) for s in SOURCES] + EXTRA
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + srcs + ["-o", LIB, "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

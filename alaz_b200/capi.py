@@ -21,7 +21,8 @@ _lib = None
 EXPORTS = [
     "alz_create", "alz_destroy", "alz_strerror", "alz_last_cuda_error", "alz_set_stream", "alz_sync",
     "alz_table_upsert", "alz_table_erase", "alz_table_commit", "alz_submit_l7", "alz_submit_l7_device",
-    "alz_submit_l7_raw", "alz_window_flush", "alz_window_flush_device", "alz_get_stats", "alz_gnn_score",
+    "alz_submit_l7_packed", "alz_submit_l7_packed_device", "alz_pack_l7",
+    "alz_submit_l7_raw", "alz_window_flush", "alz_window_flush_device", "alz_window_fetch", "alz_get_stats", "alz_gnn_score",
     "alz_gnn_score_device", "alz_edge_quantiles", "alz_submit_tcp", "alz_sock_lookup", "alz_comm_unique_id", "alz_comm_init",
     "alz_owner_rank",
 ]
@@ -51,6 +52,11 @@ def load(rebuild=False):
         "alz_submit_l7": ([vp, vp, sz], i),
         "alz_submit_l7_device": ([vp, vp, sz], i),
         "alz_submit_l7_raw": ([vp, vp, sz], i),
+        "alz_submit_l7_packed": ([vp, vp, sz, vp, sz], i),
+        "alz_submit_l7_packed_device": ([vp, vp, sz, vp], i),
+        "alz_pack_l7": ([vp, sz, vp, vp, sz], C.c_long),
+        "alz_window_fetch": ([vp, vp, sz, C.POINTER(sz)], i),
+        "alz_pinned_alloc_local": ([vp, sz, pp], i),
         "alz_window_flush": ([vp, vp, sz, C.POINTER(sz)], i),
         "alz_window_flush_device": ([vp, pp, C.POINTER(sz)], i),
         "alz_get_stats": ([vp, C.POINTER(abi.Stats)], i),
@@ -78,6 +84,10 @@ def load(rebuild=False):
         "alz_synth_dev_fill_owned": ([vp, vp, u64, u32, u32, vp, u64, C.POINTER(u64), C.POINTER(u64)], i),
         "alz_synth_dev_destroy": ([vp, vp], i),
     }
+    if abi.ABI_VERSION < 2:    # A/B timing against a round-1 build (ALZ_LIB_PATH + ALZ_ABI_VERSION=1)
+        for k in ("alz_submit_l7_packed", "alz_submit_l7_packed_device", "alz_pack_l7", "alz_window_fetch",
+                  "alz_pinned_alloc_local"):
+            sig.pop(k)
     for name, (args, res) in sig.items():
         f = getattr(L, name)   # AttributeError = header/library mismatch: loud
         f.argtypes, f.restype = args, res
@@ -92,12 +102,16 @@ def _ptr(a):
 class PinnedBuffer:
     """Library-owned pinned host memory exposed as a numpy array."""
 
-    def __init__(self, n, dtype):
+    def __init__(self, n, dtype, handle=None):
+        """handle: allocate on the NUMA node next to that handle's GPU (alz_pinned_alloc_local)."""
         self.L = load()
         self.dtype = np.dtype(dtype)
         self.nbytes = int(n) * self.dtype.itemsize
         p = C.c_void_p()
-        rc = self.L.alz_pinned_alloc(max(self.nbytes, 1), C.byref(p))
+        if handle is not None and abi.ABI_VERSION >= 2:
+            rc = self.L.alz_pinned_alloc_local(handle.h, max(self.nbytes, 1), C.byref(p))
+        else:
+            rc = self.L.alz_pinned_alloc(max(self.nbytes, 1), C.byref(p))
         if rc != 0:
             raise AlzError(rc, "alz_pinned_alloc")
         self.ptr = p.value
@@ -171,6 +185,16 @@ class Handle:
     def submit_device(self, dev_ptr, n):
         self._ck(self.L.alz_submit_l7_device(self.h, C.c_void_p(dev_ptr), n), "alz_submit_l7_device")
 
+    def submit_packed(self, recs16, overflow=None):
+        recs16 = np.ascontiguousarray(recs16, dtype=abi.L7_REC16)
+        ovf = np.ascontiguousarray(overflow if overflow is not None else np.zeros(0, np.uint64), dtype=np.uint64)
+        self._ck(self.L.alz_submit_l7_packed(self.h, _ptr(recs16), len(recs16), _ptr(ovf) if len(ovf) else None,
+                                             len(ovf)), "alz_submit_l7_packed")
+
+    def submit_packed_ptr(self, host_ptr, n, ovf_ptr=None, n_ovf=0):
+        self._ck(self.L.alz_submit_l7_packed(self.h, C.c_void_p(host_ptr), n, C.c_void_p(ovf_ptr) if ovf_ptr else None,
+                                             n_ovf), "alz_submit_l7_packed")
+
     def submit_raw(self, raw):
         raw = np.ascontiguousarray(raw, dtype=np.uint8)
         n = raw.size // abi.BPF_L7_EVENT_SIZE
@@ -224,6 +248,22 @@ class Handle:
         out = np.zeros(n, dtype=dtype)
         self._ck(self.L.alz_memcpy_d2h(self.h, _ptr(out), C.c_void_p(dev_ptr), out.nbytes), "alz_memcpy_d2h")
         return out
+
+
+def pack_l7(recs):
+    """alz_pack_l7: 32-B records -> (16-B records, overflow durations)."""
+    L = load()
+    recs = np.ascontiguousarray(recs, dtype=abi.L7_REC)
+    out = np.zeros(len(recs), dtype=abi.L7_REC16)
+    cap = max(16, len(recs) // 64)
+    while True:
+        ovf = np.zeros(cap, dtype=np.uint64)
+        k = L.alz_pack_l7(_ptr(recs), len(recs), _ptr(out), _ptr(ovf), cap)
+        if k >= 0:
+            return out, ovf[:k].copy()
+        if cap >= len(recs):
+            raise AlzError(abi.E_INVAL, "alz_pack_l7")
+        cap = len(recs)
 
 
 class Topo:

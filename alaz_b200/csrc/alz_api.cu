@@ -4,6 +4,14 @@
 //
 // There is no CPU fallback anywhere in this file: without a CUDA device
 // alz_create fails with ALZ_E_NODEVICE.
+//
+// Threading (the reference calls this seam from 4*NumCPU goroutines,
+// aggregator/data.go:230-232): alz_submit_* may be called from many OS threads. Each call
+// takes a staging slot, copies into the slot's pinned buffer outside any shared lock, and
+// holds h->mu only while it enqueues its H2D copy and kernel. Flush / commit / stats take
+// h->mu for the whole call, so they are ordered after every submit that has returned.
+#include <sched.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -45,21 +53,30 @@ static bool is_lib_pinned(const void* p, size_t bytes) {
   return false;
 }
 
-static int alloc_table(alz_handle* h, AccTable* t, uint32_t max_rows, uint32_t* n_rows_dev, bool with_count) {
+static int alloc_table(alz_handle* h, AccTable* t, uint32_t max_rows, uint32_t* n_rows_dev, bool pair_table) {
+  memset(t, 0, sizeof(*t));
   t->max_rows = max_rows;
   t->n_rows = n_rows_dev;
   const uint32_t dict_cap = next_pow2(2ull * max_rows);
   t->dict_mask = dict_cap - 1;
-  const size_t rows = (size_t)max_rows + 1;
+  const size_t rows = (size_t)max_rows + 2;
   CK(cudaMalloc(&t->dict, (size_t)dict_cap * sizeof(DictEnt)));
   CK(cudaMalloc(&t->row_key, rows * 8));
   CK(cudaMalloc(&t->lat_sum, rows * 8));
   CK(cudaMalloc(&t->err5xx, rows * 8));
-  t->count = nullptr;
-  t->row_cnt = nullptr;
-  t->row_aux = nullptr;
-  if (with_count) CK(cudaMalloc(&t->count, rows * 8));
-  else {
+  if (!pair_table) {
+    CK(cudaMalloc(&t->count, rows * 8));
+    CK(cudaMemsetAsync(t->count, 0, rows * 8, h->stream));
+  } else {
+    // reversed rows are a few per cent of the traffic: a quarter-size dictionary is ample, and both
+    // dictionaries draw rows from the one pool
+    const uint32_t rev_cap = std::max<uint32_t>(1024u, dict_cap >> 2);
+    t->dict_rev_mask = rev_cap - 1;
+    CK(cudaMalloc(&t->dict_rev, (size_t)rev_cap * sizeof(DictEnt)));
+    CK(cudaMemsetAsync(t->dict_rev, 0xFF, (size_t)rev_cap * sizeof(DictEnt), h->stream));
+    CK(cudaMalloc(&t->row_rev, rows));
+    CK(cudaMemsetAsync(t->row_rev, 0, rows, h->stream));
+    CK(cudaMemsetAsync(t->row_rev + max_rows + 1, 1, 1, h->stream));   // sentinel row of the reversed free-marker key
     CK(cudaMalloc(&t->row_cnt, rows * 4)); CK(cudaMemsetAsync(t->row_cnt, 0, rows * 4, h->stream));
     CK(cudaMalloc(&t->row_aux, rows * 4));
   }
@@ -67,19 +84,18 @@ static int alloc_table(alz_handle* h, AccTable* t, uint32_t max_rows, uint32_t* 
   CK(cudaMemsetAsync(t->dict, 0xFF, (size_t)dict_cap * sizeof(DictEnt), h->stream));
   CK(cudaMemsetAsync(t->lat_sum, 0, rows * 8, h->stream));
   CK(cudaMemsetAsync(t->err5xx, 0, rows * 8, h->stream));
-  if (with_count) CK(cudaMemsetAsync(t->count, 0, rows * 8, h->stream));
   CK(cudaMemsetAsync(t->hist, 0, rows * ALZ_NB * 4, h->stream));
   return ALZ_OK;
 }
 static void free_table(AccTable* t) {
-  cudaFree(t->dict); cudaFree(t->row_key); cudaFree(t->lat_sum); cudaFree(t->err5xx); cudaFree(t->count);
-  cudaFree(t->row_cnt); cudaFree(t->row_aux);
-  cudaFree(t->hist);
+  cudaFree(t->dict); cudaFree(t->dict_rev); cudaFree(t->row_key); cudaFree(t->row_rev); cudaFree(t->lat_sum);
+  cudaFree(t->err5xx); cudaFree(t->count); cudaFree(t->row_cnt); cudaFree(t->row_aux); cudaFree(t->hist);
   memset(t, 0, sizeof(*t));
 }
-// all keys out of the dictionary, row allocator back to zero (rows were zeroed by fold / gather)
+// all keys out of the dictionaries, row allocator back to zero (rows were zeroed by fold / gather)
 static int clear_dict(alz_handle* h, AccTable* t) {
   CK(cudaMemsetAsync(t->dict, 0xFF, ((size_t)t->dict_mask + 1) * sizeof(DictEnt), h->stream));
+  if (t->dict_rev) CK(cudaMemsetAsync(t->dict_rev, 0xFF, ((size_t)t->dict_rev_mask + 1) * sizeof(DictEnt), h->stream));
   CK(cudaMemsetAsync(t->n_rows, 0, 4, h->stream));
   return ALZ_OK;
 }
@@ -130,27 +146,34 @@ extern "C" int alz_create(const alz_config* cfg, alz_handle** out) {
   CKC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   CKC(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   h->stream = h->own_stream;
-  for (int b = 0; b < 2; ++b) {
-    CKC(cudaEventCreateWithFlags(&h->ev_copied[b], cudaEventDisableTiming));
-    CKC(cudaEventCreateWithFlags(&h->ev_consumed[b], cudaEventDisableTiming));
+  for (int b = 0; b < kStageSlots; ++b) {
+    CKC(cudaEventCreateWithFlags(&h->stage[b].copied, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&h->stage[b].consumed, cudaEventDisableTiming));
+  }
+  for (int b = 0; b < kRawSlots; ++b) {
+    CKC(cudaEventCreateWithFlags(&h->raw[b].copied, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&h->raw[b].consumed, cudaEventDisableTiming));
   }
   CKC(cudaEventCreateWithFlags(&h->ev_tmp, cudaEventDisableTiming));
+  CKC(cudaEventCreateWithFlags(&h->ev_count, cudaEventDisableTiming));
+  CKC(cudaEventCreateWithFlags(&h->ev_patch, cudaEventDisableTiming));
 
   h->ep_cap = next_pow2(2ull * h->cfg.max_endpoints);
+  h->ep_tab.assign(h->ep_cap, EpEntry{0u, 0u, 0u, 0u});
+  h->ep_touched.assign(h->ep_cap, 0);
   CKC(cudaMalloc(&h->d_ep, (size_t)h->ep_cap * sizeof(EpEntry)));
   CKC(cudaMemsetAsync(h->d_ep, 0, (size_t)h->ep_cap * sizeof(EpEntry), h->stream));
   CKC(cudaMalloc(&h->d_ctr, sizeof(Counters)));
   CKC(cudaMemsetAsync(h->d_ctr, 0, sizeof(Counters), h->stream));
-  CKC(cudaMalloc(&h->d_hot, 2 * sizeof(HotState)));
-  CKC(cudaMemsetAsync(h->d_hot, 0, 2 * sizeof(HotState), h->stream));
+  CKC(cudaMalloc(&h->d_hot, sizeof(HotState)));
+  CKC(cudaMemsetAsync(h->d_hot, 0, sizeof(HotState), h->stream));
   int rc;
   if (!(h->cfg.flags & ALZ_CFG_EAGER_JOIN)) {
-    if ((rc = alloc_table(h, &h->pairs_fwd, h->cfg.max_pairs, &h->d_ctr->fwd_rows, false)) != ALZ_OK) return fail(rc);
-    if ((rc = alloc_table(h, &h->pairs_rev, std::max<uint32_t>(1024u, h->cfg.max_pairs >> 1), &h->d_ctr->rev_rows,
-                          false)) != ALZ_OK) return fail(rc);
+    if ((rc = alloc_table(h, &h->pairs, h->cfg.max_pairs, &h->d_ctr->pair_rows, true)) != ALZ_OK) return fail(rc);
   }
-  if ((rc = alloc_table(h, &h->edges, h->cfg.max_edges, &h->d_ctr->edge_rows, true)) != ALZ_OK) return fail(rc);
+  if ((rc = alloc_table(h, &h->edges, h->cfg.max_edges, &h->d_ctr->edge_rows, false)) != ALZ_OK) return fail(rc);
   CKC(cudaMallocHost(&h->h_ctr, sizeof(Counters)));
+  memset(h->h_ctr, 0, sizeof(Counters));
   for (int b = 0; b < 2; ++b) {
     CKC(cudaMalloc(&h->d_keys[b], (size_t)h->cfg.max_edges * 8));
     CKC(cudaMalloc(&h->d_rows[b], (size_t)h->cfg.max_edges * 4));
@@ -164,24 +187,32 @@ extern "C" int alz_create(const alz_config* cfg, alz_handle** out) {
   return ALZ_OK;
 }
 
+static void free_slot(StageSlot& s) {
+  cudaFree(s.d); cudaFree(s.d_aux);
+  if (s.h) cudaFreeHost(s.h);
+  if (s.copied) cudaEventDestroy(s.copied);
+  if (s.consumed) cudaEventDestroy(s.consumed);
+  s.h = s.d = s.d_aux = nullptr;
+  s.copied = s.consumed = nullptr;
+}
+
 extern "C" int alz_destroy(alz_handle* h) {
   if (!h) return ALZ_E_INVAL;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  alz_internal_free_extensions(h);
-  free_table(&h->pairs_fwd); free_table(&h->pairs_rev); free_table(&h->edges);
-  cudaFree(h->d_ep); cudaFree(h->d_ctr); cudaFree(h->d_hot);
+  alz_internal_free_comm(h);
+  alz_internal_free_gnn(h);
+  alz_internal_free_sock(h);
+  free_table(&h->pairs); free_table(&h->edges);
+  cudaFree(h->d_ep); cudaFree(h->d_ctr); cudaFree(h->d_hot); cudaFree(h->d_patch);
+  if (h->h_patch) cudaFreeHost(h->h_patch);
   if (h->h_ctr) cudaFreeHost(h->h_ctr);
-  for (int b = 0; b < 2; ++b) {
-    cudaFree(h->d_keys[b]); cudaFree(h->d_rows[b]);
-    cudaFree(h->d_stage[b]);
-    if (h->h_stage[b]) cudaFreeHost(h->h_stage[b]);
-    if (h->ev_copied[b]) cudaEventDestroy(h->ev_copied[b]);
-    if (h->ev_consumed[b]) cudaEventDestroy(h->ev_consumed[b]);
-  }
+  for (int b = 0; b < 2; ++b) { cudaFree(h->d_keys[b]); cudaFree(h->d_rows[b]); }
+  for (int b = 0; b < kStageSlots; ++b) free_slot(h->stage[b]);
+  for (int b = 0; b < kRawSlots; ++b) free_slot(h->raw[b]);
   if (h->ev_tmp) cudaEventDestroy(h->ev_tmp);
-  cudaFree(h->d_raw_stage);
-  if (h->h_raw_stage) cudaFreeHost(h->h_raw_stage);
+  if (h->ev_count) cudaEventDestroy(h->ev_count);
+  if (h->ev_patch) cudaEventDestroy(h->ev_patch);
   cudaFree(h->d_sort_tmp); cudaFree(h->d_out);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -191,6 +222,7 @@ extern "C" int alz_destroy(alz_handle* h) {
 
 extern "C" int alz_set_stream(alz_handle* h, void* s) {
   if (!h) return ALZ_E_INVAL;
+  std::lock_guard<std::mutex> g(h->mu);
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
   h->stream = s ? (cudaStream_t)s : h->own_stream;
@@ -199,6 +231,7 @@ extern "C" int alz_set_stream(alz_handle* h, void* s) {
 
 extern "C" int alz_sync(alz_handle* h) {
   if (!h) return ALZ_E_INVAL;
+  std::lock_guard<std::mutex> g(h->mu);
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->copy_stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -225,181 +258,379 @@ extern "C" int alz_pinned_free(void* p) {
   return cudaFreeHost(p) == cudaSuccess ? ALZ_OK : ALZ_E_CUDA;
 }
 
+// Run f() with the calling thread bound to the CPUs next to this handle's GPU (sysfs local_cpulist of
+// the PCI device), so that pages it allocates and pins land on the GPU's NUMA node: with 8 ranks feeding
+// 8 GPUs through host buffers, remote-socket staging memory halves the achievable H2D rate (r1: 80 ms
+// per step at 8 ranks against 59 ms at 1-4). Best effort: without sysfs it just runs f().
+template <class F>
+static void with_gpu_local_cpus(int device, F f) {
+  cpu_set_t old, want;
+  CPU_ZERO(&want);
+  bool bound = false;
+  char bus[32] = {0};
+  if (sched_getaffinity(0, sizeof(old), &old) == 0 && cudaDeviceGetPCIBusId(bus, sizeof(bus), device) == cudaSuccess) {
+    for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+    std::string path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
+    if (FILE* fp = fopen(path.c_str(), "r")) {
+      char line[4096] = {0};
+      if (fgets(line, sizeof(line), fp)) {
+        for (char* tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+          int a = 0, b = 0;
+          if (sscanf(tok, "%d-%d", &a, &b) == 2) { for (int c = a; c <= b && c < CPU_SETSIZE; ++c) CPU_SET(c, &want); }
+          else if (sscanf(tok, "%d", &a) == 1 && a < CPU_SETSIZE) CPU_SET(a, &want);
+        }
+        cpu_set_t both;
+        CPU_AND(&both, &want, &old);
+        if (CPU_COUNT(&both) > 0 && sched_setaffinity(0, sizeof(both), &both) == 0) bound = true;
+      }
+      fclose(fp);
+    }
+  }
+  f();
+  if (bound) sched_setaffinity(0, sizeof(old), &old);
+}
+
+// pinned memory on the NUMA node of the handle's GPU
+extern "C" int alz_pinned_alloc_local(alz_handle* h, size_t bytes, void** out) {
+  if (!h || !out || bytes == 0) return ALZ_E_INVAL;
+  void* p = nullptr;
+  cudaError_t e = cudaSuccess;
+  with_gpu_local_cpus(h->device, [&] {
+    cudaSetDevice(h->device);
+    e = cudaMallocHost(&p, bytes);
+    if (e == cudaSuccess) for (size_t o = 0; o < bytes; o += 4096) ((volatile char*)p)[o] = 0;
+  });
+  if (e != cudaSuccess) return ALZ_E_NOMEM;
+  std::lock_guard<std::mutex> g(g_pin_mu);
+  g_pinned.emplace_back((const char*)p, bytes);
+  *out = p;
+  return ALZ_OK;
+}
+
 // ---- join build side -----------------------------------------------------------------
 extern "C" int alz_table_upsert(alz_handle* h, int table, uint32_t ip, uint32_t id) {
   if (!h || (table != ALZ_TABLE_POD && table != ALZ_TABLE_SVC) || id >= (1u << 29)) return ALZ_E_INVAL;
-  HostEp& e = h->ep_host[ip];
+  std::lock_guard<std::mutex> g(h->mu);
+  auto it = h->ep_host.find(ip);
+  if (it == h->ep_host.end()) {
+    if (h->ep_host.size() >= h->cfg.max_endpoints) return ALZ_E_CAPACITY;
+    it = h->ep_host.emplace(ip, HostEp{}).first;
+  }
+  HostEp& e = it->second;
   if (table == ALZ_TABLE_POD) { e.state |= kEpPod; e.pod = id; }   // persist.go:55-65
   else { e.state |= kEpSvc; e.svc = id; }                          // persist.go:114-124
-  h->ep_dirty = true;
+  h->ep_dirty_ips.push_back(ip);
   return ALZ_OK;
 }
 extern "C" int alz_table_erase(alz_handle* h, int table, uint32_t ip) {
   if (!h || (table != ALZ_TABLE_POD && table != ALZ_TABLE_SVC)) return ALZ_E_INVAL;
+  std::lock_guard<std::mutex> g(h->mu);
   auto it = h->ep_host.find(ip);
   if (it == h->ep_host.end()) return ALZ_OK;                       // delete of a missing key: no-op
   it->second.state &= ~(table == ALZ_TABLE_POD ? kEpPod : kEpSvc); // persist.go:66-70, :125-129
   if (it->second.state == 0) h->ep_host.erase(it);
-  h->ep_dirty = true;
+  h->ep_dirty_ips.push_back(ip);
   return ALZ_OK;
 }
 
-int alz_internal_fold(alz_handle* h) {
-  if (h->cfg.flags & ALZ_CFG_EAGER_JOIN) return ALZ_OK;
-  if (h->pending_since_fold == 0) return ALZ_OK;
-  // the join on distinct pairs; it also leaves per-pair counts behind, from which the next
-  // ingest launches learn which pairs are hot (alz_ingest.cu)
-  CK(cudaMemsetAsync(h->d_hot[0].bins, 0, sizeof(h->d_hot[0].bins), h->stream));
-  CK(cudaMemsetAsync(h->d_hot[1].bins, 0, sizeof(h->d_hot[1].bins), h->stream));
-  launch_fold_pairs(h->pairs_fwd, false, h->d_ep, h->ep_cap - 1, h->edges, h->d_ctr, h->d_hot[0].bins, h->sms, h->stream);
-  launch_fold_pairs(h->pairs_rev, true, h->d_ep, h->ep_cap - 1, h->edges, h->d_ctr, h->d_hot[1].bins, h->sms, h->stream);
-  launch_hot_select(h->pairs_fwd, &h->d_hot[0], false, h->sms, h->stream);
-  launch_hot_select(h->pairs_rev, &h->d_hot[1], true, h->sms, h->stream);
-  CK(cudaGetLastError());
-  int rc = clear_dict(h, &h->pairs_fwd);
-  if (rc == ALZ_OK) rc = clear_dict(h, &h->pairs_rev);
-  h->pending_since_fold = 0;
-  return rc;
+// host mirror of the open-addressed endpoint table: linear probing, deletion by backward shift (no
+// tombstones, so the device's probe loop keeps its "stop at the first free slot" rule)
+static void ep_touch(alz_handle* h, uint32_t slot) {
+  if (!h->ep_touched[slot]) { h->ep_touched[slot] = 1; h->ep_touched_list.push_back(slot); }
 }
+static void ep_mirror_put(alz_handle* h, uint32_t ip, const HostEp& v) {
+  const uint32_t mask = h->ep_cap - 1;
+  uint32_t slot = hash32(ip) & mask;
+  while ((h->ep_tab[slot].state & kEpOcc) && h->ep_tab[slot].ip != ip) slot = (slot + 1) & mask;
+  h->ep_tab[slot] = EpEntry{ip, kEpOcc | v.state, v.pod, v.svc};
+  ep_touch(h, slot);
+}
+static void ep_mirror_del(alz_handle* h, uint32_t ip) {
+  const uint32_t mask = h->ep_cap - 1;
+  uint32_t i = hash32(ip) & mask;
+  while ((h->ep_tab[i].state & kEpOcc) && h->ep_tab[i].ip != ip) i = (i + 1) & mask;
+  if (!(h->ep_tab[i].state & kEpOcc)) return;
+  uint32_t j = i;
+  for (;;) {
+    j = (j + 1) & mask;
+    if (!(h->ep_tab[j].state & kEpOcc)) break;
+    const uint32_t k = hash32(h->ep_tab[j].ip) & mask;            // home of the entry at j
+    const bool stays = (i <= j) ? (i < k && k <= j) : (i < k || k <= j);
+    if (stays) continue;
+    h->ep_tab[i] = h->ep_tab[j];
+    ep_touch(h, i);
+    i = j;
+  }
+  h->ep_tab[i] = EpEntry{0u, 0u, 0u, 0u};
+  ep_touch(h, i);
+}
+
+struct EpPatch { uint32_t slot, pad[3]; EpEntry e; };
+static_assert(sizeof(EpPatch) == 32, "EpPatch layout");
+
+static int fold_locked(alz_handle* h);
 
 extern "C" int alz_table_commit(alz_handle* h) {
   if (!h) return ALZ_E_INVAL;
+  std::lock_guard<std::mutex> g(h->mu);
   CK(cudaSetDevice(h->device));
-  if (!h->ep_dirty) return ALZ_OK;
-  if (h->ep_host.size() > h->cfg.max_endpoints) return ALZ_E_CAPACITY;
+  if (h->ep_dirty_ips.empty()) return ALZ_OK;
   // events already submitted are joined through the tables they arrived under
-  int rc = alz_internal_fold(h);
+  int rc = fold_locked(h);
   if (rc != ALZ_OK) return rc;
-  std::vector<EpEntry> tab(h->ep_cap);
-  memset(tab.data(), 0, tab.size() * sizeof(EpEntry));
-  const uint32_t mask = h->ep_cap - 1;
-  for (auto& kv : h->ep_host) {
-    uint32_t slot = hash32(kv.first) & mask;
-    while (tab[slot].state & kEpOcc) slot = (slot + 1) & mask;
-    tab[slot].ip = kv.first;
-    tab[slot].state = kEpOcc | kv.second.state;
-    tab[slot].pod = kv.second.pod;
-    tab[slot].svc = kv.second.svc;
+  for (uint32_t ip : h->ep_dirty_ips) {
+    auto it = h->ep_host.find(ip);
+    if (it == h->ep_host.end()) ep_mirror_del(h, ip); else ep_mirror_put(h, ip, it->second);
   }
-  CK(cudaStreamSynchronize(h->stream));
-  CK(cudaMemcpy(h->d_ep, tab.data(), tab.size() * sizeof(EpEntry), cudaMemcpyHostToDevice));
-  h->ep_dirty = false;
+  h->ep_dirty_ips.clear();
+  // only the slots that changed travel: (slot, entry) records through a pinned buffer, scattered on the
+  // device in stream order (an informer burst under churn touches a handful of slots of a table that
+  // may hold millions)
+  const size_t n = h->ep_touched_list.size();
+  if (n == 0) return ALZ_OK;
+  if (n > h->patch_cap) {
+    CK(cudaEventSynchronize(h->ev_patch));
+    if (h->h_patch) cudaFreeHost(h->h_patch);
+    cudaFree(h->d_patch);
+    h->h_patch = h->d_patch = nullptr;
+    h->patch_cap = std::max<size_t>(1024, n * 2);
+    CK(cudaMallocHost(&h->h_patch, h->patch_cap * sizeof(EpPatch)));
+    CK(cudaMalloc(&h->d_patch, h->patch_cap * sizeof(EpPatch)));
+  }
+  CK(cudaEventSynchronize(h->ev_patch));   // the previous commit's upload has left the pinned buffer
+  EpPatch* p = (EpPatch*)h->h_patch;
+  for (size_t i = 0; i < n; ++i) {
+    const uint32_t slot = h->ep_touched_list[i];
+    p[i].slot = slot; p[i].pad[0] = p[i].pad[1] = p[i].pad[2] = 0;
+    p[i].e = h->ep_tab[slot];
+    h->ep_touched[slot] = 0;
+  }
+  h->ep_touched_list.clear();
+  CK(cudaMemcpyAsync(h->d_patch, h->h_patch, n * sizeof(EpPatch), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaEventRecord(h->ev_patch, h->stream));
+  launch_ep_patch(h->d_ep, h->d_patch, (uint32_t)n, h->sms, h->stream);
+  CK(cudaGetLastError());
   return ALZ_OK;
 }
 
+// ---- fold: the join on distinct pairs ------------------------------------------------------
+// It also leaves per-pair counts behind, from which the next ingest launches learn which pairs are hot
+// (alz_ingest.cu). Split in two so that a flush can read the edge count between the halves.
+static int fold_first_half(alz_handle* h) {
+  launch_fold_resolve(h->pairs, h->d_ep, h->ep_cap - 1, h->edges, h->d_ctr, h->d_hot, h->sms, h->stream);
+  CK(cudaGetLastError());
+  return ALZ_OK;
+}
+static int fold_second_half(alz_handle* h) {
+  launch_fold_add(h->pairs, h->edges, h->d_ctr, h->d_hot, h->sms, h->stream);
+  launch_hot_select(h->pairs, h->d_hot, h->sms, h->stream);
+  CK(cudaGetLastError());
+  int rc = clear_dict(h, &h->pairs);
+  h->pending_since_fold = 0;
+  return rc;
+}
+static int fold_locked(alz_handle* h) {
+  if (h->cfg.flags & ALZ_CFG_EAGER_JOIN) return ALZ_OK;
+  if (h->pending_since_fold == 0) return ALZ_OK;
+  int rc = fold_first_half(h);
+  if (rc != ALZ_OK) return rc;
+  return fold_second_half(h);
+}
+int alz_internal_fold(alz_handle* h) { return fold_locked(h); }
+
 // ---- ingest ------------------------------------------------------------------------------
-static int ingest_device(alz_handle* h, const alz_l7_rec* d, uint64_t n) {
-  if (h->cfg.flags & ALZ_CFG_EAGER_JOIN)
-    launch_ingest_eager(d, n, h->d_ep, h->ep_cap - 1, h->edges, h->d_ctr, h->sms, h->stream);
-  else
-  {
-    if (h->cfg.flags & ALZ_CFG_NO_SMEM_CACHE)
-      launch_ingest_pairs_v1(d, n, h->pairs_fwd, h->pairs_rev, h->d_ctr, h->sms, h->stream);
-    else
-      launch_ingest_pairs_v4(d, n, h->pairs_fwd, h->pairs_rev, h->d_ctr, &h->d_hot[0], &h->d_hot[1], h->d_ep,
-                             h->ep_cap - 1, h->sms, h->stream);
+// requires h->mu
+static int ingest_device(alz_handle* h, const void* d, uint64_t n, bool rec16, const uint64_t* d_ovf) {
+  if (rec16) {
+    if (h->cfg.flags & (ALZ_CFG_EAGER_JOIN | ALZ_CFG_NO_SMEM_CACHE)) return ALZ_E_UNSUPPORTED;
+    launch_ingest_pairs_v6_rec16((const alz_l7_rec16*)d, n, d_ovf, h->pairs, h->d_ctr, h->d_hot, h->d_ep, h->ep_cap - 1,
+                                 h->sms, h->stream);
+  } else if (h->cfg.flags & ALZ_CFG_EAGER_JOIN) {
+    launch_ingest_eager((const alz_l7_rec*)d, n, h->d_ep, h->ep_cap - 1, h->edges, h->d_ctr, h->sms, h->stream);
+  } else if (h->cfg.flags & ALZ_CFG_NO_SMEM_CACHE) {
+    launch_ingest_pairs_v1((const alz_l7_rec*)d, n, h->pairs, h->d_ctr, h->d_ep, h->ep_cap - 1, h->sms, h->stream);
+  } else {
+    launch_ingest_pairs_v6((const alz_l7_rec*)d, n, h->pairs, h->d_ctr, h->d_hot, h->d_ep, h->ep_cap - 1, h->sms,
+                           h->stream);
   }
   CK(cudaGetLastError());
   h->events_in += n;
   h->pending_since_fold += n;
   // pair histograms are u32: fold before any bucket could wrap
-  if (h->pending_since_fold >= (1ull << 31)) return alz_internal_fold(h);
+  if (h->pending_since_fold >= (1ull << 31)) return fold_locked(h);
   return ALZ_OK;
 }
 
 extern "C" int alz_submit_l7_device(alz_handle* h, const alz_l7_rec* d, size_t n) {
   if (!h || (!d && n)) return ALZ_E_INVAL;
-  if (((uintptr_t)d & 31u) != 0) return ALZ_E_INVAL;  // 256-bit loads
+  if (((uintptr_t)d & 31u) != 0) return ALZ_E_INVAL;  // 32-B records, bulk copies
+  std::lock_guard<std::mutex> g(h->mu);
   CK(cudaSetDevice(h->device));
-  return ingest_device(h, d, n);
+  return ingest_device(h, d, n, false, nullptr);
 }
 
-static int ensure_stage(alz_handle* h) {
-  if (h->d_stage[0]) return ALZ_OK;
-  const size_t bytes = (size_t)h->cfg.max_batch * sizeof(alz_l7_rec);
-  for (int b = 0; b < 2; ++b) {
-    CK(cudaMalloc(&h->d_stage[b], bytes));
-    CK(cudaMallocHost(&h->h_stage[b], bytes));
+extern "C" int alz_submit_l7_packed_device(alz_handle* h, const alz_l7_rec16* d, size_t n, const uint64_t* d_ovf) {
+  if (!h || (!d && n)) return ALZ_E_INVAL;
+  if (((uintptr_t)d & 15u) != 0) return ALZ_E_INVAL;
+  std::lock_guard<std::mutex> g(h->mu);
+  CK(cudaSetDevice(h->device));
+  return ingest_device(h, d, n, true, d_ovf);
+}
+
+// staging slot s ready for `bytes` (allocated on first use, pinned memory next to the GPU)
+static int ensure_slot(alz_handle* h, StageSlot& s, size_t bytes, size_t aux_bytes) {
+  if (s.h) return ALZ_OK;
+  cudaError_t e = cudaSuccess;
+  with_gpu_local_cpus(h->device, [&] {
+    cudaSetDevice(h->device);
+    e = cudaMallocHost(&s.h, bytes);
+    if (e == cudaSuccess) for (size_t o = 0; o < bytes; o += 4096) ((volatile char*)s.h)[o] = 0;
+  });
+  if (e != cudaSuccess) { s.h = nullptr; h->last_err = cudaGetErrorString(e); return ALZ_E_NOMEM; }
+  CK(cudaMalloc(&s.d, bytes));
+  if (aux_bytes) CK(cudaMalloc(&s.d_aux, aux_bytes));
+  return ALZ_OK;
+}
+
+// Host records -> device -> ingest, in chunks of max_batch, through the staging slots. rec_bytes = 32
+// (alz_l7_rec) or 16 (alz_l7_rec16).
+static int submit_host(alz_handle* h, const void* recs, size_t n, size_t rec_bytes, const uint64_t* d_ovf) {
+  const bool direct = is_lib_pinned(recs, n * rec_bytes);
+  const size_t slot_bytes = (size_t)h->cfg.max_batch * sizeof(alz_l7_rec);
+  const size_t per = slot_bytes / rec_bytes;   // records per chunk (a 16-B chunk holds twice as many)
+  size_t done = 0;
+  while (done < n) {
+    const size_t m = std::min(per, n - done);
+    uint64_t turn;
+    { std::lock_guard<std::mutex> t(h->turn_mu); turn = h->stage_turn++; }
+    StageSlot& s = h->stage[turn % kStageSlots];
+    std::lock_guard<std::mutex> own(s.mu);
+    int rc = ensure_slot(h, s, slot_bytes, 0);
+    if (rc != ALZ_OK) return rc;
+    const void* src = (const char*)recs + done * rec_bytes;
+    if (!direct) {
+      CK(cudaEventSynchronize(s.copied));      // the previous H2D out of this pinned buffer is done
+      memcpy(s.h, src, m * rec_bytes);         // in parallel with other submitting threads
+      src = s.h;
+    }
+    {
+      std::lock_guard<std::mutex> g(h->mu);
+      CK(cudaStreamWaitEvent(h->copy_stream, s.consumed, 0));   // the kernel that read s.d
+      CK(cudaMemcpyAsync(s.d, src, m * rec_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+      CK(cudaEventRecord(s.copied, h->copy_stream));
+      CK(cudaStreamWaitEvent(h->stream, s.copied, 0));
+      rc = ingest_device(h, s.d, m, rec_bytes == sizeof(alz_l7_rec16), d_ovf);
+      if (rc != ALZ_OK) return rc;
+      CK(cudaEventRecord(s.consumed, h->stream));
+    }
+    done += m;
   }
+  if (direct) CK(cudaStreamSynchronize(h->copy_stream));   // the caller may reuse its pinned buffer once we return
   return ALZ_OK;
 }
 
 extern "C" int alz_submit_l7(alz_handle* h, const alz_l7_rec* recs, size_t n) {
   if (!h || (!recs && n)) return ALZ_E_INVAL;
   CK(cudaSetDevice(h->device));
-  int rc = ensure_stage(h);
-  if (rc != ALZ_OK) return rc;
-  const bool direct = is_lib_pinned(recs, n * sizeof(alz_l7_rec));
-  size_t done = 0;
-  while (done < n) {
-    const size_t m = std::min<size_t>(h->cfg.max_batch, n - done);
-    const int b = (int)(h->stage_turn++ & 1u);
-    const void* src = recs + done;
-    if (!direct) {
-      CK(cudaEventSynchronize(h->ev_copied[b]));   // previous H2D out of this pinned buffer is done
-      memcpy(h->h_stage[b], recs + done, m * sizeof(alz_l7_rec));
-      src = h->h_stage[b];
+  return submit_host(h, recs, n, sizeof(alz_l7_rec), nullptr);
+}
+
+extern "C" int alz_submit_l7_packed(alz_handle* h, const alz_l7_rec16* recs, size_t n, const uint64_t* ovf, size_t n_ovf) {
+  if (!h || (!recs && n) || (!ovf && n_ovf)) return ALZ_E_INVAL;
+  CK(cudaSetDevice(h->device));
+  uint64_t* d_ovf = nullptr;
+  if (n_ovf) {   // rare (durations >= 4.29 s): a stream-ordered allocation that lives until the kernels have run
+    std::lock_guard<std::mutex> g(h->mu);
+    CK(cudaMallocAsync(&d_ovf, n_ovf * 8, h->stream));
+    CK(cudaMemcpyAsync(d_ovf, ovf, n_ovf * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));   // ovf is caller memory (possibly pageable): done with it before returning
+  }
+  int rc = submit_host(h, recs, n, sizeof(alz_l7_rec16), d_ovf);
+  if (d_ovf) { std::lock_guard<std::mutex> g(h->mu); cudaFreeAsync(d_ovf, h->stream); }
+  return rc;
+}
+
+extern "C" long alz_pack_l7(const alz_l7_rec* recs, size_t n, alz_l7_rec16* out, uint64_t* ovf, size_t cap_ovf) {
+  if ((!recs || !out) && n) return -1;
+  size_t k = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const alz_l7_rec& r = recs[i];
+    alz_l7_rec16 o;
+    o.saddr = r.saddr; o.daddr = r.daddr; o.status = r.status;
+    o.protocol = r.protocol & 0x7Fu; o.method_flags = r.method_flags;
+    if (r.protocol & 0x80u) o.protocol = 0x7Fu;   // no such protocol either way: stays "not a request row"
+    if (r.duration_ns >> 32) {
+      if (k >= cap_ovf || !ovf) return -1;
+      ovf[k] = r.duration_ns;
+      o.duration_ns = (uint32_t)k++;
+      o.protocol |= ALZ_REC16_DUR_OVERFLOW;
+    } else {
+      o.duration_ns = (uint32_t)r.duration_ns;
     }
-    CK(cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[b], 0));  // kernel that read d_stage[b]
-    CK(cudaMemcpyAsync(h->d_stage[b], src, m * sizeof(alz_l7_rec), cudaMemcpyHostToDevice, h->copy_stream));
-    CK(cudaEventRecord(h->ev_copied[b], h->copy_stream));
-    CK(cudaStreamWaitEvent(h->stream, h->ev_copied[b], 0));
-    rc = ingest_device(h, h->d_stage[b], m);
-    if (rc != ALZ_OK) return rc;
-    CK(cudaEventRecord(h->ev_consumed[b], h->stream));
-    done += m;
+    out[i] = o;
   }
-  if (direct) {  // the caller may reuse its pinned buffer once we return
-    CK(cudaStreamSynchronize(h->copy_stream));
-  }
-  return ALZ_OK;
+  return (long)k;
 }
 
 extern "C" int alz_submit_l7_raw(alz_handle* h, const void* raw, size_t n) {
   if (!h || (!raw && n)) return ALZ_E_INVAL;
   CK(cudaSetDevice(h->device));
-  int rc = ensure_stage(h);
-  if (rc != ALZ_OK) return rc;
   // raw chunk: as many samples as fit the byte size of one compact staging buffer
   const size_t chunk = std::max<size_t>(1, ((size_t)h->cfg.max_batch * sizeof(alz_l7_rec)) / ALZ_BPF_L7_EVENT_SIZE);
-  if (!h->d_raw_stage) {
-    CK(cudaMalloc(&h->d_raw_stage, chunk * ALZ_BPF_L7_EVENT_SIZE));
-    CK(cudaMallocHost(&h->h_raw_stage, chunk * ALZ_BPF_L7_EVENT_SIZE));
-  }
   const bool direct = is_lib_pinned(raw, n * ALZ_BPF_L7_EVENT_SIZE);
   const uint8_t* p = (const uint8_t*)raw;
   size_t done = 0;
   while (done < n) {
     const size_t m = std::min(chunk, n - done);
-    const void* src = p + done * ALZ_BPF_L7_EVENT_SIZE;
-    // single raw staging buffer: wait until the compaction kernel has consumed it
-    CK(cudaStreamSynchronize(h->stream));
-    if (!direct) { memcpy(h->h_raw_stage, src, m * ALZ_BPF_L7_EVENT_SIZE); src = h->h_raw_stage; }
-    CK(cudaMemcpyAsync(h->d_raw_stage, src, m * ALZ_BPF_L7_EVENT_SIZE, cudaMemcpyHostToDevice, h->stream));
-    launch_compact_raw(h->d_raw_stage, m, h->d_stage[0], h->sms, h->stream);
-    rc = ingest_device(h, h->d_stage[0], m);
+    uint64_t turn;
+    { std::lock_guard<std::mutex> t(h->turn_mu); turn = h->raw_turn++; }
+    StageSlot& s = h->raw[turn % kRawSlots];
+    std::lock_guard<std::mutex> own(s.mu);
+    int rc = ensure_slot(h, s, chunk * ALZ_BPF_L7_EVENT_SIZE, chunk * sizeof(alz_l7_rec));
     if (rc != ALZ_OK) return rc;
+    const void* src = p + done * ALZ_BPF_L7_EVENT_SIZE;
+    if (!direct) {
+      CK(cudaEventSynchronize(s.copied));
+      memcpy(s.h, src, m * ALZ_BPF_L7_EVENT_SIZE);
+      src = s.h;
+    }
+    {
+      std::lock_guard<std::mutex> g(h->mu);
+      // the copy of chunk k+1 overlaps the compaction + ingest of chunk k (two slots, two streams)
+      CK(cudaStreamWaitEvent(h->copy_stream, s.consumed, 0));
+      CK(cudaMemcpyAsync(s.d, src, m * ALZ_BPF_L7_EVENT_SIZE, cudaMemcpyHostToDevice, h->copy_stream));
+      CK(cudaEventRecord(s.copied, h->copy_stream));
+      CK(cudaStreamWaitEvent(h->stream, s.copied, 0));
+      launch_compact_raw((const uint8_t*)s.d, m, (alz_l7_rec*)s.d_aux, h->sms, h->stream);
+      rc = ingest_device(h, s.d_aux, m, false, nullptr);
+      if (rc != ALZ_OK) return rc;
+      CK(cudaEventRecord(s.consumed, h->stream));
+    }
     done += m;
   }
-  CK(cudaStreamSynchronize(h->stream));
+  if (direct) CK(cudaStreamSynchronize(h->copy_stream));
   return ALZ_OK;
 }
 
 // ---- window result ---------------------------------------------------------------------------
-static int read_counters(alz_handle* h) {
+// Fold + sort of the live edge keys (no reset). After it h->n_live edges sit in d_keys[1]/d_rows[1].
+// The edge count is final once the first half of the fold has run, so the counters are copied out right
+// there and the host waits on an event for THAT copy only: the second half of the fold is still
+// running on the GPU while the host sizes and enqueues the sort (r1 stalled the whole stream here).
+// *overflow: the window lost rows (pair or edge table full); the flush still emits what it has.
+static int prepare_flush(alz_handle* h, bool* overflow) {
+  *overflow = false;
+  const bool fold = !(h->cfg.flags & ALZ_CFG_EAGER_JOIN) && h->pending_since_fold != 0;
+  int rc = ALZ_OK;
+  if (fold && (rc = fold_first_half(h)) != ALZ_OK) return rc;
   CK(cudaMemcpyAsync(h->h_ctr, h->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  return ALZ_OK;
-}
-
-// fold + sort of the live edge keys (no reset). After it h->n_live edges sit in d_keys[1]/d_rows[1].
-static int prepare_flush(alz_handle* h) {
-  int rc = alz_internal_fold(h);
-  if (rc != ALZ_OK) return rc;
-  rc = read_counters(h);
-  if (rc != ALZ_OK) return rc;
+  CK(cudaEventRecord(h->ev_count, h->stream));
+  if (fold && (rc = fold_second_half(h)) != ALZ_OK) return rc;
+  CK(cudaEventSynchronize(h->ev_count));
   h->n_live = h->h_ctr->edge_rows;
-  if (h->n_live > h->cfg.max_edges) { h->n_live = h->cfg.max_edges; return ALZ_E_CAPACITY; }
+  if (h->n_live > h->cfg.max_edges) { h->n_live = h->cfg.max_edges; *overflow = true; }
+  // events the pair table could not take during this window's ingest launches
+  if (h->h_ctr->capacity_events != h->lost_reported) { h->lost_reported = h->h_ctr->capacity_events; *overflow = true; }
   if (h->n_live) {
     launch_iota(h->d_rows[0], h->n_live, h->sms, h->stream);
     sort_pairs(h->d_sort_tmp, h->sort_tmp_bytes, h->edges.row_key, h->d_keys[1], h->d_rows[0], h->d_rows[1],
@@ -419,40 +650,50 @@ static int finish_flush(alz_handle* h) {
   return ALZ_OK;
 }
 
-extern "C" int alz_window_flush_device(alz_handle* h, const alz_edge_out** dev_edges, size_t* n_out) {
-  if (!h || !n_out) return ALZ_E_INVAL;
-  CK(cudaSetDevice(h->device));
-  int rc = prepare_flush(h);
+static int flush_device_locked(alz_handle* h, const alz_edge_out** dev_edges, size_t* n_out) {
+  bool overflow = false;
+  int rc = prepare_flush(h, &overflow);
   *n_out = h->n_live;
-  if (rc != ALZ_OK) return rc;
-  const bool lost = h->h_ctr->capacity_events != 0;
-  rc = alz_internal_merge_ranks(h);  // multi-GPU: canonical merge + all-reduce (alz_comm.cu); no-op at 1 rank
-  if (rc == ALZ_E_UNSUPPORTED) rc = finish_flush(h);
-  if (rc != ALZ_OK) return rc;
+  int mrc = alz_internal_merge_ranks(h, rc);  // multi-GPU: canonical merge + one collective (alz_comm.cu)
+  if (mrc == ALZ_E_UNSUPPORTED) {             // single rank
+    if (rc != ALZ_OK) return rc;
+    mrc = finish_flush(h);
+  }
+  if (mrc != ALZ_OK) return mrc;
   *n_out = h->last_n_edges;
   if (dev_edges) *dev_edges = h->d_out;
-  return lost ? ALZ_E_CAPACITY : ALZ_OK;
+  return overflow ? ALZ_E_CAPACITY : ALZ_OK;
+}
+
+extern "C" int alz_window_flush_device(alz_handle* h, const alz_edge_out** dev_edges, size_t* n_out) {
+  if (!h || !n_out) return ALZ_E_INVAL;
+  std::lock_guard<std::mutex> g(h->mu);
+  CK(cudaSetDevice(h->device));
+  return flush_device_locked(h, dev_edges, n_out);
 }
 
 extern "C" int alz_window_flush(alz_handle* h, alz_edge_out* out, size_t cap, size_t* n_out) {
   if (!h || !n_out || (!out && cap)) return ALZ_E_INVAL;
+  std::lock_guard<std::mutex> g(h->mu);
   CK(cudaSetDevice(h->device));
   if (h->comm_nranks <= 1) {
     // size check first so that a too-small buffer keeps the window intact
-    int rc = prepare_flush(h);
+    bool overflow = false;
+    int rc = prepare_flush(h, &overflow);
     *n_out = h->n_live;
     if (rc != ALZ_OK) return rc;
-    if (h->n_live > cap) return ALZ_E_CAPACITY;
-    const bool lost = h->h_ctr->capacity_events != 0;
+    if (h->n_live > cap) { if (overflow) h->lost_reported = ~0ull; return ALZ_E_CAPACITY; }   // report the loss again next time
     rc = finish_flush(h);
     if (rc != ALZ_OK) return rc;
     if (h->n_live) CK(cudaMemcpyAsync(out, h->d_out, (size_t)h->n_live * sizeof(alz_edge_out),
                                       cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    return lost ? ALZ_E_CAPACITY : ALZ_OK;
+    return overflow ? ALZ_E_CAPACITY : ALZ_OK;
   }
+  // several ranks: the merge consumes the window on every rank, so a too-small buffer cannot keep it.
+  // The merged rows stay on the device (alz_window_fetch) and *n_out says how many there are.
   const alz_edge_out* d = nullptr;
-  int rc = alz_window_flush_device(h, &d, n_out);
+  int rc = flush_device_locked(h, &d, n_out);
   if (rc != ALZ_OK && rc != ALZ_E_CAPACITY) return rc;
   if (*n_out > cap) return ALZ_E_CAPACITY;
   if (*n_out) CK(cudaMemcpyAsync(out, d, *n_out * sizeof(alz_edge_out), cudaMemcpyDeviceToHost, h->stream));
@@ -460,28 +701,47 @@ extern "C" int alz_window_flush(alz_handle* h, alz_edge_out* out, size_t cap, si
   return rc;
 }
 
+// the rows of the last flushed window again (e.g. after a flush that returned ALZ_E_CAPACITY because the
+// caller's buffer was too small on a multi-rank handle)
+extern "C" int alz_window_fetch(alz_handle* h, alz_edge_out* out, size_t cap, size_t* n_out) {
+  if (!h || !n_out || (!out && cap)) return ALZ_E_INVAL;
+  std::lock_guard<std::mutex> g(h->mu);
+  CK(cudaSetDevice(h->device));
+  *n_out = h->last_n_edges;
+  if (h->last_n_edges > cap) return ALZ_E_CAPACITY;
+  if (h->last_n_edges) CK(cudaMemcpyAsync(out, h->d_out, (size_t)h->last_n_edges * sizeof(alz_edge_out),
+                                          cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return ALZ_OK;
+}
+
 extern "C" int alz_get_stats(alz_handle* h, alz_stats* st) {
   if (!h || !st) return ALZ_E_INVAL;
+  std::lock_guard<std::mutex> g(h->mu);
   CK(cudaSetDevice(h->device));
-  int rc = read_counters(h);
-  if (rc != ALZ_OK) return rc;
+  CK(cudaMemcpyAsync(h->h_ctr, h->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
   memset(st, 0, sizeof(*st));
+  const uint64_t lost = h->h_ctr->capacity_events + h->h_ctr->fold_lost_events;
   st->events_in = h->events_in;
   st->not_request = h->h_ctr->not_request;
   st->src_unresolved = h->h_ctr->src_unresolved;   // complete once pending pairs are folded
-  st->rows_emitted = h->events_in - st->not_request - st->src_unresolved - h->h_ctr->capacity_events;
-  st->pairs_live = (uint64_t)h->h_ctr->fwd_rows + h->h_ctr->rev_rows;
+  st->rows_emitted = h->events_in - st->not_request - st->src_unresolved - lost;
+  st->pairs_live = h->h_ctr->pair_rows;
   st->edges_live = h->h_ctr->edge_rows;
   st->tcp_events_in = h->tcp_events_in;
   st->tcp_localhost_dropped = h->tcp_localhost_dropped;
+  st->capacity_events = lost;
+  st->windows = h->windows;
   return ALZ_OK;
 }
 
 // make pending pairs visible in the edge accumulators (and in src_unresolved)
 extern "C" int alz_fold(alz_handle* h) {
   if (!h) return ALZ_E_INVAL;
+  std::lock_guard<std::mutex> g(h->mu);
   CK(cudaSetDevice(h->device));
-  return alz_internal_fold(h);
+  return fold_locked(h);
 }
 
 extern "C" uint32_t alz_owner_rank(uint32_t saddr, uint32_t nranks) { return owner_rank(saddr, nranks); }
@@ -502,6 +762,7 @@ extern "C" int alz_dev_free(alz_handle* h, void* p) {
 }
 extern "C" int alz_memcpy_h2d(alz_handle* h, void* dst, const void* src, size_t bytes) {
   if (!h) return ALZ_E_INVAL;
+  std::lock_guard<std::mutex> g(h->mu);
   CK(cudaSetDevice(h->device));
   CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -509,6 +770,7 @@ extern "C" int alz_memcpy_h2d(alz_handle* h, void* dst, const void* src, size_t 
 }
 extern "C" int alz_memcpy_d2h(alz_handle* h, void* dst, const void* src, size_t bytes) {
   if (!h) return ALZ_E_INVAL;
+  std::lock_guard<std::mutex> g(h->mu);
   CK(cudaSetDevice(h->device));
   CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -522,6 +784,7 @@ struct alz_synth_dev {
 
 extern "C" int alz_synth_dev_create(alz_handle* h, const alz_synth_topo* t, alz_synth_dev** out) {
   if (!h || !t || !out) return ALZ_E_INVAL;
+  std::lock_guard<std::mutex> g(h->mu);
   CK(cudaSetDevice(h->device));
   alz_synth_dev* d = new (std::nothrow) alz_synth_dev();
   if (!d) return ALZ_E_NOMEM;
@@ -532,8 +795,9 @@ extern "C" int alz_synth_dev_create(alz_handle* h, const alz_synth_topo* t, alz_
   const size_t bytes[6] = {E * 4, E * 4, E, E * 4, E * 4, (ALZ_SYNTH_LATQ + 1) * 8};
   for (int i = 0; i < 6; ++i) {
     CK(cudaMalloc(&d->bufs[i], bytes[i]));
-    CK(cudaMemcpy(d->bufs[i], src[i], bytes[i], cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(d->bufs[i], src[i], bytes[i], cudaMemcpyHostToDevice, h->stream));
   }
+  CK(cudaStreamSynchronize(h->stream));   // the sources are pageable caller memory
   d->view.edge_saddr = (const uint32_t*)d->bufs[0];
   d->view.edge_daddr = (const uint32_t*)d->bufs[1];
   d->view.edge_flags = (const uint8_t*)d->bufs[2];
@@ -545,6 +809,7 @@ extern "C" int alz_synth_dev_create(alz_handle* h, const alz_synth_topo* t, alz_
 }
 extern "C" int alz_synth_dev_fill(alz_handle* h, alz_synth_dev* d, uint64_t first, uint64_t n, alz_l7_rec* dev_out) {
   if (!h || !d || (!dev_out && n)) return ALZ_E_INVAL;
+  std::lock_guard<std::mutex> g(h->mu);
   CK(cudaSetDevice(h->device));
   launch_synth(d->view, first, n, dev_out, h->sms, h->stream);
   CK(cudaGetLastError());
@@ -555,6 +820,7 @@ extern "C" int alz_synth_dev_fill(alz_handle* h, alz_synth_dev* d, uint64_t firs
 extern "C" int alz_synth_dev_fill_owned(alz_handle* h, alz_synth_dev* d, uint64_t first, uint32_t nranks, uint32_t rank,
                                         alz_l7_rec* dev_out, uint64_t want, uint64_t* n_written, uint64_t* n_scanned) {
   if (!h || !d || !dev_out || !n_written || !n_scanned || nranks == 0 || rank >= nranks) return ALZ_E_INVAL;
+  std::lock_guard<std::mutex> g(h->mu);
   CK(cudaSetDevice(h->device));
   unsigned long long* d_cnt = nullptr;
   CK(cudaMalloc(&d_cnt, 8));

@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 
 #include "alz_handle.h"
@@ -207,6 +208,7 @@ extern "C" int alz_comm_unique_id(void* out_id) {
 
 extern "C" int alz_comm_init(alz_handle* h, int nranks, int rank, const void* id_bytes) {
   if (!h || !id_bytes || nranks < 1 || rank < 0 || rank >= nranks) return ALZ_E_INVAL;
+  std::lock_guard<std::mutex> g(h->mu);
   if (h->comm) return ALZ_E_STATE;
   if (!load_nccl()) { h->last_err = "dlopen(libnccl.so.2) failed"; return ALZ_E_NCCL; }
   CK(cudaSetDevice(h->device));
@@ -248,9 +250,10 @@ void alz_internal_free_comm(alz_handle* h) {
 
 // Called by alz_window_flush_device after prepare_flush(): local live edges are
 // sorted in d_keys[1] (keys) / d_rows[1] (rows), h->n_live of them.
-int alz_internal_merge_ranks(alz_handle* h) {
+int alz_internal_merge_ranks(alz_handle* h, int local_rc) {
   alz_comm_state* c = h->comm;
   if (!c || h->comm_nranks <= 1) return ALZ_E_UNSUPPORTED;
+  if (local_rc != ALZ_OK) return local_rc;
   const int R = h->comm_nranks;
   cudaStream_t s = h->stream;
   const unsigned grid = (unsigned)h->sms * 4;

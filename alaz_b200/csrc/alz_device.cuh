@@ -43,6 +43,12 @@ __host__ __device__ __forceinline__ uint32_t owner_rank(uint32_t saddr, uint32_t
   return (uint32_t)(((uint64_t)hash32(saddr ^ 0xA1A2B200u) * nranks) >> 32);
 }
 
+// Socket-pair key of the pair dictionaries: daddr in the high word, saddr in the low word — the order the two
+// words have in a record, so a record's first 8 bytes ARE its key (no shuffling in the per-event path).
+__host__ __device__ __forceinline__ uint64_t make_pair_key(uint32_t saddr, uint32_t daddr) { return ((uint64_t)daddr << 32) | saddr; }
+__host__ __device__ __forceinline__ uint32_t pair_saddr(uint64_t key) { return (uint32_t)key; }
+__host__ __device__ __forceinline__ uint32_t pair_daddr(uint64_t key) { return (uint32_t)(key >> 32); }
+
 // cheap 32-bit hash of a socket pair for the pair dictionaries and the per-CTA table (the per-event
 // path pays for this once; hash64 costs two 64-bit multiplies)
 __host__ __device__ __forceinline__ uint32_t pair_hash(uint64_t key) {
@@ -122,15 +128,21 @@ constexpr uint32_t kLostRow = 0xFFFFFFFEu;  // dictionary or row pool exhausted
 struct AccTable {
   DictEnt* dict;      // [dict_mask + 1]
   uint32_t dict_mask;
-  uint32_t max_rows;  // rows [0, max_rows) are allocatable; row max_rows is the sentinel row
+  // pair table only: second dictionary for the socket pairs of reversed rows (AMQP DELIVER, REDIS
+  // PUSHED_EVENT). Both dictionaries hand out rows of the same pool; row_rev[row] says which one.
+  DictEnt* dict_rev;
+  uint32_t dict_rev_mask;
+  uint32_t max_rows;  // rows [0, max_rows) are allocatable; rows max_rows, max_rows + 1 are the sentinel rows of the
+                      // key that equals the free marker (forward / reversed); every per-row array has max_rows + 2 entries
   uint32_t* n_rows;   // device counter of allocated rows
-  uint64_t* row_key;  // [max_rows + 1]
-  uint64_t* lat_sum;  // [max_rows + 1]
-  uint64_t* err5xx;   // [max_rows + 1]
-  uint64_t* count;    // [max_rows + 1] (edge table only; pair tables derive it from hist)
-  uint32_t* row_cnt;  // [max_rows + 1] (pair tables only) events of the row at the last fold, saturated
-  uint32_t* row_aux;  // [max_rows + 1] (pair tables only) edge row found by fold_resolve_kernel
-  uint32_t* hist;     // [(max_rows + 1) * ALZ_NB]
+  uint64_t* row_key;  // [max_rows + 2]
+  uint8_t* row_rev;   // [max_rows + 2] (pair table only)
+  uint64_t* lat_sum;  // [max_rows + 2]
+  uint64_t* err5xx;   // [max_rows + 2]
+  uint64_t* count;    // [max_rows + 2] (edge table only; the pair table derives it from hist)
+  uint32_t* row_cnt;  // [max_rows + 2] (pair table only) events of the row at the last fold, saturated
+  uint32_t* row_aux;  // [max_rows + 2] (pair table only) edge row found by fold_resolve_kernel
+  uint32_t* hist;     // [(max_rows + 2) * ALZ_NB]
 };
 
 // row of `key`, inserting it if absent; >= kLostRow when capacity is exhausted
@@ -182,38 +194,41 @@ __device__ __forceinline__ uint32_t ep_lookup(const EpEntry* __restrict__ tab, u
 // (profiles/r1_v4_ingest_ncu.txt: 890k row allocations per 100M events, 190k of them real).
 // Existing pairs are found without touching the endpoint table. Returns kDropRow for a rejected pair.
 constexpr uint32_t kDropRow = 0xFFFFFFFDu;
-__device__ __forceinline__ uint32_t find_or_insert_pair(const AccTable& t, uint64_t key,
+__device__ __forceinline__ uint32_t find_or_insert_pair(const AccTable& t, uint64_t key, bool rev,
                                                         const EpEntry* __restrict__ ep, uint32_t ep_mask) {
-  if (key == kEmptyKey) return t.max_rows;
-  uint32_t slot = pair_hash(key) & t.dict_mask;
+  // the one key that collides with the free marker has fixed rows: max_rows (forward), max_rows + 1 (reversed)
+  if (key == kEmptyKey) return t.max_rows + (rev ? 1u : 0u);
+  DictEnt* const dict = rev ? t.dict_rev : t.dict;
+  const uint32_t mask = rev ? t.dict_rev_mask : t.dict_mask;
+  uint32_t slot = pair_hash(key) & mask;
   bool checked = false;
 #pragma unroll 1
   for (uint32_t p = 0; p < kMaxProbe; ++p) {
-    const uint4 e = __ldcg(reinterpret_cast<const uint4*>(&t.dict[slot]));
+    const uint4 e = __ldcg(reinterpret_cast<const uint4*>(&dict[slot]));
     uint64_t k = ((uint64_t)e.y << 32) | e.x;
     uint32_t row = e.z;
     if (k == kEmptyKey) {
       if (!checked) {
         uint32_t pod, svc;
-        if ((ep_lookup(ep, ep_mask, (uint32_t)(key >> 32), &pod, &svc) & kEpPod) == 0u) return kDropRow;
+        if ((ep_lookup(ep, ep_mask, pair_saddr(key), &pod, &svc) & kEpPod) == 0u) return kDropRow;
         checked = true;
       }
-      const uint64_t old = atomicCAS((unsigned long long*)&t.dict[slot].key, (unsigned long long)kEmptyKey,
+      const uint64_t old = atomicCAS((unsigned long long*)&dict[slot].key, (unsigned long long)kEmptyKey,
                                      (unsigned long long)key);
       if (old == kEmptyKey) {
         row = atomicAdd(t.n_rows, 1u);
-        if (row >= t.max_rows) row = kLostRow; else t.row_key[row] = key;
-        *reinterpret_cast<volatile uint32_t*>(&t.dict[slot].row) = row;
+        if (row >= t.max_rows) row = kLostRow; else { t.row_key[row] = key; t.row_rev[row] = rev ? 1u : 0u; }
+        *reinterpret_cast<volatile uint32_t*>(&dict[slot].row) = row;
         return row;
       }
       k = old;
       row = kNoRow;
     }
     if (k == key) {
-      while (row == kNoRow) row = *reinterpret_cast<volatile uint32_t*>(&t.dict[slot].row);
+      while (row == kNoRow) row = *reinterpret_cast<volatile uint32_t*>(&dict[slot].row);
       return row;
     }
-    slot = (slot + 1u) & t.dict_mask;
+    slot = (slot + 1u) & mask;
   }
   return kLostRow;
 }
@@ -253,15 +268,14 @@ __device__ __forceinline__ uint32_t rec_mflags(const Rec& r) { return r.w[3] >> 
 __device__ __forceinline__ uint64_t rec_duration(const Rec& r) { return ((uint64_t)r.w[5] << 32) | r.w[4]; }
 
 // ---- hot-pair feedback (alz_ingest.cu): which socket pairs took the most events last fold ----
-constexpr int kHotA = 64;     // tier A: inserted into the per-CTA table first
-constexpr int kHotB = 1024;   // tier B capacity
+constexpr int kHotMax = 1024;   // capacity of the list; the ingest kernel preloads as many as its table takes
 struct HotState {
-  uint32_t bins[128];          // quarter-octave histogram of per-pair event counts
-  uint32_t thr_a, thr_b;       // lowest bin of tier A / of tier B
-  uint32_t n_a, n_b;
-  uint64_t keys_a[kHotA];
-  uint64_t keys_b[kHotB];
+  uint32_t bins[128];          // quarter-octave histogram of per-pair event counts (forward pairs)
+  uint32_t thr_a, thr_b;       // lowest bin of tier A (hottest, listed first) / of tier B
+  uint32_t n_a, n_b;           // tier A occupies keys[0, n_a), tier B keys[kHotA, kHotA + n_b)
+  uint64_t keys[kHotMax];
 };
+constexpr int kHotA = 64;
 // monotone bin of a count >= 1: 4 bins per octave
 __device__ __forceinline__ uint32_t count_bin(uint32_t c) {
   const uint32_t o = 31u - (uint32_t)__clz((int)c);
@@ -273,9 +287,9 @@ __device__ __forceinline__ uint32_t count_bin(uint32_t c) {
 struct Counters {
   unsigned long long not_request;
   unsigned long long src_unresolved;
-  unsigned long long capacity_events;  // events lost to an exhausted dictionary / row pool
-  unsigned long long pad0;
-  uint32_t fwd_rows, rev_rows, edge_rows, pad1;  // row allocators of the three tables
+  unsigned long long capacity_events;   // events lost at ingest to an exhausted pair dictionary / row pool
+  unsigned long long fold_lost_events;  // events lost at fold to an exhausted edge dictionary / row pool
+  uint32_t pair_rows, edge_rows, pad1[2];   // row allocators of the two tables
   unsigned long long pad2[2];
 };
 

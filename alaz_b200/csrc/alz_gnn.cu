@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <mutex>
 #include <vector>
 
 #include "alz_handle.h"
@@ -442,8 +443,7 @@ struct alz_gnn_state {
     }                                                                                  \
   } while (0)
 
-static int gnn_init(alz_handle* h) {
-  if (h->gnn) return ALZ_OK;
+static int gnn_init_impl(alz_handle* h) {
   alz_gnn_state* g = new alz_gnn_state();
   h->gnn = g;
   g->cap_e = h->cfg.max_edges;
@@ -472,8 +472,8 @@ static int gnn_init(alz_handle* h) {
   for (int l = 0; l < 2; ++l) {
     CK(cudaMalloc(&g->d_W[l], 128 * D * 4));
     CK(cudaMalloc(&g->d_b[l], D * 4));
-    CK(cudaMemcpy(g->d_W[l], w.W[l].data(), 128 * D * 4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(g->d_b[l], w.b[l].data(), D * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(g->d_W[l], w.W[l].data(), 128 * D * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(g->d_b[l], w.b[l].data(), D * 4, cudaMemcpyHostToDevice, h->stream));
   }
   {
     const char* simt = getenv("ALZ_GNN_SIMT");   // comparison knob: FP32 FFMA layer instead of tcgen05
@@ -489,14 +489,25 @@ static int gnn_init(alz_handle* h) {
           can[tc::TN * tc::TK + off] = lo;
         }
       CK(cudaMalloc(&g->d_Wcan[l], 2 * tc::B_BYTES));
-      CK(cudaMemcpy(g->d_Wcan[l], can.data(), 2 * tc::B_BYTES, cudaMemcpyHostToDevice));
+      CK(cudaMemcpyAsync(g->d_Wcan[l], can.data(), 2 * tc::B_BYTES, cudaMemcpyHostToDevice, h->stream));
+      CK(cudaStreamSynchronize(h->stream));   // `can` is rewritten for the next layer
     }
     CK(cudaFuncSetAttribute(tc::sage_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
   }
   CK(cudaMalloc(&g->d_a, 132 * 4));
-  CK(cudaMemcpy(g->d_a, w.a.data(), 132 * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpyAsync(g->d_a, w.a.data(), 132 * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));     // the host-side weight vectors die with this frame
   g->c = w.c;
   return ALZ_OK;
+}
+
+void alz_internal_free_gnn(alz_handle* h);
+// a half-built state never stays published: a failed allocation frees everything and the next call retries
+static int gnn_init(alz_handle* h) {
+  if (h->gnn) return ALZ_OK;
+  const int rc = gnn_init_impl(h);
+  if (rc != ALZ_OK) alz_internal_free_gnn(h);
+  return rc;
 }
 
 void alz_internal_free_gnn(alz_handle* h) {
@@ -564,8 +575,7 @@ static int gnn_run(alz_handle* h) {
   return ALZ_OK;
 }
 
-extern "C" int alz_gnn_score_device(alz_handle* h, const float** dev_scores, size_t* n_out) {
-  if (!h || !n_out) return ALZ_E_INVAL;
+static int gnn_score_device_locked(alz_handle* h, const float** dev_scores, size_t* n_out) {
   CK(cudaSetDevice(h->device));
   int rc = gnn_run(h);
   *n_out = h->gnn ? h->gnn->n_e : 0;
@@ -574,10 +584,17 @@ extern "C" int alz_gnn_score_device(alz_handle* h, const float** dev_scores, siz
   return ALZ_OK;
 }
 
+extern "C" int alz_gnn_score_device(alz_handle* h, const float** dev_scores, size_t* n_out) {
+  if (!h || !n_out) return ALZ_E_INVAL;
+  std::lock_guard<std::mutex> g(h->mu);
+  return gnn_score_device_locked(h, dev_scores, n_out);
+}
+
 extern "C" int alz_gnn_score(alz_handle* h, float* edge_scores, size_t cap, size_t* n_out) {
   if (!h || !n_out || (!edge_scores && cap)) return ALZ_E_INVAL;
+  std::lock_guard<std::mutex> g(h->mu);
   const float* d = nullptr;
-  int rc = alz_gnn_score_device(h, &d, n_out);
+  int rc = gnn_score_device_locked(h, &d, n_out);
   if (rc != ALZ_OK) return rc;
   if (*n_out > cap) return ALZ_E_CAPACITY;
   if (*n_out) CK(cudaMemcpyAsync(edge_scores, d, *n_out * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -588,6 +605,7 @@ extern "C" int alz_gnn_score(alz_handle* h, float* edge_scores, size_t cap, size
 // debug/test: node keys ((kind << 32) | value, ascending) and the layer-2 embeddings of the last alz_gnn_score
 extern "C" int alz_gnn_nodes(alz_handle* h, uint64_t* node_keys, float* h2, size_t cap, size_t* n_out) {
   if (!h || !n_out) return ALZ_E_INVAL;
+  std::lock_guard<std::mutex> g(h->mu);
   if (!h->gnn) return ALZ_E_STATE;
   CK(cudaSetDevice(h->device));
   *n_out = h->gnn->n_v;

@@ -1,26 +1,35 @@
 // alz_ingest.cu — the dominant kernel: l7 events -> per-socket-pair accumulators
-// (DESIGN.md §3 step 1, §5). One persistent CTA of 1024 threads per SM.
+// (DESIGN.md §3 step 1, §5). One persistent CTA per SM.
 //
-// Each CTA keeps a private table of hot socket pairs in shared memory (the stream
-// is Zipf-skewed; without it the hottest pairs serialise in one L2 slice):
-//   * 4-way buckets with 16-bit tags: a lookup is one 8-byte load of the four tags and one
-//     key load for the lanes whose tag matched (two random LDS.128 per lane made the shared-
-//     memory pipe the limiter), no probe loop, every lane walks the same instructions;
-//   * which pairs are hot is fed back from the previous fold (hot_select kernels
-//     below): tier A = the ~64 hottest, inserted first so they cannot lose a
-//     bucket race, tier B = the rest up to the table size. With no history (first
-//     window) pairs are admitted first-come while buckets have room;
-//   * racing admissions may duplicate a key inside a bucket: harmless, both rows
-//     are added into the global table when the CTA drains.
-// Cold pairs go to the global dictionary: the home slot of all events of a thread
-// is fetched before any is consumed (memory-level parallelism) and a hit there is
-// reduced at once. Everything else — a new pair, a collision, an unresolvable
-// source — is rare (~4 % of events) and loop-shaped, so it is NOT run inline: the
-// lane pushes the event onto its warp's queue in shared memory (ballot-compacted,
-// no atomics) and the warp runs the slow path for 32 queued events at a time.
-// The main loop therefore stays converged: with the slow path inline, lanes
-// came back from it in separate groups and the whole loop body issued ~1.55x
-// (profiles/r1_v4b_ingest_ncu.txt: 20 of 32 lanes active on the loop's own code).
+// Data movement: every warp owns a two-stage ring in shared memory and streams its
+// chunks of the record array into it with TMA bulk copies (cp.async.bulk + mbarrier
+// complete_tx, issued by lane 0, L2 evict-first). Lanes copy their records from the
+// ring into registers, the stage is handed back to the TMA at once, and the next two
+// chunks are in flight while the warp works: no per-lane address arithmetic, no
+// scoreboard stall on the first use of a streamed record, no cross-warp barrier
+// anywhere in the main loop.
+//
+// Work per event, three tiers:
+//   hot   the event's socket pair is in the CTA's shared-memory table (the stream is
+//         Zipf-skewed: ~70 % of events): one direct-mapped probe (fingerprint + row,
+//         verified against the row's key), one shared histogram increment, one shared
+//         add of the latency. Which pairs are hot is fed back from the previous fold
+//         (hot_select kernels below); 1/8 of the rows stay free for first-come
+//         admission, which is also what the very first window runs on.
+//   cold  everything else is NOT handled inline: the lane pushes the event onto its
+//         warp's queue (ballot-compacted, no atomics) and the warp runs the cold path
+//         for 32 queued events at a time with all lanes busy — global dictionary probe
+//         of the home slot, then reductions (REDG) into the pair's row in L2. The hot
+//         loop therefore carries no global-memory code and stays converged; r1's
+//         kernel issued the cold path's instructions for every warp iteration
+//         (profiles/r1_final_ingest_ncu.txt: 247 instructions per event).
+//         The probes of a batch are consumed one batch later, so their L2 round trip
+//         is off the warp's critical path.
+//   slow  a cold event whose home slot does not hold its pair (new pair, collision,
+//         unresolvable source: ~7 % of the cold events) is queued once more and 32 of
+//         them at a time walk find_or_insert_pair; inline, nearly every cold batch would
+//         run that loop for a lane or two.
+// Reversed rows (AMQP DELIVER / REDIS PUSHED_EVENT, ~3 % of events) always go cold.
 #include <cstdlib>
 
 #include "alz_kernels.cuh"
@@ -29,341 +38,433 @@ namespace alz {
 
 namespace {
 
-constexpr int kLatSub = 4;              // latency sub-accumulators per row, picked by lane: every event of a pair adds to
-                                        // its latency sum, so a hot pair's lanes would all serialise on one word
+constexpr int kLatSub = 4;                 // latency sub-accumulators per row, picked by lane: every event of a pair adds to
+                                           // its latency sum, so a hot pair's lanes would all serialise on one word
 constexpr int kRowWords = ALZ_NB + 2 * kLatSub + 1;   // 64 hist cells, 4 x (lat_lo, lat_hi), err5xx = 73 (odd stride)
-constexpr uint32_t kFwdBuckets = 128, kRevBuckets = 16, kWays = 4;
-constexpr uint32_t kSlots = (kFwdBuckets + kRevBuckets) * kWays;
-constexpr uint32_t kQueue = 64;          // slow-path queue entries per warp (ring)
+constexpr uint32_t kTab = 4096;            // direct-mapped lookup entries: fingerprint (hash bits 19..0, bit 0 forced) << 12 | row
+constexpr uint32_t kBusy = 0xFFFu;         // entry whose row field is no row: claimed, not (or never) published
+constexpr uint32_t kSlowQ = 64;            // slow queue entries per warp (ring)
+constexpr uint32_t kQBytes = 24;           // queue entry: key u64, dur u64, meta u32, pad
+constexpr uint32_t kSmemMax = 232448;      // 227 KB per CTA on sm_100
 
-struct Smem {
-  uint64_t* keys;   // [kSlots]  bucket-major, 4 keys per bucket
-  uint16_t* tags;   // [kSlots]  16 hash bits per way (0 = free): a lookup reads these 8 bytes, then one key
-  uint32_t* fill;   // [kFwdBuckets + kRevBuckets] ways handed out
-  uint32_t* rows;   // [kSlots * kRowWords]
+template <int kWarps, int kU, int kRecWords>
+struct Layout {
+  // cold queue entries per warp (ring): up to 31 left over from the last iteration + 32 * kU new ones
+  static constexpr uint32_t kColdQ = (32 * kU + 31 <= 64) ? 64u : (32 * kU + 31 <= 128) ? 128u : 256u;
+  static constexpr uint32_t kChunk = 32u * kU;                          // events per chunk (per warp per iteration)
+  static constexpr uint32_t kChunkBytes = kChunk * kRecWords * 4u;
+  static constexpr uint32_t kRing = (uint32_t)kWarps * 2u * kChunkBytes;
+  static constexpr uint32_t kBars = kRing;                              // kWarps * 2 mbarriers
+  static constexpr uint32_t kTabOff = kBars + (uint32_t)kWarps * 16u;
+  static constexpr uint32_t kColdOff = kTabOff + kTab * 4u;
+  static constexpr uint32_t kSlowOff = kColdOff + (uint32_t)kWarps * kColdQ * kQBytes;
+  static constexpr uint32_t kMisc = kSlowOff + (uint32_t)kWarps * kSlowQ * kQBytes;   // row allocator
+  static constexpr uint32_t kRowKeys = kMisc + 16u;
+  static constexpr uint32_t kFixed = kRowKeys + 8u;                     // + (kRows + 1) * 8 + kRows * kRowWords * 4
+  static constexpr uint32_t kRows = ((kSmemMax - kFixed) / (kRowWords * 4u + 8u)) / 32u * 32u;
+  static constexpr uint32_t kRowsOff = kRowKeys + (kRows + 1u) * 8u;
+  static constexpr uint32_t kBytes = kRowsOff + kRows * kRowWords * 4u;
+  static constexpr uint32_t kPreload = kRows - kRows / 8u;              // rows the hot list may take
+  static_assert(kBytes <= kSmemMax, "shared memory layout too large");
+  static_assert(kRows < kBusy, "row field is 12 bits");
 };
 
-__device__ __forceinline__ uint32_t bucket_of(uint32_t h, bool rv) {
-  const uint32_t hb = h >> 20;   // high bits: independent of the dictionary's low-bit slot
-  return rv ? kFwdBuckets + (hb & (kRevBuckets - 1u)) : (hb & (kFwdBuckets - 1u));
+// ---- TMA / mbarrier (PTX) -------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ uint32_t tag_of(uint32_t h) { return (h & 0xFFFFu) | 1u; }
-
-// slot of key in its bucket or -1. One 8-byte load of the four tags, then the key of the first way whose
-// tag matches (only lanes with a match load it). A second way with an equal tag, or a tag that is visible
-// before its key, reads as a miss: the event then takes the global path, which is always correct.
-// *room = the bucket still has a free way.
-__device__ __forceinline__ int smem_lookup(const Smem& s, uint32_t bucket, uint64_t key, uint32_t tag, bool* room) {
-  const uint2 t = *reinterpret_cast<const uint2*>(&s.tags[bucket * kWays]);
-  const uint32_t t0 = t.x & 0xFFFFu, t1 = t.x >> 16, t2 = t.y & 0xFFFFu, t3 = t.y >> 16;
-  *room = t3 == 0u;              // ways fill in order 0..3
-  int w = -1;
-  w = (t3 == tag) ? 3 : w;
-  w = (t2 == tag) ? 2 : w;
-  w = (t1 == tag) ? 1 : w;
-  w = (t0 == tag) ? 0 : w;
-  if (w >= 0 && s.keys[bucket * kWays + (uint32_t)w] != key) w = -1;
-  return w < 0 ? -1 : (int)(bucket * kWays) + w;
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-
-// claim a free way of the bucket for key; -1 if the bucket is full
-__device__ __forceinline__ int smem_admit(const Smem& s, uint32_t bucket, uint64_t key, uint32_t tag) {
-  const uint32_t w = atomicAdd(&s.fill[bucket], 1u);
-  if (w >= kWays) return -1;
-  s.keys[bucket * kWays + w] = key;
-  // no fence here on purpose: a reader that sees the tag before the key takes it for a miss (still correct),
-  // and a __threadfence_block() anywhere in this kernel makes nvcc emit every global reduction as ATOMG
-  // (with return) instead of REDG: +70 % kernel time (profiles/r1_v6_tagfence_ncu.txt)
-  *reinterpret_cast<volatile uint16_t*>(&s.tags[bucket * kWays + w]) = (uint16_t)tag;
-  return (int)(bucket * kWays + w);
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
 }
-
-__device__ __forceinline__ void smem_accumulate(const Smem& s, int slot, uint32_t bucket, uint64_t dur, bool err) {
-  uint32_t* row = s.rows + (size_t)slot * kRowWords;
-  atomicAdd(&row[bucket], 1u);
-  uint32_t* lat = row + ALZ_NB + 2 * (threadIdx.x & (kLatSub - 1));
-  const uint32_t lo = (uint32_t)dur;
-  const uint32_t old = atomicAdd(&lat[0], lo);
-  const uint32_t hi = (uint32_t)(dur >> 32) + ((old + lo < old) ? 1u : 0u);
-  if (hi) atomicAdd(&lat[1], hi);
-  if (err) atomicAdd(&row[ALZ_NB + 2 * kLatSub], 1u);
+// global -> shared bulk copy, completion counted on the mbarrier; L2 evict-first so that the stream does not
+// push the accumulator rows out of L2
+__device__ __forceinline__ void tma_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
 }
-
-struct Ev {
-  uint64_t key, dur;
-  uint32_t bucket;
-  bool act, rev, err;
-};
-// processL7's switch as bit tests (aggregator/data.go:1364-1383): request rows for
-// HTTP(1) AMQP(2) POSTGRES(3) REDIS(5) MYSQL(7) MONGO(8); the SQL/Mongo ones unless rejected
-__device__ __forceinline__ Ev decode(const Rec& r, bool live) {
-  Ev e;
-  const uint32_t p = rec_protocol(r), mf = rec_mflags(r);
-  const bool row = p <= 8u && ((0x1AEu >> p) & 1u);
-  const bool sql = p <= 8u && ((0x188u >> p) & 1u);
-  e.act = live && row && !(sql && (mf & ALZ_MF_PAYLOAD_REJECT));
-  e.rev = (mf & ALZ_MF_METHOD_MASK) == 2u && (p == ALZ_PROTO_AMQP || p == ALZ_PROTO_REDIS);  // DELIVER / PUSHED_EVENT
-  e.key = ((uint64_t)rec_saddr(r) << 32) | rec_daddr(r);
-  e.dur = rec_duration(r);
-  e.bucket = latency_bucket(e.dur);
-  e.err = is_5xx(p, rec_status(r));
-  return e;
+// global reductions are written as PTX red so that no fence elsewhere in the kernel can turn them into
+// returning atomics (r1 found nvcc emitting ATOMG for every atomicAdd once a __threadfence_block() was present)
+__device__ __forceinline__ void red_add_u32(uint32_t* p, uint32_t v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-
-// streaming load: read once, keep it out of L1 and first in line for L2 eviction so the
-// accumulator rows stay resident
-__device__ __forceinline__ Rec load_rec_stream(const alz_l7_rec* p, uint64_t policy) {
-  Rec r;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
-               : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]),
-                 "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
-               : "l"(p), "l"(policy));
+__device__ __forceinline__ void red_add_u64(uint64_t* p, uint64_t v) {
+  asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {   // one lane of the (converged) warp
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0u;
+}
+__device__ __forceinline__ uint32_t shr_clamp(uint32_t v, uint32_t by) {   // PTX shr: amounts > 31 give 0
+  uint32_t r;
+  asm("shr.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(by));
   return r;
 }
 
-// tier A then tier B of one table's hot list into its buckets
-__device__ __forceinline__ void preload_hot(const Smem& s, const HotState* hot, bool rv) {
-  if (hot == nullptr) return;
-  const uint32_t na = min(hot->n_a, (uint32_t)kHotA), nb = min(hot->n_b, (uint32_t)kHotB);
-  for (uint32_t i = threadIdx.x; i < na; i += blockDim.x) {
-    const uint64_t k = hot->keys_a[i];
-    if (k != kEmptyKey) { const uint32_t hh = pair_hash(k); smem_admit(s, bucket_of(hh, rv), k, tag_of(hh)); }
-  }
-  __syncthreads();
-  for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
-    const uint64_t k = hot->keys_b[i];
-    if (k != kEmptyKey) { const uint32_t hh = pair_hash(k); smem_admit(s, bucket_of(hh, rv), k, tag_of(hh)); }
-  }
+// docs/SPEC.md §4 through the float exponent: round-toward-zero keeps floor(log2 d) and the next mantissa bit
+// exact for every u64, so bits >> 22 = 2 * (127 + o) + bit(o-1); one conversion instead of a 64-bit clz chain
+__device__ __forceinline__ uint32_t latency_bucket_rz(uint64_t d) {
+  const int b = (int)(__float_as_uint(__ull2float_rz(d)) >> 22) - 2 * (127 + 8);
+  return (uint32_t)min(max(b, 0), ALZ_NB - 1);
 }
 
-// private rows [first, first + count) into global table g; a warp per slot
-__device__ __forceinline__ void smem_drain(const Smem& s, uint32_t first, uint32_t count, const AccTable& g,
+// processL7's switch (aggregator/data.go:1364-1383) as a 3-bit class per protocol value, packed in one word:
+// bit 0 a request row is built (HTTP 1, AMQP 2, POSTGRES 3, REDIS 5, MYSQL 7, MONGO 8), bit 1 the row is dropped
+// when the payload parser rejected it (POSTGRES, MYSQL, MONGO), bit 2 method 2 reverses the row (AMQP DELIVER,
+// REDIS PUSHED_EVENT). Protocol values > 8 shift everything out: class 0 = no row.
+constexpr uint32_t proto_class(uint32_t p) {
+  return ((0x1AEu >> p) & 1u) | (((0x188u >> p) & 1u) << 1) | (((0x024u >> p) & 1u) << 2);
+}
+constexpr uint32_t kProtoLut = proto_class(0) | proto_class(1) << 3 | proto_class(2) << 6 | proto_class(3) << 9 |
+                               proto_class(4) << 12 | proto_class(5) << 15 | proto_class(6) << 18 |
+                               proto_class(7) << 21 | proto_class(8) << 24;
+
+// hash of the per-CTA table only: two multiply-adds; the index comes from its top bits, the fingerprint from the
+// rest. Weak low bits only cost a wasted verify (the row's key decides). The dictionary hash (pair_hash) is computed
+// for cold events only.
+__device__ __forceinline__ uint32_t table_hash(uint64_t key) {
+  return (uint32_t)key * 0x9E3779B1u + (uint32_t)(key >> 32) * 0x85EBCA6Bu;
+}
+constexpr uint32_t kTabShift = 20;         // index = hash >> 20 (12 bits)
+
+struct Shared {
+  uint32_t* tab;      // [kTab]
+  uint64_t* rowkey;   // [kRows + 1], entry kRows = kEmptyKey (never a hit)
+  uint32_t* rows;     // [kRows * kRowWords]
+  uint32_t* n_rows;   // rows handed out
+};
+
+__device__ __forceinline__ uint32_t tab_fp(uint32_t h) { return (h << 12) | 0x1000u; }   // never 0 in bits 31..12
+__device__ __forceinline__ uint32_t tab_entry(uint32_t h, uint32_t row) { return tab_fp(h) | row; }
+
+// claim the direct-mapped slot of `key` and give it a row; false if the slot is taken or the rows are used up.
+// `publish_fenced`: other warps are probing concurrently, so the row's key must be visible before the entry
+__device__ __forceinline__ bool smem_admit(const Shared& s, uint64_t key, uint32_t h, uint32_t limit, bool publish_fenced) {
+  const uint32_t idx = h >> kTabShift;
+  if (atomicCAS(&s.tab[idx], 0u, kBusy) != 0u) return false;
+  const uint32_t row = atomicAdd(s.n_rows, 1u);
+  if (row >= limit) return false;                       // slot stays kBusy: reads as a miss for everyone
+  s.rowkey[row] = key;
+  if (publish_fenced) __threadfence_block();
+  *reinterpret_cast<volatile uint32_t*>(&s.tab[idx]) = tab_entry(h, row);
+  return true;
+}
+
+// one warp's queue of deferred events in shared memory: a ring of 24-byte entries {key u64, dur u64, meta u32}
+// filled by ballot compaction. meta: bits 0..5 latency bucket, bit 8 reversed row, bit 9 counts as 5xx
+template <uint32_t kCap>
+struct Queue {
+  uint8_t* base;
+  uint32_t head, count;
+  __device__ __forceinline__ void bind(uint8_t* b) { base = b; head = 0; count = 0; }
+  __device__ __forceinline__ uint8_t* at(uint32_t i) const { return base + ((head + i) & (kCap - 1u)) * kQBytes; }
+  // every lane calls; lanes with `want` append their event
+  __device__ __forceinline__ uint32_t push(bool want, uint64_t k, uint64_t d, uint32_t m, uint32_t lane_lt) {
+    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, want);
+    if (want) {
+      uint8_t* e = at(count + __popc(mask & lane_lt));
+      *reinterpret_cast<uint64_t*>(e) = k;
+      *reinterpret_cast<uint64_t*>(e + 8) = d;
+      *reinterpret_cast<uint32_t*>(e + 16) = m;
+    }
+    const uint32_t added = __popc(mask);
+    count += added;
+    return added;
+  }
+  __device__ __forceinline__ void get(uint32_t i, uint64_t* k, uint64_t* d, uint32_t* m) const {
+    const uint8_t* e = at(i);
+    *k = *reinterpret_cast<const uint64_t*>(e);
+    *d = *reinterpret_cast<const uint64_t*>(e + 8);
+    *m = *reinterpret_cast<const uint32_t*>(e + 16);
+  }
+  __device__ __forceinline__ void pop(uint32_t n) { head = (head + n) & (kCap - 1u); count -= n; }
+};
+
+// a batch of cold events whose dictionary home slots have been requested
+struct Probe {
+  uint4 ent;          // the 16-byte DictEnt as loaded
+  uint64_t key, dur;
+  uint32_t meta;      // bit 31: this lane holds an event
+};
+
+// slow tier, 32 queued events at a time: the pair is new to the dictionary, or its home slot is taken by another
+// pair, or its source is no pod (dropped like the reference does, aggregator/data.go:829-832)
+template <uint32_t kRows>
+__device__ __forceinline__ void slow_batch(Queue<kSlowQ>& q, uint32_t count, const AccTable& t, const Shared& s,
                                            const EpEntry* __restrict__ ep, uint32_t ep_mask, uint32_t* lost,
                                            uint32_t* unresolved) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const bool mine = lane < count;
+  if (mine) {
+    uint64_t key, dur;
+    uint32_t meta;
+    q.get(lane, &key, &dur, &meta);
+    const bool rv = (meta & 0x100u) != 0u;
+    const uint32_t row = find_or_insert_pair(t, key, rv, ep, ep_mask);
+    if (row >= kDropRow) { if (row == kDropRow) *unresolved += 1u; else *lost += 1u; }
+    else {
+      red_add_u32(&t.hist[(size_t)row * ALZ_NB + (meta & 0x3Fu)], 1u);
+      red_add_u64(&t.lat_sum[row], dur);
+      if (meta & 0x200u) red_add_u64(&t.err5xx[row], 1ull);
+      // a pair the dictionary did not know yet: give it a private row while some are left (first-come)
+      if (!rv && key != kEmptyKey && *reinterpret_cast<volatile uint32_t*>(s.n_rows) < kRows)
+        smem_admit(s, key, table_hash(key), kRows, true);
+    }
+  }
+  __syncwarp();
+  q.pop(count);
+}
+
+// cold tier, step 1: take `count` events off the cold queue and request their home slots
+template <uint32_t kColdQ>
+__device__ __forceinline__ Probe cold_issue(Queue<kColdQ>& q, uint32_t count, const AccTable& t) {
+  const uint32_t lane = threadIdx.x & 31u;
+  Probe p;
+  p.ent = make_uint4(0u, 0u, kNoRow, 0u);
+  p.key = 0; p.dur = 0; p.meta = 0;
+  if (lane < count) {
+    q.get(lane, &p.key, &p.dur, &p.meta);
+    p.meta |= 0x80000000u;
+    const bool rv = (p.meta & 0x100u) != 0u;
+    const DictEnt* dict = rv ? t.dict_rev : t.dict;
+    const uint32_t mask = rv ? t.dict_rev_mask : t.dict_mask;
+    p.ent = __ldcg(reinterpret_cast<const uint4*>(&dict[pair_hash(p.key) & mask]));
+  }
+  __syncwarp();
+  q.pop(count);
+  return p;
+}
+// cold tier, step 2 (one batch later, so the L2 round trip of the probes is off the critical path): a home-slot
+// hit is reduced into its row at once, anything else joins the slow queue
+template <uint32_t kRows>
+__device__ __forceinline__ void cold_consume(const Probe& p, Queue<kSlowQ>& slow, const AccTable& t, const Shared& s,
+                                             const EpEntry* __restrict__ ep, uint32_t ep_mask, uint32_t lane_lt,
+                                             uint32_t* lost, uint32_t* unresolved) {
+  const bool valid = (p.meta & 0x80000000u) != 0u;
+  const bool home = valid && p.ent.x == (uint32_t)p.key && p.ent.y == (uint32_t)(p.key >> 32) && p.ent.z < kDropRow &&
+                    p.key != kEmptyKey;
+  if (home) {
+    red_add_u32(&t.hist[(size_t)p.ent.z * ALZ_NB + (p.meta & 0x3Fu)], 1u);
+    red_add_u64(&t.lat_sum[p.ent.z], p.dur);
+    if (p.meta & 0x200u) red_add_u64(&t.err5xx[p.ent.z], 1ull);
+  }
+  slow.push(valid && !home, p.key, p.dur, p.meta & 0x3FFu, lane_lt);
+  __syncwarp();
+  if (slow.count >= 32u) slow_batch<kRows>(slow, 32u, t, s, ep, ep_mask, lost, unresolved);
+}
+
+// private rows into the global table; a warp per row
+template <uint32_t kRows>
+__device__ __forceinline__ void smem_drain(const Shared& s, const AccTable& g, const EpEntry* __restrict__ ep,
+                                           uint32_t ep_mask, uint32_t* lost, uint32_t* unresolved) {
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (uint32_t i = warp; i < count; i += nwarps) {
-    const uint32_t slot = first + i;
-    const uint64_t key = s.keys[slot];
+  const uint32_t used = min(*s.n_rows, kRows);
+  for (uint32_t r = warp; r < used; r += nwarps) {
+    const uint64_t key = s.rowkey[r];
     if (key == kEmptyKey) continue;   // warp-uniform
-    const uint32_t* row = s.rows + (size_t)slot * kRowWords;
+    const uint32_t* row = s.rows + (size_t)r * kRowWords;
     const uint32_t h0 = row[lane], h1 = row[32u + lane];
     uint32_t c = h0 + h1;
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
     if (c == 0u) continue;            // preloaded but never hit in this launch: no global row needed
     uint32_t grow = 0;
-    if (lane == 0) grow = find_or_insert_pair(g, key, ep, ep_mask);
+    if (lane == 0) grow = find_or_insert_pair(g, key, false, ep, ep_mask);
     grow = __shfl_sync(0xFFFFFFFFu, grow, 0);
     if (grow >= kDropRow) {   // source is not a pod (dropped like the reference does) or capacity
       if (lane == 0) { if (grow == kDropRow) *unresolved += c; else *lost += c; }
       continue;
     }
-    if (h0) atomicAdd(&g.hist[(size_t)grow * ALZ_NB + lane], h0);
-    if (h1) atomicAdd(&g.hist[(size_t)grow * ALZ_NB + 32u + lane], h1);
+    if (h0) red_add_u32(&g.hist[(size_t)grow * ALZ_NB + lane], h0);
+    if (h1) red_add_u32(&g.hist[(size_t)grow * ALZ_NB + 32u + lane], h1);
     if (lane == 0) {
       uint64_t lat = 0;
       for (int q = 0; q < kLatSub; ++q) lat += ((uint64_t)row[ALZ_NB + 2 * q + 1] << 32) + row[ALZ_NB + 2 * q];
-      if (lat) atomicAdd((unsigned long long*)&g.lat_sum[grow], (unsigned long long)lat);
+      if (lat) red_add_u64(&g.lat_sum[grow], lat);
       const uint32_t er = row[ALZ_NB + 2 * kLatSub];
-      if (er) atomicAdd((unsigned long long*)&g.err5xx[grow], (unsigned long long)er);
+      if (er) red_add_u64(&g.err5xx[grow], (uint64_t)er);
     }
   }
 }
 
-// the warp's slow path: lane i takes queue entry (head + i) for i < count
-__device__ __forceinline__ void slow_path_32(const uint64_t* q_key, const uint64_t* q_dur, const uint32_t* q_meta,
-                                             uint32_t head, uint32_t count, const AccTable& fwd, const AccTable& rev,
-                                             const EpEntry* __restrict__ ep, uint32_t ep_mask, uint32_t* lost,
-                                             uint32_t* unresolved) {
-  const uint32_t lane = threadIdx.x & 31u;
-  const bool mine = lane < count;
-  const uint32_t pos = (head + lane) & (kQueue - 1u);
-  uint64_t key = 0, dur = 0;
-  uint32_t meta = 0, row = kLostRow;
-  if (mine) { key = q_key[pos]; dur = q_dur[pos]; meta = q_meta[pos]; }
-  const bool rv = (meta & 0x100u) != 0u;
-  if (mine) row = find_or_insert_pair(rv ? rev : fwd, key, ep, ep_mask);
-  __syncwarp();
-  if (mine) {
-    if (row >= kDropRow) { if (row == kDropRow) *unresolved += 1u; else *lost += 1u; }
-    else {
-      const AccTable& t = rv ? rev : fwd;
-      atomicAdd(&t.hist[(size_t)row * ALZ_NB + (meta & 0xFFu)], 1u);
-      atomicAdd((unsigned long long*)&t.lat_sum[row], (unsigned long long)dur);
-      if (meta & 0x200u) atomicAdd((unsigned long long*)&t.err5xx[row], 1ull);
-    }
-  }
-  __syncwarp();
-}
+// kRecWords = 8: alz_l7_rec (32 B). kRecWords = 4: alz_l7_rec16 (16 B; durations >= 2^32 ns sit in dur_ovf)
+template <int kWarps, int kU, int kRecWords>
+__global__ void __launch_bounds__(kWarps * 32, 1)
+ingest_pairs_v6_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable pairs, Counters* ctr,
+                       const HotState* __restrict__ hot, const EpEntry* __restrict__ ep, uint32_t ep_mask,
+                       const uint64_t* __restrict__ dur_ovf) {
+  using L = Layout<kWarps, kU, kRecWords>;
+  constexpr uint32_t kRows = L::kRows;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t lane_lt = (1u << lane) - 1u;
+  Shared s;
+  s.tab = reinterpret_cast<uint32_t*>(smem_raw + L::kTabOff);
+  s.n_rows = reinterpret_cast<uint32_t*>(smem_raw + L::kMisc);
+  s.rowkey = reinterpret_cast<uint64_t*>(smem_raw + L::kRowKeys);
+  s.rows = reinterpret_cast<uint32_t*>(smem_raw + L::kRowsOff);
+  constexpr uint32_t kColdQ = L::kColdQ;
+  Queue<kColdQ> cold;
+  Queue<kSlowQ> slow;
+  cold.bind(smem_raw + L::kColdOff + (size_t)warp * kColdQ * kQBytes);
+  slow.bind(smem_raw + L::kSlowOff + (size_t)warp * kSlowQ * kQBytes);
+  const uint8_t* ring = smem_raw + (size_t)warp * 2u * L::kChunkBytes;
+  const uint32_t ring_a = smem_u32(ring);
+  const uint32_t bar_a = smem_u32(smem_raw + L::kBars + warp * 16u);
 
-// a fetched dictionary home slot waiting to be used
-struct Pend {
-  uint4 ent;       // the 16-byte DictEnt as loaded
-  uint64_t key, dur;
-  uint32_t meta;   // bit 31 valid, bit 9 5xx, bit 8 reversed, bits 0..7 latency bucket
-};
-
-// use the probes: a hit reduces into its row at once, anything else joins the warp's slow-path queue
-template <int kUnroll>
-__device__ __forceinline__ void consume_probes(const Pend* p, const AccTable& fwd, const AccTable& rev,
-                                               const EpEntry* __restrict__ ep, uint32_t ep_mask, uint64_t* q_key,
-                                               uint64_t* q_dur, uint32_t* q_meta, uint32_t& q_head, uint32_t& q_count,
-                                               uint32_t* lost, uint32_t* unresolved) {
-  const uint32_t lane = threadIdx.x & 31u;
-#pragma unroll
-  for (int u = 0; u < kUnroll; ++u) {
-    const bool g = (p[u].meta & 0x80000000u) != 0u;
-    const bool rv = (p[u].meta & 0x100u) != 0u;
-    const uint64_t k = ((uint64_t)p[u].ent.y << 32) | p[u].ent.x;
-    const bool hit = g && k == p[u].key && p[u].ent.z < kDropRow && p[u].key != kEmptyKey;
-    if (hit) {
-      const AccTable& t = rv ? rev : fwd;
-      atomicAdd(&t.hist[(size_t)p[u].ent.z * ALZ_NB + (p[u].meta & 0xFFu)], 1u);
-      atomicAdd((unsigned long long*)&t.lat_sum[p[u].ent.z], (unsigned long long)p[u].dur);
-      if (p[u].meta & 0x200u) atomicAdd((unsigned long long*)&t.err5xx[p[u].ent.z], 1ull);
-    }
-    const bool slow = g && !hit;
-    const uint32_t m = __ballot_sync(0xFFFFFFFFu, slow);
-    if (slow) {
-      const uint32_t pos = (q_head + q_count + __popc(m & ((1u << lane) - 1u))) & (kQueue - 1u);
-      q_key[pos] = p[u].key;
-      q_dur[pos] = p[u].dur;
-      q_meta[pos] = p[u].meta & 0x3FFu;
-    }
-    q_count += __popc(m);
-    __syncwarp();
-    if (q_count >= 32u) {
-      slow_path_32(q_key, q_dur, q_meta, q_head, 32u, fwd, rev, ep, ep_mask, lost, unresolved);
-      q_head = (q_head + 32u) & (kQueue - 1u);
-      q_count -= 32u;
-    }
-  }
-}
-
-template <int kThreads, int kUnroll, bool kPrefetch, bool kPipe>
-__global__ void __launch_bounds__(kThreads, 1) ingest_pairs_v4_kernel(const alz_l7_rec* __restrict__ recs, uint64_t n,
-                                                                      AccTable fwd, AccTable rev, Counters* ctr,
-                                                                      const HotState* hot_fwd, const HotState* hot_rev,
-                                                                      const EpEntry* __restrict__ ep, uint32_t ep_mask) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  Smem s;
-  s.keys = reinterpret_cast<uint64_t*>(smem_raw);
-  s.tags = reinterpret_cast<uint16_t*>(smem_raw + (size_t)kSlots * 8);
-  s.fill = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kSlots * 10);
-  s.rows = s.fill + (kFwdBuckets + kRevBuckets);
-  // per-warp slow-path queues behind the table
-  uint8_t* qbase = reinterpret_cast<uint8_t*>(s.rows + (size_t)kSlots * kRowWords) + (size_t)(threadIdx.x >> 5) * kQueue * 20;
-  uint64_t* q_key = reinterpret_cast<uint64_t*>(qbase);
-  uint64_t* q_dur = q_key + kQueue;
-  uint32_t* q_meta = reinterpret_cast<uint32_t*>(q_dur + kQueue);
-  uint32_t q_head = 0, q_count = 0;
-  for (uint32_t i = threadIdx.x; i < kSlots; i += kThreads) { s.keys[i] = kEmptyKey; s.tags[i] = 0; }
-  for (uint32_t i = threadIdx.x; i < kFwdBuckets + kRevBuckets; i += kThreads) s.fill[i] = 0u;
-  for (uint32_t i = threadIdx.x; i < kSlots * kRowWords; i += kThreads) s.rows[i] = 0u;
-  __syncthreads();
-  preload_hot(s, hot_fwd, false);
-  preload_hot(s, hot_rev, true);
-  __syncthreads();
-
+  // chunks of this warp: c, c + stride, ... (a chunk = 32 * kU consecutive records); all but possibly the last
+  // chunk of the array are full. 32-bit chunk numbers: n < 2^37 events per launch (the ABI layer splits above).
+  const uint32_t n_chunks = (uint32_t)((n + L::kChunk - 1u) / L::kChunk);
+  const uint32_t c_stride = gridDim.x * kWarps;
+  const uint32_t c_first = blockIdx.x * kWarps + warp;
+  const uint32_t tail = (uint32_t)(n - (uint64_t)(n_chunks - 1u) * L::kChunk);   // events in the last chunk, 1..kChunk
   uint64_t policy;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  // producer state (used by the elected lane): the chunk two iterations ahead and its address
+  uint32_t c_next = c_first;
+  const uint32_t* src_next = recs + (uint64_t)c_first * (L::kChunk * kRecWords);
+  const uint64_t src_step = (uint64_t)c_stride * (L::kChunk * kRecWords);        // in words
+  auto issue = [&](uint32_t stage) {   // one lane; requests chunk c_next if there is one
+    if (c_next < n_chunks) {
+      const uint32_t bytes = (c_next == n_chunks - 1u ? tail : L::kChunk) * (uint32_t)kRecWords * 4u;
+      mbar_expect_tx(bar_a + stage * 8u, bytes);
+      tma_load(ring_a + stage * L::kChunkBytes, src_next, bytes, bar_a + stage * 8u, policy);
+    }
+  };
+  // the first two chunks are requested before the table is even built
+  if (lane == 0) {
+    mbar_init(bar_a, 1u);
+    mbar_init(bar_a + 8u, 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    issue(0u);
+    c_next += c_stride; src_next += src_step;
+    issue(1u);
+  }
+  c_next += 2u * c_stride - (lane == 0 ? c_stride : 0u);   // every lane tracks the producer state, so any lane can be elected
+  src_next += 2u * src_step - (lane == 0 ? src_step : 0u);
 
-  uint32_t not_request = 0, lost = 0, unresolved = 0;
-  Pend pend[kUnroll];
-#pragma unroll
-  for (int u = 0; u < kUnroll; ++u) { pend[u].ent = make_uint4(0u, 0u, 0u, 0u); pend[u].key = 0; pend[u].dur = 0; pend[u].meta = 0u; }
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint64_t stride = (uint64_t)gridDim.x * kThreads;
-  const uint64_t first = (uint64_t)blockIdx.x * kThreads + (threadIdx.x & ~31u);
-  Rec nxt[kUnroll];
-  bool nlive[kUnroll];
-  if (kPrefetch) {   // records of the first iteration
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const uint64_t j = first + (uint64_t)u * stride + lane;
-      nlive[u] = j < n;
-      nxt[u] = Rec{};
-      if (nlive[u]) nxt[u] = load_rec_stream(recs + j, policy);
-    }
-  }
-  for (uint64_t base = first; base < n; base += stride * kUnroll) {
-    __syncwarp();
-    Rec r[kUnroll];
-    bool live[kUnroll];
-    if (kPrefetch) {
-      // take this iteration's records, put the next iteration's loads in flight before any processing
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) { r[u] = nxt[u]; live[u] = nlive[u]; }
-      const uint64_t nb = base + stride * kUnroll;
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        const uint64_t j = nb + (uint64_t)u * stride + lane;
-        nlive[u] = j < n;
-        if (nlive[u]) nxt[u] = load_rec_stream(recs + j, policy);
-      }
-    } else {
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        const uint64_t j = base + (uint64_t)u * stride + lane;
-        live[u] = j < n;
-        r[u] = Rec{};
-        if (live[u]) r[u] = load_rec_stream(recs + j, policy);
-      }
-    }
-    Ev e[kUnroll];
-    int ss[kUnroll];
-    uint32_t sb[kUnroll], hh[kUnroll];
-    bool room[kUnroll];
-    // stage 1: decode, shared-memory lookup (no loop, no divergence)
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      e[u] = decode(r[u], live[u]);
-      not_request += (live[u] && !e[u].act) ? 1u : 0u;
-      hh[u] = pair_hash(e[u].key);
-      sb[u] = bucket_of(hh[u], e[u].rev);
-      ss[u] = smem_lookup(s, sb[u], e[u].key, tag_of(hh[u]), &room[u]);
-      if (!e[u].act || e[u].key == kEmptyKey) ss[u] = -1;
-    }
-    // stage 2: first-come admission of misses while their bucket has room (rare once warm)
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u)
-      if (room[u] && e[u].act && ss[u] < 0 && e[u].key != kEmptyKey)
-        ss[u] = smem_admit(s, sb[u], e[u].key, tag_of(hh[u]));
-    __syncwarp();
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u)
-      if (ss[u] >= 0) smem_accumulate(s, ss[u], e[u].bucket, e[u].dur, e[u].err);
-    // stage 3: the rest goes to the global dictionary. The home slots are fetched now and, with kPipe,
-    // consumed one iteration later, so the L2 round trip of the probe hides behind a whole iteration
-    Pend cur[kUnroll];
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const bool g = e[u].act && ss[u] < 0;
-      const AccTable& t = e[u].rev ? rev : fwd;
-      const uint32_t home = hh[u] & t.dict_mask;
-      cur[u].key = e[u].key;
-      cur[u].dur = e[u].dur;
-      cur[u].meta = g ? (0x80000000u | e[u].bucket | (e[u].rev ? 0x100u : 0u) | (e[u].err ? 0x200u : 0u)) : 0u;
-      cur[u].ent = make_uint4(0u, 0u, 0u, 0u);
-      if (g) cur[u].ent = __ldcg(reinterpret_cast<const uint4*>(&t.dict[home]));
-    }
-    if (kPipe) {
-      consume_probes<kUnroll>(pend, fwd, rev, ep, ep_mask, q_key, q_dur, q_meta, q_head, q_count, &lost, &unresolved);
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) pend[u] = cur[u];
-    } else {
-      consume_probes<kUnroll>(cur, fwd, rev, ep, ep_mask, q_key, q_dur, q_meta, q_head, q_count, &lost, &unresolved);
-    }
-  }
-  if (kPipe) consume_probes<kUnroll>(pend, fwd, rev, ep, ep_mask, q_key, q_dur, q_meta, q_head, q_count, &lost, &unresolved);
-  if (q_count) slow_path_32(q_key, q_dur, q_meta, q_head, q_count, fwd, rev, ep, ep_mask, &lost, &unresolved);
+  for (uint32_t i = threadIdx.x; i < kTab; i += kWarps * 32) s.tab[i] = 0u;
+  for (uint32_t i = threadIdx.x; i <= kRows; i += kWarps * 32) s.rowkey[i] = kEmptyKey;
+  for (uint32_t i = threadIdx.x; i < kRows * kRowWords; i += kWarps * 32) s.rows[i] = 0u;
+  if (threadIdx.x == 0) *s.n_rows = 0u;
   __syncthreads();
-  smem_drain(s, 0u, kFwdBuckets * kWays, fwd, ep, ep_mask, &lost, &unresolved);
-  smem_drain(s, kFwdBuckets * kWays, kRevBuckets * kWays, rev, ep, ep_mask, &lost, &unresolved);
+  if (hot != nullptr) {   // tier A first so that the hottest pairs cannot lose a slot to a cooler one
+    const uint32_t na = min(hot->n_a, (uint32_t)kHotA);
+    const uint32_t nb = min(min(hot->n_b, (uint32_t)(kHotMax - kHotA)), L::kPreload - min(na, L::kPreload));
+    for (uint32_t i = threadIdx.x; i < na; i += kWarps * 32) {
+      const uint64_t k = hot->keys[i];
+      if (k != kEmptyKey) smem_admit(s, k, table_hash(k), L::kPreload, false);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < nb; i += kWarps * 32) {
+      const uint64_t k = hot->keys[kHotA + i];
+      if (k != kEmptyKey) smem_admit(s, k, table_hash(k), L::kPreload, false);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && *s.n_rows > L::kPreload) *s.n_rows = L::kPreload;   // failed claims past the limit
+  }
+  __syncthreads();
+
+  uint32_t lost = 0, unresolved = 0;
+  Probe pend;                          // probes issued, not yet consumed (lanes without an event: meta = 0)
+  pend.ent = make_uint4(0u, 0u, kNoRow, 0u);
+  pend.key = 0; pend.dur = 0; pend.meta = 0;
+  uint32_t it = 0, n_hit = 0, n_live = 0, n_cold = 0;
+  for (uint32_t c = c_first; c < n_chunks; c += c_stride, ++it) {
+    const uint32_t stage = it & 1u;
+    mbar_wait(bar_a + stage * 8u, (it >> 1) & 1u);
+    // records of this chunk into registers (lane l takes records l, l + 32, ...)
+    uint32_t w[kU][kRecWords];
+    const uint8_t* st = ring + stage * L::kChunkBytes;
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const uint4* p = reinterpret_cast<const uint4*>(st + ((size_t)u * 32u + lane) * (kRecWords * 4u));
+      const uint4 a = p[0];
+      w[u][0] = a.x; w[u][1] = a.y; w[u][2] = a.z; w[u][3] = a.w;
+      if (kRecWords == 8) {
+        const uint2 b = *reinterpret_cast<const uint2*>(p + 1);   // duration; write_time is not read here
+        w[u][4] = b.x; w[u][5] = b.y;
+      }
+    }
+    __syncwarp();   // every lane has its records: the stage goes back to the TMA
+    if (elect_one()) issue(stage);
+    c_next += c_stride; src_next += src_step;
+    const uint32_t n_here = (c == n_chunks - 1u) ? tail : L::kChunk;
+    n_live += n_here;
+
+    // hot tier for all kU events of the lane (independent chains), then one pass over the cold queue
+    uint64_t key[kU], dur[kU];
+    uint32_t meta[kU];
+    bool coldf[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const bool live = (uint32_t)u * 32u + lane < n_here;
+      const uint32_t mw = (kRecWords == 8) ? w[u][3] : w[u][2];   // status | protocol << 16 | method_flags << 24
+      uint32_t p = __byte_perm(mw, 0u, 0x4442u);                  // protocol byte
+      if (kRecWords == 8) dur[u] = ((uint64_t)w[u][5] << 32) | w[u][4];
+      else {
+        dur[u] = w[u][3];
+        if (p & 0x80u) { dur[u] = live ? __ldg(&dur_ovf[w[u][3]]) : 0ull; p &= 0x7Fu; }
+      }
+      const uint32_t cls = shr_clamp(kProtoLut, 3u * p);
+      // a row is built unless the class says "payload parser decides" and the parser said no (bit 30 of mw)
+      const bool act = live && (cls & 1u) && !((cls & 2u) && (mw & ((uint32_t)ALZ_MF_PAYLOAD_REJECT << 24)));
+      const bool rv = (cls & 4u) && (mw & ((uint32_t)ALZ_MF_METHOD_MASK << 24)) == (2u << 24);   // DELIVER / PUSHED_EVENT
+      const bool err = p == ALZ_PROTO_HTTP && ((mw & 0xFFFFu) - 500u) < 100u;
+      key[u] = ((uint64_t)w[u][1] << 32) | w[u][0];               // make_pair_key: the record's first two words as they lie
+      const uint32_t bucket = latency_bucket_rz(dur[u]);
+      meta[u] = bucket | (rv ? 0x100u : 0u) | (err ? 0x200u : 0u);
+
+      // direct-mapped probe, verified against the row's key
+      const uint32_t h = table_hash(key[u]);
+      const uint32_t x = s.tab[h >> kTabShift] ^ tab_fp(h);
+      const uint32_t r = min(x, kRows);
+      const bool hit = act && !rv && x < kRows && s.rowkey[r] == key[u];
+      if (hit) {
+        ++n_hit;
+        uint32_t* row = s.rows + r * kRowWords;
+        atomicAdd(&row[bucket], 1u);
+        uint32_t* lat = row + ALZ_NB + 2u * (lane & (kLatSub - 1u));
+        const uint32_t lo = (uint32_t)dur[u], dhi = (uint32_t)(dur[u] >> 32);
+        const uint32_t old = atomicAdd(&lat[0], lo);
+        if (old > ~lo || dhi != 0u) atomicAdd(&lat[1], dhi + (old > ~lo ? 1u : 0u));   // carry out of the low word
+        if (err) atomicAdd(&row[ALZ_NB + 2 * kLatSub], 1u);
+      }
+      coldf[u] = act && !hit;
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) n_cold += cold.push(coldf[u], key[u], dur[u], meta[u], lane_lt);
+    __syncwarp();
+    while (cold.count >= 32u) {
+      const Probe now = cold_issue(cold, 32u, pairs);
+      cold_consume<kRows>(pend, slow, pairs, s, ep, ep_mask, lane_lt, &lost, &unresolved);
+      pend = now;
+    }
+  }
+  if (cold.count) {
+    const Probe now = cold_issue(cold, cold.count, pairs);
+    cold_consume<kRows>(pend, slow, pairs, s, ep, ep_mask, lane_lt, &lost, &unresolved);
+    pend = now;
+  }
+  cold_consume<kRows>(pend, slow, pairs, s, ep, ep_mask, lane_lt, &lost, &unresolved);
+  while (slow.count) slow_batch<kRows>(slow, min(slow.count, 32u), pairs, s, ep, ep_mask, &lost, &unresolved);
+  __syncthreads();
+  smem_drain<kRows>(s, pairs, ep, ep_mask, &lost, &unresolved);
   for (int o = 16; o > 0; o >>= 1) {
-    not_request += __shfl_xor_sync(0xFFFFFFFFu, not_request, o);
+    n_hit += __shfl_xor_sync(0xFFFFFFFFu, n_hit, o);
     lost += __shfl_xor_sync(0xFFFFFFFFu, lost, o);
     unresolved += __shfl_xor_sync(0xFFFFFFFFu, unresolved, o);
   }
+  // events that built no request row = events seen - hot hits - cold pushes (the last two are counted anyway)
+  const uint32_t not_request = n_live - n_cold - n_hit;
   if (lane == 0) {
     if (not_request) atomicAdd(&ctr->not_request, (unsigned long long)not_request);
     if (lost) atomicAdd(&ctr->capacity_events, (unsigned long long)lost);
@@ -372,74 +473,77 @@ __global__ void __launch_bounds__(kThreads, 1) ingest_pairs_v4_kernel(const alz_
 }
 
 // ---- hot-pair feedback: after a fold, pick the pairs that took the most events -----
-// fold_pairs_kernel left row_cnt[row] and a 128-bin (quarter-octave) histogram of the
-// counts; thresholds = the lowest bins that keep tier A <= kHotA and A+B <= target.
-__global__ void hot_pick_kernel(HotState* hot, uint32_t target_total) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  uint32_t cum = 0, thr_a = 128, thr_b = 128;
-  for (int b = 127; b >= 0; --b) {
-    cum += hot->bins[b];
-    if (cum <= (uint32_t)kHotA) thr_a = (uint32_t)b;
-    if (cum <= target_total) thr_b = (uint32_t)b;
+// fold_pairs_kernel left row_cnt[row] and a 128-bin (quarter-octave) histogram of the counts of the
+// forward rows; thresholds = the lowest bins that keep tier A <= kHotA and A+B <= target. Every block
+// derives the same two thresholds from the bins itself (128 adds) instead of a separate launch.
+__global__ void __launch_bounds__(256) hot_emit_kernel(AccTable pairs, HotState* hot, uint32_t target_total) {
+  __shared__ uint32_t s_thr[2];
+  if (threadIdx.x == 0) {
+    uint32_t cum = 0, thr_a = 128, thr_b = 128;
+    for (int b = 127; b >= 0; --b) {
+      cum += hot->bins[b];
+      if (cum <= (uint32_t)kHotA) thr_a = (uint32_t)b;
+      if (cum <= target_total) thr_b = (uint32_t)b;
+    }
+    s_thr[0] = thr_a; s_thr[1] = thr_b;
+    if (blockIdx.x == 0) { hot->thr_a = thr_a; hot->thr_b = thr_b; }
   }
-  hot->thr_a = thr_a;
-  hot->thr_b = thr_b;
-  hot->n_a = 0;
-  hot->n_b = 0;
-}
-__global__ void __launch_bounds__(256) hot_emit_kernel(AccTable pairs, HotState* hot) {
+  __syncthreads();
+  const uint32_t thr_a = s_thr[0], thr_b = s_thr[1];
   const uint32_t n_rows = min(*pairs.n_rows, pairs.max_rows);
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t row = blockIdx.x * blockDim.x + threadIdx.x; row < n_rows; row += stride) {
     const uint32_t c = pairs.row_cnt[row];
-    if (c == 0u) continue;
+    if (c == 0u || pairs.row_rev[row]) continue;     // reversed rows never enter the per-CTA table
     const uint32_t b = count_bin(c);
-    if (b >= hot->thr_a) {
+    if (b >= thr_a) {
       const uint32_t p = atomicAdd(&hot->n_a, 1u);
-      if (p < (uint32_t)kHotA) hot->keys_a[p] = pairs.row_key[row];
-    } else if (b >= hot->thr_b) {
+      if (p < (uint32_t)kHotA) hot->keys[p] = pairs.row_key[row];
+    } else if (b >= thr_b) {
       const uint32_t p = atomicAdd(&hot->n_b, 1u);
-      if (p < (uint32_t)kHotB) hot->keys_b[p] = pairs.row_key[row];
+      if (p < (uint32_t)(kHotMax - kHotA)) hot->keys[kHotA + p] = pairs.row_key[row];
     }
   }
 }
 
-}  // namespace
-
-template <int kThreads, int kUnroll, bool kPrefetch, bool kPipe>
-static void launch_variant(const alz_l7_rec* recs, uint64_t n, const AccTable& fwd, const AccTable& rev, Counters* ctr,
-                           const HotState* hot_fwd, const HotState* hot_rev, const EpEntry* ep, uint32_t ep_mask,
-                           int sms, cudaStream_t s) {
-  const size_t smem = (size_t)kSlots * 10 + (size_t)(kFwdBuckets + kRevBuckets) * 4 + (size_t)kSlots * kRowWords * 4 +
-                      (size_t)(kThreads / 32) * kQueue * 20;
+template <int kWarps, int kU, int kRecWords>
+void launch_variant(const void* recs, uint64_t n, const AccTable& pairs, Counters* ctr, const HotState* hot,
+                    const EpEntry* ep, uint32_t ep_mask, const uint64_t* dur_ovf, int sms, cudaStream_t s) {
+  using L = Layout<kWarps, kU, kRecWords>;
   // per device (a process may drive several GPUs), so not cached in a static
-  cudaFuncSetAttribute(ingest_pairs_v4_kernel<kThreads, kUnroll, kPrefetch, kPipe>,
-                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  ingest_pairs_v4_kernel<kThreads, kUnroll, kPrefetch, kPipe><<<(unsigned)sms, kThreads, smem, s>>>(
-      recs, n, fwd, rev, ctr, hot_fwd, hot_rev, ep, ep_mask);
+  cudaFuncSetAttribute(ingest_pairs_v6_kernel<kWarps, kU, kRecWords>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)L::kBytes);
+  ingest_pairs_v6_kernel<kWarps, kU, kRecWords><<<(unsigned)sms, kWarps * 32, L::kBytes, s>>>(
+      (const uint32_t*)recs, n, pairs, ctr, hot, ep, ep_mask, dur_ovf);
 }
 
-void launch_ingest_pairs_v4(const alz_l7_rec* recs, uint64_t n, const AccTable& fwd, const AccTable& rev,
-                            Counters* ctr, const HotState* hot_fwd, const HotState* hot_rev, const EpEntry* ep,
-                            uint32_t ep_mask, int sms, cudaStream_t s) {
+}  // namespace
+
+uint32_t ingest_table_rows() { return Layout<16, 2, 8>::kRows; }
+
+void launch_ingest_pairs_v6(const alz_l7_rec* recs, uint64_t n, const AccTable& pairs, Counters* ctr,
+                            const HotState* hot, const EpEntry* ep, uint32_t ep_mask, int sms, cudaStream_t s) {
   if (n == 0) return;
-  // ALZ_INGEST_VARIANT: tuning knob for profiling runs (default = the measured best)
-  static const int variant = [] { const char* v = getenv("ALZ_INGEST_VARIANT"); return v ? atoi(v) : 0; }();
-  switch (variant) {
-    case 1: launch_variant<1024, 2, false, true>(recs, n, fwd, rev, ctr, hot_fwd, hot_rev, ep, ep_mask, sms, s); break;
-    case 2: launch_variant<768, 2, true, true>(recs, n, fwd, rev, ctr, hot_fwd, hot_rev, ep, ep_mask, sms, s); break;
-    case 3: launch_variant<768, 2, false, true>(recs, n, fwd, rev, ctr, hot_fwd, hot_rev, ep, ep_mask, sms, s); break;
-    case 4: launch_variant<1024, 2, true, false>(recs, n, fwd, rev, ctr, hot_fwd, hot_rev, ep, ep_mask, sms, s); break;
-    case 5: launch_variant<1024, 2, true, true>(recs, n, fwd, rev, ctr, hot_fwd, hot_rev, ep, ep_mask, sms, s); break;
-    default: launch_variant<1024, 2, false, false>(recs, n, fwd, rev, ctr, hot_fwd, hot_rev, ep, ep_mask, sms, s); break;
+  // ALZ_INGEST_SHAPE: CTA shape for profiling runs (default = the measured best)
+  static const int shape = [] { const char* v = getenv("ALZ_INGEST_SHAPE"); return v ? atoi(v) : 0; }();
+  switch (shape) {
+    case 1: launch_variant<32, 1, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, nullptr, sms, s); break;
+    case 2: launch_variant<12, 2, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, nullptr, sms, s); break;
+    case 3: launch_variant<20, 2, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, nullptr, sms, s); break;
+    default: launch_variant<16, 2, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, nullptr, sms, s); break;
   }
 }
 
+void launch_ingest_pairs_v6_rec16(const alz_l7_rec16* recs, uint64_t n, const uint64_t* dur_ovf, const AccTable& pairs,
+                                  Counters* ctr, const HotState* hot, const EpEntry* ep, uint32_t ep_mask, int sms,
+                                  cudaStream_t s) {
+  if (n == 0) return;
+  launch_variant<16, 2, 4>(recs, n, pairs, ctr, hot, ep, ep_mask, dur_ovf, sms, s);
+}
+
 // after fold_pairs_kernel(pairs, ..., hot->bins): choose next window's hot list
-void launch_hot_select(const AccTable& pairs, HotState* hot, bool rev, int sms, cudaStream_t s) {
-  const uint32_t target = rev ? (kRevBuckets * kWays * 7u) / 8u : (kFwdBuckets * kWays * 7u) / 8u;
-  hot_pick_kernel<<<1, 32, 0, s>>>(hot, target);
-  hot_emit_kernel<<<(unsigned)sms * 4, 256, 0, s>>>(pairs, hot);
+void launch_hot_select(const AccTable& pairs, HotState* hot, int sms, cudaStream_t s) {
+  hot_emit_kernel<<<(unsigned)sms * 2, 256, 0, s>>>(pairs, hot, Layout<16, 2, 8>::kPreload);
 }
 
 }  // namespace alz

@@ -14,13 +14,15 @@
 // version let lanes leave the probe loops on their own paths and the
 // reductions then issued with ~2 active lanes per instruction
 // (profiles/r1_v2_ingest_ncu.txt).
+#include <algorithm>
+
 #include "alz_kernels.cuh"
 
 namespace alz {
 
 // per-event fields every plan needs
 struct Ev {
-  uint64_t key;   // (saddr << 32) | daddr
+  uint64_t key;   // make_pair_key(saddr, daddr)
   uint64_t dur;
   uint32_t bucket;
   bool act;       // the reference would hand a row to PersistRequest (before resolve)
@@ -32,7 +34,7 @@ __device__ __forceinline__ Ev decode(const Rec& r, bool live) {
   const uint32_t proto = rec_protocol(r), mf = rec_mflags(r);
   e.act = live && emits_request_row(proto, mf);
   e.rev = is_reversed(proto, mf);
-  e.key = ((uint64_t)rec_saddr(r) << 32) | rec_daddr(r);
+  e.key = make_pair_key(rec_saddr(r), rec_daddr(r));
   e.dur = rec_duration(r);
   e.bucket = latency_bucket(e.dur);
   e.err = is_5xx(proto, rec_status(r));
@@ -65,8 +67,9 @@ __device__ __forceinline__ void flush_thread_counters(Counters* ctr, uint32_t no
 // ---------------------------------------------------------------------------
 template <int UNROLL>
 __global__ void __launch_bounds__(256) ingest_pairs_kernel(const alz_l7_rec* __restrict__ recs, uint64_t n,
-                                                           AccTable fwd, AccTable rev, Counters* ctr) {
-  uint32_t not_request = 0, lost = 0;
+                                                           AccTable pairs, Counters* ctr, const EpEntry* __restrict__ ep,
+                                                           uint32_t ep_mask) {
+  uint32_t not_request = 0, lost = 0, unresolved = 0;
   const uint32_t lane = threadIdx.x & 31u;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride * UNROLL) {
@@ -83,15 +86,16 @@ __global__ void __launch_bounds__(256) ingest_pairs_kernel(const alz_l7_rec* __r
       const Ev e = decode(r[u], live[u]);
       not_request += (live[u] && !e.act) ? 1u : 0u;
       uint32_t row = kLostRow;
-      if (e.act) row = find_or_insert(e.rev ? rev : fwd, e.key);
+      if (e.act) row = find_or_insert_pair(pairs, e.key, e.rev, ep, ep_mask);
       __syncwarp();
       if (e.act) {
-        if (row >= kLostRow) ++lost;
-        else global_accumulate(e.rev ? rev : fwd, row, e.bucket, e.dur, e.err);
+        if (row == kDropRow) ++unresolved;
+        else if (row >= kLostRow) ++lost;
+        else global_accumulate(pairs, row, e.bucket, e.dur, e.err);
       }
     }
   }
-  flush_thread_counters(ctr, not_request, 0u, lost);
+  flush_thread_counters(ctr, not_request, unresolved, lost);
 }
 
 // ---------------------------------------------------------------------------
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__(256) ingest_eager_kernel(const alz_l7_rec* __r
     not_request += (live && !e.act) ? 1u : 0u;
     uint64_t ekey = 0;
     bool ok = false;
-    if (e.act) ok = resolve_edge(ep, ep_mask, (uint32_t)(e.key >> 32), (uint32_t)e.key, e.rev, &ekey);
+    if (e.act) ok = resolve_edge(ep, ep_mask, pair_saddr(e.key), pair_daddr(e.key), e.rev, &ekey);
     __syncwarp();
     unresolved += (e.act && !ok) ? 1u : 0u;
     uint32_t row = kLostRow;
@@ -137,21 +141,30 @@ __global__ void __launch_bounds__(256) ingest_eager_kernel(const alz_l7_rec* __r
 // pass 1, a thread per pair row: resolve and find the edge row. All the dependent
 // table/dictionary probes of a pair sit in one thread, 32 pairs per warp in flight
 // (the one-warp-per-row version spent its time in lane 0's probe chain).
-__global__ void __launch_bounds__(256) fold_resolve_kernel(AccTable pairs, bool rev, const EpEntry* __restrict__ ep,
-                                                           uint32_t ep_mask, AccTable edges) {
+__global__ void __launch_bounds__(256) fold_resolve_kernel(AccTable pairs, const EpEntry* __restrict__ ep,
+                                                           uint32_t ep_mask, AccTable edges, HotState* hot) {
+  // the hot-list bookkeeping of this fold starts from zero (fold_pairs_kernel fills the bins, hot_emit
+  // the list; both run after this kernel, the ingest launches that read the list ran before it)
+  if (blockIdx.x == 0 && hot != nullptr) {
+    if (threadIdx.x < 128) hot->bins[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) { hot->n_a = 0u; hot->n_b = 0u; }
+  }
   const uint32_t n_rows = min(*pairs.n_rows, pairs.max_rows);
   const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= n_rows; i += stride) {
-    const uint32_t row = (i == n_rows) ? pairs.max_rows : i;
-    const uint64_t key = (row == pairs.max_rows) ? kEmptyKey : pairs.row_key[row];
-    if (row == pairs.max_rows) {                               // the sentinel row exists even when unused
+  // rows [0, n_rows) plus the two sentinel rows (index n_rows + k stands for row max_rows + k)
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rows + 2u; i += stride) {
+    const bool sentinel = i >= n_rows;
+    const uint32_t row = sentinel ? pairs.max_rows + (i - n_rows) : i;
+    const uint64_t key = sentinel ? kEmptyKey : pairs.row_key[row];
+    const bool rev = sentinel ? (i - n_rows) != 0u : pairs.row_rev[row] != 0u;
+    if (sentinel) {                                            // the sentinel rows exist even when unused
       uint32_t any = 0;
       for (int b = 0; b < ALZ_NB; ++b) any |= pairs.hist[(size_t)row * ALZ_NB + b];
       if (any == 0u) { pairs.row_aux[row] = kDropRow; continue; }
     }
     uint64_t ekey = 0;
     uint32_t erow = kDropRow;                                  // source is not a pod: data.go:829-832
-    if (resolve_edge(ep, ep_mask, (uint32_t)(key >> 32), (uint32_t)key, rev, &ekey)) erow = find_or_insert(edges, ekey);
+    if (resolve_edge(ep, ep_mask, pair_saddr(key), pair_daddr(key), rev, &ekey)) erow = find_or_insert(edges, ekey);
     pairs.row_aux[row] = erow;
   }
 }
@@ -164,12 +177,12 @@ __global__ void __launch_bounds__(256) fold_pairs_kernel(AccTable pairs, AccTabl
   const uint32_t lane = threadIdx.x & 31u, sl = lane & 7u;
   const uint32_t groups_per_grid = (gridDim.x * blockDim.x) >> 3;
   const uint32_t n_rows = min(*pairs.n_rows, pairs.max_rows);
-  const uint32_t n_iter = (n_rows + 1u + groups_per_grid - 1u) / groups_per_grid;   // same trip count for every lane
+  const uint32_t n_iter = (n_rows + 2u + groups_per_grid - 1u) / groups_per_grid;   // same trip count for every lane
   uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-  // rows [0, n_rows) plus the sentinel row (index n_rows stands for row max_rows)
+  // rows [0, n_rows) plus the two sentinel rows (index n_rows + k stands for row max_rows + k)
   for (uint32_t it = 0; it < n_iter; ++it, i += groups_per_grid) {
-    const bool valid = i <= n_rows;
-    const uint32_t row = !valid ? 0u : (i == n_rows) ? pairs.max_rows : i;
+    const bool valid = i < n_rows + 2u;
+    const uint32_t row = !valid ? 0u : (i >= n_rows) ? pairs.max_rows + (i - n_rows) : i;
     uint4* cells = reinterpret_cast<uint4*>(pairs.hist + (size_t)row * ALZ_NB + sl * 8u);
     uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
     if (valid) { a = cells[0]; b = cells[1]; }
@@ -178,10 +191,10 @@ __global__ void __launch_bounds__(256) fold_pairs_kernel(AccTable pairs, AccTabl
     cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 2);
     cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 4);
     if (!valid || cnt == 0) continue;  // unused sentinel row (allocated rows always hold >= 1 event)
-    if (sl == 0 && row != pairs.max_rows && pairs.row_cnt != nullptr) {   // feedback for the next ingest
+    if (sl == 0 && row < pairs.max_rows && pairs.row_cnt != nullptr) {    // feedback for the next ingest
       const uint32_t c32 = cnt > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)cnt;
       pairs.row_cnt[row] = c32;
-      if (hot_bins != nullptr) atomicAdd(&hot_bins[count_bin(c32)], 1u);
+      if (hot_bins != nullptr && !pairs.row_rev[row]) atomicAdd(&hot_bins[count_bin(c32)], 1u);
     }
     const uint32_t erow = pairs.row_aux[row];
     if (erow < kDropRow) {
@@ -202,7 +215,7 @@ __global__ void __launch_bounds__(256) fold_pairs_kernel(AccTable pairs, AccTabl
       }
     } else if (sl == 0) {
       if (erow == kDropRow) atomicAdd(&ctr->src_unresolved, (unsigned long long)cnt);
-      else atomicAdd(&ctr->capacity_events, (unsigned long long)cnt);
+      else atomicAdd(&ctr->fold_lost_events, (unsigned long long)cnt);
     }
     cells[0] = make_uint4(0u, 0u, 0u, 0u);
     cells[1] = make_uint4(0u, 0u, 0u, 0u);
@@ -324,20 +337,37 @@ __global__ void __launch_bounds__(256) synth_owned_kernel(alz_synth_view v, uint
 // ---------------------------------------------------------------------------
 static inline unsigned grid_for(int sms, int per_sm) { return (unsigned)(sms * per_sm); }
 
-void launch_ingest_pairs_v1(const alz_l7_rec* recs, uint64_t n, const AccTable& fwd, const AccTable& rev,
-                            Counters* ctr, int sms, cudaStream_t s) {
+void launch_ingest_pairs_v1(const alz_l7_rec* recs, uint64_t n, const AccTable& pairs, Counters* ctr,
+                            const EpEntry* ep, uint32_t ep_mask, int sms, cudaStream_t s) {
   if (n == 0) return;   // global reductions only (ALZ_CFG_NO_SMEM_CACHE; kept for the ncu comparison)
-  ingest_pairs_kernel<4><<<grid_for(sms, 8), 256, 0, s>>>(recs, n, fwd, rev, ctr);
+  ingest_pairs_kernel<4><<<grid_for(sms, 8), 256, 0, s>>>(recs, n, pairs, ctr, ep, ep_mask);
 }
 void launch_ingest_eager(const alz_l7_rec* recs, uint64_t n, const EpEntry* ep, uint32_t ep_mask,
                          const AccTable& edges, Counters* ctr, int sms, cudaStream_t s) {
   if (n == 0) return;
   ingest_eager_kernel<<<grid_for(sms, 8), 256, 0, s>>>(recs, n, ep, ep_mask, edges, ctr);
 }
-void launch_fold_pairs(const AccTable& pairs, bool rev, const EpEntry* ep, uint32_t ep_mask,
-                       const AccTable& edges, Counters* ctr, uint32_t* hot_bins, int sms, cudaStream_t s) {
-  fold_resolve_kernel<<<grid_for(sms, 4), 256, 0, s>>>(pairs, rev, ep, ep_mask, edges);
-  fold_pairs_kernel<<<grid_for(sms, 8), 256, 0, s>>>(pairs, edges, ctr, hot_bins);
+void launch_fold_resolve(const AccTable& pairs, const EpEntry* ep, uint32_t ep_mask, const AccTable& edges,
+                         Counters* ctr, HotState* hot, int sms, cudaStream_t s) {
+  (void)ctr;
+  fold_resolve_kernel<<<grid_for(sms, 4), 256, 0, s>>>(pairs, ep, ep_mask, edges, hot);
+}
+void launch_fold_add(const AccTable& pairs, const AccTable& edges, Counters* ctr, HotState* hot, int sms,
+                     cudaStream_t s) {
+  fold_pairs_kernel<<<grid_for(sms, 8), 256, 0, s>>>(pairs, edges, ctr, hot ? hot->bins : nullptr);
+}
+// changed slots of the endpoint table (alz_table_commit): patch[i] = {slot, pad x3, entry}
+__global__ void __launch_bounds__(256) ep_patch_kernel(EpEntry* __restrict__ tab, const uint4* __restrict__ patch, uint32_t n) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint4 hd = patch[2 * i], e = patch[2 * i + 1];
+    *reinterpret_cast<uint4*>(&tab[hd.x]) = e;
+  }
+}
+void launch_ep_patch(EpEntry* tab, const void* patch, uint32_t n, int sms, cudaStream_t s) {
+  if (n == 0) return;
+  const unsigned grid = (unsigned)std::min<uint32_t>((n + 255u) / 256u, (uint32_t)sms * 4u);
+  ep_patch_kernel<<<grid, 256, 0, s>>>(tab, (const uint4*)patch, n);
 }
 void launch_iota(uint32_t* out, uint32_t n, int sms, cudaStream_t s) {
   if (n == 0) return;

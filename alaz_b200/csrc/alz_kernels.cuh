@@ -4,16 +4,22 @@
 #include "../synth/alz_synth.h"
 
 namespace alz {
-void launch_ingest_pairs_v1(const alz_l7_rec* recs, uint64_t n, const AccTable& fwd, const AccTable& rev,
-                            Counters* ctr, int sms, cudaStream_t s);
-void launch_ingest_pairs_v4(const alz_l7_rec* recs, uint64_t n, const AccTable& fwd, const AccTable& rev,
-                            Counters* ctr, const HotState* hot_fwd, const HotState* hot_rev, const EpEntry* ep,
-                            uint32_t ep_mask, int sms, cudaStream_t s);
-void launch_hot_select(const AccTable& pairs, HotState* hot, bool rev, int sms, cudaStream_t s);
+void launch_ingest_pairs_v1(const alz_l7_rec* recs, uint64_t n, const AccTable& pairs, Counters* ctr,
+                            const EpEntry* ep, uint32_t ep_mask, int sms, cudaStream_t s);
+void launch_ingest_pairs_v6(const alz_l7_rec* recs, uint64_t n, const AccTable& pairs, Counters* ctr,
+                            const HotState* hot, const EpEntry* ep, uint32_t ep_mask, int sms, cudaStream_t s);
+void launch_ingest_pairs_v6_rec16(const alz_l7_rec16* recs, uint64_t n, const uint64_t* dur_ovf, const AccTable& pairs,
+                                  Counters* ctr, const HotState* hot, const EpEntry* ep, uint32_t ep_mask, int sms,
+                                  cudaStream_t s);
+uint32_t ingest_table_rows();
+void launch_hot_select(const AccTable& pairs, HotState* hot, int sms, cudaStream_t s);
 void launch_ingest_eager(const alz_l7_rec* recs, uint64_t n, const EpEntry* ep, uint32_t ep_mask,
                          const AccTable& edges, Counters* ctr, int sms, cudaStream_t s);
-void launch_fold_pairs(const AccTable& pairs, bool rev, const EpEntry* ep, uint32_t ep_mask,
-                       const AccTable& edges, Counters* ctr, uint32_t* hot_bins, int sms, cudaStream_t s);
+void launch_fold_resolve(const AccTable& pairs, const EpEntry* ep, uint32_t ep_mask, const AccTable& edges,
+                         Counters* ctr, HotState* hot, int sms, cudaStream_t s);
+void launch_fold_add(const AccTable& pairs, const AccTable& edges, Counters* ctr, HotState* hot, int sms,
+                     cudaStream_t s);
+void launch_ep_patch(EpEntry* tab, const void* patch, uint32_t n, int sms, cudaStream_t s);
 void launch_iota(uint32_t* out, uint32_t n, int sms, cudaStream_t s);
 void launch_gather_edges(const AccTable& edges, const uint64_t* keys, const uint32_t* rows, uint32_t n_live,
                          alz_edge_out* out, bool reset, int sms, cudaStream_t s);

@@ -12,6 +12,7 @@
 // with an open-addressed (pid,fd) index in HBM and each query does the reference's binary search
 // and its open/closed-gap rules on the device.
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -143,6 +144,7 @@ static void add_value(std::vector<SockRec>& v, uint64_t ts, const alz_tcp_rec* s
 
 extern "C" int alz_submit_tcp(alz_handle* h, const alz_tcp_rec* recs, size_t n) {
   if (!h || (!recs && n)) return ALZ_E_INVAL;
+  std::lock_guard<std::mutex> g(h->mu);
   if (!h->sock) h->sock = new alz_sock_state();
   alz_sock_state* s = h->sock;
   for (size_t i = 0; i < n; ++i) {
@@ -200,6 +202,7 @@ static int upload_lines(alz_handle* h) {
 extern "C" int alz_sock_lookup(alz_handle* h, const alz_sock_query* q, size_t n, alz_sock_result* out) {
   if (!h || (!q && n) || (!out && n)) return ALZ_E_INVAL;
   if (n == 0) return ALZ_OK;
+  std::lock_guard<std::mutex> g(h->mu);
   CK(cudaSetDevice(h->device));
   if (!h->sock) h->sock = new alz_sock_state();
   alz_sock_state* s = h->sock;

@@ -63,10 +63,16 @@ Aggregator::Aggregator(DataStore* ds, const AggregatorConfig& cfg) : ds_(ds), cf
   c.max_endpoints = cfg.MaxEndpoints;
   c.max_pairs = cfg.MaxPairs;
   c.max_batch = (uint32_t)cfg.BatchSize;
+  if (cfg_.BatchSize == 0) cfg_.BatchSize = 1;
   const int rc = alz_create(&c, &h_);
   if (rc != ALZ_OK) { err_ = alz_strerror(rc); h_ = nullptr; return; }
   void* p = nullptr;
-  if (alz_pinned_alloc(cfg.BatchSize * sizeof(alz_l7_rec), &p) != ALZ_OK) { err_ = "alz_pinned_alloc"; return; }
+  if (alz_pinned_alloc(cfg_.BatchSize * sizeof(alz_l7_rec), &p) != ALZ_OK) {
+    err_ = "alz_pinned_alloc";   // no batch buffer: the aggregator is unusable, Ok() says so
+    alz_destroy(h_);
+    h_ = nullptr;
+    return;
+  }
   batch_ = static_cast<alz_l7_rec*>(p);
   out_.resize(cfg.MaxPairs);
 }
@@ -76,19 +82,41 @@ Aggregator::~Aggregator() {
   if (h_) alz_destroy(h_);
 }
 
-uint32_t Aggregator::Intern(std::unordered_map<std::string, uint32_t>& ids, std::vector<std::string>& names,
-                            const std::string& uid) {
+uint32_t Aggregator::Interner::Acquire(const std::string& uid) {
   auto it = ids.find(uid);
   if (it != ids.end()) return it->second;
-  const uint32_t id = (uint32_t)names.size();
+  uint32_t id;
+  if (!free_ids.empty()) { id = free_ids.back(); free_ids.pop_back(); names[id] = uid; }
+  else { id = (uint32_t)names.size(); names.push_back(uid); refs.push_back(0); }
   ids.emplace(uid, id);
-  names.push_back(uid);
   return id;
+}
+void Aggregator::Interner::Map(uint32_t ip, uint32_t id) {
+  auto it = ip_to_id.find(ip);
+  if (it != ip_to_id.end()) { if (it->second == id) return; Unmap(ip); }
+  ip_to_id[ip] = id;
+  refs[id]++;
+}
+void Aggregator::Interner::Unmap(uint32_t ip) {
+  auto it = ip_to_id.find(ip);
+  if (it == ip_to_id.end()) return;
+  const uint32_t id = it->second;
+  ip_to_id.erase(it);
+  // no IP resolves to the id any more: edges of the open window may still carry it, so it is recycled one
+  // window later (a UID whose stale IP entry is still in the table keeps its id, like the reference keeps the
+  // map entry: ADD/UPDATE never delete the old IP, aggregator/persist.go:55-65)
+  if (--refs[id] == 0) pending_free.push_back(id);
+}
+void Aggregator::Interner::EndWindow() {
+  for (uint32_t id : pending_free)
+    if (refs[id] == 0) { ids.erase(names[id]); free_ids.push_back(id); }
+  pending_free.clear();
 }
 
 // processPod / processSvc: ADD and UPDATE write map[ip] = uid, DELETE removes (persist.go:55-71, 114-130)
 void Aggregator::ProcessK8s(const K8sResourceMessage& m) {
   if (!h_) return;
+  std::lock_guard<std::mutex> g(mu_);
   const bool pod = m.ResourceType == "Pod";
   if (!pod && m.ResourceType != "Service") return;   // other kinds are only relayed to the backend
   if (m.IP.empty()) return;                          // persist.go:37-40
@@ -98,11 +126,15 @@ void Aggregator::ProcessK8s(const K8sResourceMessage& m) {
   // events already batched were resolved by the reference with the tables as they were: submit first
   if (batch_n_) SubmitBatch();
   const int table = pod ? ALZ_TABLE_POD : ALZ_TABLE_SVC;
+  Interner& in = pod ? pods_ : svcs_;
   if (m.EventType == "Add" || m.EventType == "Update") {
-    const uint32_t id = pod ? Intern(pod_ids_, pod_uids_, m.UID) : Intern(svc_ids_, svc_uids_, m.UID);
-    alz_table_upsert(h_, table, ip, id);
+    const uint32_t id = in.Acquire(m.UID);
+    const int rc = alz_table_upsert(h_, table, ip, id);
+    if (rc != ALZ_OK) { err_ = std::string("alz_table_upsert: ") + alz_strerror(rc); return; }
+    in.Map(ip, id);
   } else if (m.EventType == "Delete") {
     alz_table_erase(h_, table, ip);
+    in.Unmap(ip);
   } else {
     return;
   }
@@ -113,19 +145,27 @@ int Aggregator::SubmitBatch() {
   if (!h_) return ALZ_E_STATE;
   if (tables_dirty_) {
     const int rc = alz_table_commit(h_);
-    if (rc != ALZ_OK) return rc;
+    if (rc != ALZ_OK) {   // events batched behind a failed commit are dropped, never left to pile up
+      dropped_events_ += batch_n_;
+      batch_n_ = 0;
+      err_ = std::string("alz_table_commit: ") + alz_strerror(rc);
+      return rc;
+    }
     tables_dirty_ = false;
   }
   if (batch_n_ == 0) return ALZ_OK;
   const int rc = alz_submit_l7(h_, batch_, batch_n_);
-  batch_n_ = 0;
+  if (rc != ALZ_OK) { dropped_events_ += batch_n_; err_ = std::string("alz_submit_l7: ") + alz_strerror(rc); }
+  batch_n_ = 0;   // the batch is gone either way: a failed submit must not let the buffer overrun
   return rc;
 }
 
 // the reader side of processL7: one compact record per event; the switch itself runs on the device
 void Aggregator::ProcessL7(const L7Event& e) {
   if (!h_) return;
-  if (tables_dirty_) SubmitBatch();   // commit table changes before events that follow them
+  std::lock_guard<std::mutex> g(mu_);
+  if (tables_dirty_ || batch_n_ >= cfg_.BatchSize) SubmitBatch();   // table changes precede the events that follow them
+  if (batch_n_ >= cfg_.BatchSize) return;                            // cannot happen (SubmitBatch empties the batch)
   alz_l7_rec& r = batch_[batch_n_++];
   r.saddr = e.Saddr; r.daddr = e.Daddr; r.sport = e.Sport; r.dport = e.Dport;
   r.status = e.Status > 65535u ? 65535u : (uint16_t)e.Status;
@@ -134,7 +174,7 @@ void Aggregator::ProcessL7(const L7Event& e) {
                              (e.PayloadRejected ? ALZ_MF_PAYLOAD_REJECT : 0));
   r.duration_ns = e.Duration;
   r.write_time_ns = e.WriteTimeNs;
-  if (batch_n_ == cfg_.BatchSize) SubmitBatch();
+  if (batch_n_ >= cfg_.BatchSize) SubmitBatch();
 }
 
 void Aggregator::ProcessTcpConnect(const TcpConnectEvent& e) {
@@ -153,6 +193,7 @@ void Aggregator::ProcessTcpConnect(const TcpConnectEvent& e) {
 
 int Aggregator::Flush(bool with_scores) {
   if (!h_) return ALZ_E_STATE;
+  std::lock_guard<std::mutex> g(mu_);
   int rc = SubmitBatch();
   if (rc != ALZ_OK) return rc;
   size_t n = 0;
@@ -169,8 +210,8 @@ int Aggregator::Flush(bool with_scores) {
     const alz_edge_out& o = out_[i];
     EdgeWindow& w = edges[i];
     auto uid = [&](uint8_t t, uint32_t v) -> std::string {
-      if (t == ALZ_NODE_POD) return v < pod_uids_.size() ? pod_uids_[v] : std::string("?");
-      if (t == ALZ_NODE_SVC) return v < svc_uids_.size() ? svc_uids_[v] : std::string("?");
+      if (t == ALZ_NODE_POD) return v < pods_.names.size() ? pods_.names[v] : std::string("?");
+      if (t == ALZ_NODE_SVC) return v < svcs_.names.size() ? svcs_.names[v] : std::string("?");
       return FormatIPv4(v);   // outbound: the raw daddr string (data.go:862)
     };
     w.FromType = NodeTypeName(o.from_type); w.FromUID = uid(o.from_type, o.from);
@@ -179,6 +220,8 @@ int Aggregator::Flush(bool with_scores) {
     memcpy(w.Hist, o.hist, sizeof w.Hist);
     if (with_scores) w.Score = scores_[i];
   }
+  pods_.EndWindow();
+  svcs_.EndWindow();
   return ds_ ? ds_->PersistEdgeWindow(edges) : ALZ_OK;
 }
 

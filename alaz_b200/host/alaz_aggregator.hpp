@@ -10,6 +10,7 @@
 //   ds.PersistRequest(row) per event                       ds->PersistEdgeWindow(edges)   datastore/datastore.go:13
 #pragma once
 #include <cstdint>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -80,6 +81,13 @@ class Aggregator {
 
   bool Ok() const { return h_ != nullptr; }
   const std::string& LastError() const { return err_; }
+  // events dropped because a submit failed (capacity, CUDA error): the reference only logs such errors too
+  // (aggregator/data.go:1244-1247), but the count is kept
+  uint64_t DroppedEvents() const { return dropped_events_; }
+
+  // All Process* methods and Flush may be called from several threads (the reference runs 4*NumCPU processL7
+  // workers, aggregator/data.go:230-232); the batch buffer is guarded by one mutex, the library below is
+  // thread-safe on its own.
 
   void ProcessK8s(const K8sResourceMessage& m);
   void ProcessL7(const L7Event& e);
@@ -92,8 +100,18 @@ class Aggregator {
   static std::string FormatIPv4(uint32_t ip);
 
  private:
-  int SubmitBatch();
-  uint32_t Intern(std::unordered_map<std::string, uint32_t>& ids, std::vector<std::string>& names, const std::string& uid);
+  int SubmitBatch();   // requires mu_
+  struct Interner {     // UID <-> dense id (< 2^29), ids recycled one window after their last IP mapping went away
+    std::unordered_map<std::string, uint32_t> ids;
+    std::vector<std::string> names;
+    std::vector<uint32_t> refs;                       // IP entries currently mapping to the id
+    std::unordered_map<uint32_t, uint32_t> ip_to_id;  // mirror of the device table's value per IP
+    std::vector<uint32_t> free_ids, pending_free;
+    uint32_t Acquire(const std::string& uid);
+    void Map(uint32_t ip, uint32_t id);
+    void Unmap(uint32_t ip);
+    void EndWindow();
+  };
 
   DataStore* ds_;
   alz_handle* h_ = nullptr;
@@ -102,8 +120,9 @@ class Aggregator {
   alz_l7_rec* batch_ = nullptr;   // pinned (alz_pinned_alloc)
   size_t batch_n_ = 0;
   bool tables_dirty_ = false;
-  std::unordered_map<std::string, uint32_t> pod_ids_, svc_ids_;   // UID interner (ids < 2^29)
-  std::vector<std::string> pod_uids_, svc_uids_;
+  std::mutex mu_;
+  uint64_t dropped_events_ = 0;
+  Interner pods_, svcs_;
   std::vector<alz_edge_out> out_;
   std::vector<float> scores_;
 };

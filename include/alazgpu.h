@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ALZ_ABI_VERSION 1
+#define ALZ_ABI_VERSION 2
 
 /* ---- status codes -------------------------------------------------------- */
 typedef enum alz_status {
@@ -84,6 +84,20 @@ typedef struct alz_l7_rec {
   uint64_t duration_ns;  /* l7_event.duration (l7.c:788) */
   uint64_t write_time_ns;
 } alz_l7_rec;
+
+/* Packed L7 record, 16 B: the fields of alz_l7_rec that resolve/emit/reduce read, for callers whose
+ * events cross PCIe (half the bytes per event on the wire). Lossless: a duration >= 2^32 ns is stored
+ * in the overflow array handed to the same submit call, the record carries its index there and bit 7
+ * of `protocol` is set. No ports and no write time: windows of packed records are cut by the caller. */
+typedef struct alz_l7_rec16 {
+  uint32_t saddr;
+  uint32_t daddr;
+  uint16_t status;
+  uint8_t protocol;      /* ALZ_PROTO_* | ALZ_REC16_DUR_OVERFLOW */
+  uint8_t method_flags;  /* method | ALZ_MF_* */
+  uint32_t duration_ns;  /* or index into the overflow array */
+} alz_l7_rec16;
+#define ALZ_REC16_DUR_OVERFLOW 0x80u
 
 /* tcp_state record, 40 B, from struct tcp_event (ebpf/c/struct.h:2-12).
  * type: 1=ESTABLISHED 5=CLOSED (ebpf/tcp_state/tcp.go:19-25); addresses as in
@@ -163,7 +177,9 @@ typedef struct alz_stats {
   uint64_t edges_live;
   uint64_t tcp_events_in;
   uint64_t tcp_localhost_dropped; /* aggregator/data.go:409, 455 */
-  uint64_t _reserved[8];
+  uint64_t capacity_events;  /* events lost to an exhausted pair/edge table (cumulative) */
+  uint64_t windows;          /* windows flushed */
+  uint64_t _reserved[6];
 } alz_stats;
 
 typedef struct alz_handle alz_handle;
@@ -190,10 +206,22 @@ int alz_table_commit(alz_handle* h);
 
 /* ---- event ingest: replaces processL7 .. PersistRequest --------------------
  * (aggregator/data.go:1364-1383 dispatch, :1081-1362 row build,
- *  :827-870 setFromToV2). */
+ *  :827-870 setFromToV2). The alz_submit_* calls may be made from many OS threads at once, like the
+ * reference's 4*NumCPU processL7 workers (aggregator/data.go:230-232): callers copy into separate
+ * pinned staging slots in parallel and only the enqueue is serialised. A flush or table commit is
+ * ordered after every submit that returned before it was called. */
 int alz_submit_l7(alz_handle* h, const alz_l7_rec* host_recs, size_t n);
 /* same, records already resident in this GPU's HBM */
 int alz_submit_l7_device(alz_handle* h, const alz_l7_rec* dev_recs, size_t n);
+/* same, 16-B packed records (host memory); dur_overflow[n_overflow] holds the durations the records
+ * index (may be NULL when n_overflow == 0) */
+int alz_submit_l7_packed(alz_handle* h, const alz_l7_rec16* host_recs, size_t n,
+                         const uint64_t* dur_overflow, size_t n_overflow);
+int alz_submit_l7_packed_device(alz_handle* h, const alz_l7_rec16* dev_recs, size_t n,
+                                const uint64_t* dev_dur_overflow);
+/* host-side packer: alz_l7_rec[n] -> alz_l7_rec16[n]; overflow durations appended to dur_overflow
+ * (capacity cap_overflow). Returns the number of overflow entries written, or -1 if cap is too small. */
+long alz_pack_l7(const alz_l7_rec* recs, size_t n, alz_l7_rec16* out, uint64_t* dur_overflow, size_t cap_overflow);
 /* n raw perf samples exactly as perf.Reader yields them: 1096-B
  * struct l7_event (ebpf/l7_req/l7.go:345-369, :704); payload ignored. */
 int alz_submit_l7_raw(alz_handle* h, const void* host_bpf_l7_events, size_t n);
@@ -208,6 +236,10 @@ int alz_window_flush(alz_handle* h, alz_edge_out* out, size_t cap, size_t* n_out
 /* as above but leaves the result on the device for alz_gnn_score / peers;
  * *dev_edges stays valid until the next flush on this handle */
 int alz_window_flush_device(alz_handle* h, const alz_edge_out** dev_edges, size_t* n_out);
+/* the rows of the last flushed window once more. On a multi-rank handle the merge consumes the window on
+ * every rank, so a flush whose `cap` was too small cannot keep it: it returns ALZ_E_CAPACITY with *n_out set
+ * and the merged rows stay fetchable here until the next flush. */
+int alz_window_fetch(alz_handle* h, alz_edge_out* out, size_t cap, size_t* n_out);
 int alz_get_stats(alz_handle* h, alz_stats* out);
 
 /* ---- GNN anomaly pass over the last flushed window (docs/SPEC.md §6) -------- */

@@ -14,6 +14,9 @@ extern "C" {
 /* pinned host buffers: alz_submit_l7 / alz_submit_l7_raw from such a buffer skip
  * the staging memcpy (the Go side can fill them directly: C memory, cgo-legal) */
 int alz_pinned_alloc(size_t bytes, void** out);
+/* same, on the NUMA node next to the handle's GPU (8 ranks feeding 8 GPUs: staging on the remote socket
+ * halves the reachable H2D rate) */
+int alz_pinned_alloc_local(alz_handle* h, size_t bytes, void** out);
 int alz_pinned_free(void* p);
 
 int alz_dev_alloc(alz_handle* h, size_t bytes, void** out);

@@ -91,6 +91,7 @@ def pyref_edges(agg):
     for i, ((ft, fu, tt, tu), g) in enumerate(agg.groups.items()):
         a, b = node(ft, fu), node(tt, tu)
         out[i]["from_type"], out[i]["from"], out[i]["to_type"], out[i]["to"] = a[0], a[1], b[0], b[1]
-        out[i]["count"], out[i]["err5xx"], out[i]["lat_sum_ns"] = g["count"], g["err5xx"], g["lat_sum"]
+        out[i]["count"], out[i]["err5xx"] = g["count"], g["err5xx"]
+        out[i]["lat_sum_ns"] = g["lat_sum"] & 0xFFFFFFFFFFFFFFFF   # the accumulators are u64: sums are defined modulo 2^64 (docs/SPEC.md)
         out[i]["hist"] = g["hist"]
     return sort_edges(out)

@@ -200,23 +200,33 @@ def test_edge_cases_empty_single_ragged_and_sentinel_pair():
     h.close()
 
 
-def test_capacity_is_reported_not_silent():
+def test_capacity_is_reported_not_silent_and_covers_one_window():
+    """A full pair/edge table is reported by the flush of THAT window; the handle keeps working and the
+    next, healthy window returns ALZ_OK with exact edges (r1 returned ALZ_E_CAPACITY for ever after)."""
     t = ol.Topo(500, seed=8)
     ev = t.events(0, 300_000)
-    h = capi.Handle(max_endpoints=4096, max_pairs=64, max_edges=64)   # far too small
-    h.load_tables(t.pod_ip, t.svc_ip)
-    h.submit(ev)
-    with pytest.raises(capi.AlzError) as e:
-        h.flush()
-    assert e.value.status == abi.E_CAPACITY
-    h.close()
+    for max_pairs, max_edges in ((64, 64), (1 << 15, 64)):   # pair table too small; only the edge table too small
+        h = capi.Handle(max_endpoints=4096, max_pairs=max_pairs, max_edges=max_edges)
+        h.load_tables(t.pod_ip, t.svc_ip)
+        h.submit(ev)
+        with pytest.raises(capi.AlzError) as e:
+            h.flush()
+        assert e.value.status == abi.E_CAPACITY
+        assert h.stats()["capacity_events"] > 0
+        small = ev[ev["saddr"] == ev["saddr"][0]][:2000]      # a handful of pairs: fits
+        o = ol.Oracle(); o.load_tables(t.pod_ip, t.svc_ip); o.process(small)
+        h.submit(small)
+        got = h.flush()                                       # ALZ_OK again
+        assert edges_equal(got, o.edges()), explain_diff(got, o.edges())
+        h.close()
 
 
-def test_full_size_properties_config2():
-    """BASELINE configs[1]: 10k services / 100M events on one GPU. The oracle would take
-    minutes here, so check what must hold at any size: conservation of rows, count ==
-    sum(hist), total latency == sum of the emitted rows' durations (numpy over the stream),
-    and window linearity (A then B in one window == whole)."""
+def test_full_size_config2_bit_exact_and_properties():
+    """BASELINE configs[1]: 10k services / 100M events on one GPU, at full size.
+    (1) per-edge bit-exact against the oracle run with every host core on the very same 100M records;
+    (2) size-independent properties: conservation of rows, count == sum(hist), total latency == an
+    independent numpy pass over the stream; (3) window linearity (A then B in one window == whole)."""
+    import os
     S, N, CH = 10_000, 100_000_000, 10_000_000
     t = capi.Topo(S, seed=0xA1A20000 + 1)
     h = capi.Handle(max_endpoints=4 * S, max_pairs=1 << 20)
@@ -224,19 +234,18 @@ def test_full_size_properties_config2():
     d = h.dev_alloc(N * 32)
     t.fill_device(h, 0, N, d)
     h.submit_device(d, N)
-    st_before = None
     edges = h.flush()
     st = h.stats()
     assert st["events_in"] == N
     assert int(edges["count"].sum()) == st["rows_emitted"] == N - st["not_request"] - st["src_unresolved"]
     assert np.array_equal(edges["hist"].sum(axis=1), edges["count"])
-    # independent numpy pass over the stream, chunked D2H
+    # the same records on the host (the device generator is bit-identical to the host one, tested above)
+    ev_all = np.empty(N, dtype=abi.L7_REC)
     pods = np.sort(t.pod_ip)
-    lat = 0
-    rows = 0
-    err = 0
+    lat = rows = err = 0
     for c in range(0, N, CH):
         ev = h.d2h(d + c * 32, CH, abi.L7_REC)
+        ev_all[c:c + CH] = ev
         emit = np.isin(ev["protocol"], [abi.PROTO_HTTP, abi.PROTO_AMQP, abi.PROTO_REDIS])
         idx = np.searchsorted(pods, ev["saddr"])
         idx[idx == len(pods)] = 0
@@ -246,9 +255,20 @@ def test_full_size_properties_config2():
         lat += int(ev["duration_ns"][m].sum(dtype=np.uint64))
         err += int((m & (ev["protocol"] == abi.PROTO_HTTP) & (ev["status"] >= 500) & (ev["status"] < 600)).sum())
     assert rows == st["rows_emitted"]
-    assert lat == int(edges["lat_sum_ns"].sum(dtype=np.uint64))
+    assert lat % (1 << 64) == int(edges["lat_sum_ns"].sum(dtype=np.uint64))
     assert err == int(edges["err5xx"].sum())
-    # linearity: two halves submitted separately into one window give the same edges
+    # (1) the oracle on all 100M records
+    o = ol.Oracle()
+    o.load_tables(t.pod_ip, t.svc_ip)
+    o.process(ev_all, max(1, os.cpu_count() or 1))
+    exp = o.edges()
+    assert edges_equal(edges, exp), explain_diff(edges, exp)
+    ost = o.stats()
+    for k in ("events_in", "rows_emitted", "not_request", "src_unresolved"):
+        assert st[k] == ost[k], (k, st[k], ost[k])
+    o.close()
+    del ev_all
+    # (3) linearity: two halves submitted separately into one window give the same edges
     h.submit_device(d, N // 2)
     h.submit_device(d + (N // 2) * 32, N - N // 2)
     again = h.flush()
