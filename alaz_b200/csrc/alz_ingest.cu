@@ -4,8 +4,8 @@
 // Data movement: every warp owns a two-stage ring in shared memory and streams its
 // chunks of the record array into it with TMA bulk copies (cp.async.bulk + mbarrier
 // complete_tx, issued by lane 0, L2 evict-first). Lanes copy their records from the
-// ring into registers, the stage is handed back to the TMA at once, and the next two
-// chunks are in flight while the warp works: no per-lane address arithmetic, no
+// ring into registers, the stage is handed back to the TMA as soon as those loads have
+// returned, and the next two chunks are in flight while the warp works: no per-lane address arithmetic, no
 // scoreboard stall on the first use of a streamed record, no cross-warp barrier
 // anywhere in the main loop.
 //
@@ -23,8 +23,8 @@
 //         loop therefore carries no global-memory code and stays converged; r1's
 //         kernel issued the cold path's instructions for every warp iteration
 //         (profiles/r1_final_ingest_ncu.txt: 247 instructions per event).
-//         The probes of a batch are consumed one batch later, so their L2 round trip
-//         is off the warp's critical path.
+//         The probes are cp.async copies into shared memory and are consumed when the
+//         next batch is requested, so their L2/DRAM round trip is off the critical path.
 //   slow  a cold event whose home slot does not hold its pair (new pair, collision,
 //         unresolvable source: ~7 % of the cold events) is queued once more and 32 of
 //         them at a time walk find_or_insert_pair; inline, nearly every cold batch would
@@ -58,7 +58,8 @@ struct Layout {
   static constexpr uint32_t kTabOff = kBars + (uint32_t)kWarps * 16u;
   static constexpr uint32_t kColdOff = kTabOff + kTab * 4u;
   static constexpr uint32_t kSlowOff = kColdOff + (uint32_t)kWarps * kColdQ * kQBytes;
-  static constexpr uint32_t kMisc = kSlowOff + (uint32_t)kWarps * kSlowQ * kQBytes;   // row allocator
+  static constexpr uint32_t kProbeOff = kSlowOff + (uint32_t)kWarps * kSlowQ * kQBytes;   // per warp: 32 x 16-B DictEnt
+  static constexpr uint32_t kMisc = kProbeOff + (uint32_t)kWarps * 512u;                  // row allocator
   static constexpr uint32_t kRowKeys = kMisc + 16u;
   static constexpr uint32_t kFixed = kRowKeys + 8u;                     // + (kRows + 1) * 8 + kRows * kRowWords * 4
   static constexpr uint32_t kRows = ((kSmemMax - kFixed) / (kRowWords * 4u + 8u)) / 32u * 32u;
@@ -97,6 +98,24 @@ __device__ __forceinline__ void red_add_u32(uint32_t* p, uint32_t v) {
 }
 __device__ __forceinline__ void red_add_u64(uint64_t* p, uint64_t v) {
   asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// 16-byte global -> shared copy that no register waits on (LDGSTS); L2 only (the dictionary is written by other CTAs)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// shared-memory reductions under a predicate, written as PTX so that the hot tier is one straight line of code
+// (with C++ ifs nvcc branches around each atomic and the two events of a lane cannot overlap)
+__device__ __forceinline__ void red_shared_add_if(bool p, uint32_t addr, uint32_t v) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q red.shared.add.u32 [%0], %1;\n\t}"
+               ::"r"(addr), "r"(v), "r"((uint32_t)p) : "memory");
+}
+__device__ __forceinline__ uint32_t atom_shared_add_if(bool p, uint32_t addr, uint32_t v) {
+  uint32_t old = 0;
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q atom.shared.add.u32 %0, [%1], %2;\n\t}"
+               : "+r"(old) : "r"(addr), "r"(v), "r"((uint32_t)p) : "memory");
+  return old;
 }
 __device__ __forceinline__ bool elect_one() {   // one lane of the (converged) warp
   uint32_t pred;
@@ -188,13 +207,6 @@ struct Queue {
   __device__ __forceinline__ void pop(uint32_t n) { head = (head + n) & (kCap - 1u); count -= n; }
 };
 
-// a batch of cold events whose dictionary home slots have been requested
-struct Probe {
-  uint4 ent;          // the 16-byte DictEnt as loaded
-  uint64_t key, dur;
-  uint32_t meta;      // bit 31: this lane holds an event
-};
-
 // slow tier, 32 queued events at a time: the pair is new to the dictionary, or its home slot is taken by another
 // pair, or its source is no pod (dropped like the reference does, aggregator/data.go:829-832)
 template <uint32_t kRows>
@@ -223,41 +235,47 @@ __device__ __forceinline__ void slow_batch(Queue<kSlowQ>& q, uint32_t count, con
   q.pop(count);
 }
 
-// cold tier, step 1: take `count` events off the cold queue and request their home slots
+// cold tier, step 1: request the dictionary home slots of the first `count` queued events. The 16-byte entries
+// are copied straight into the warp's probe buffer in shared memory (cp.async): nothing waits on them until the
+// batch is consumed, which happens when the NEXT batch is ready to be requested — one to two iterations later,
+// so the L2/DRAM round trip of the probes is off the warp's critical path. (Holding the probes in registers did
+// not work: handing them from one loop trip to the next needs a move, and the move waits for the load.)
 template <uint32_t kColdQ>
-__device__ __forceinline__ Probe cold_issue(Queue<kColdQ>& q, uint32_t count, const AccTable& t) {
+__device__ __forceinline__ void cold_issue(const Queue<kColdQ>& q, uint32_t count, const AccTable& t, uint32_t probe_a) {
   const uint32_t lane = threadIdx.x & 31u;
-  Probe p;
-  p.ent = make_uint4(0u, 0u, kNoRow, 0u);
-  p.key = 0; p.dur = 0; p.meta = 0;
   if (lane < count) {
-    q.get(lane, &p.key, &p.dur, &p.meta);
-    p.meta |= 0x80000000u;
-    const bool rv = (p.meta & 0x100u) != 0u;
+    uint64_t key, dur;
+    uint32_t meta;
+    q.get(lane, &key, &dur, &meta);
+    const bool rv = (meta & 0x100u) != 0u;
     const DictEnt* dict = rv ? t.dict_rev : t.dict;
     const uint32_t mask = rv ? t.dict_rev_mask : t.dict_mask;
-    p.ent = __ldcg(reinterpret_cast<const uint4*>(&dict[pair_hash(p.key) & mask]));
+    cp_async16(probe_a + lane * 16u, &dict[pair_hash(key) & mask]);
   }
+  cp_async_commit();
+}
+// cold tier, step 2: the probes have landed. A home-slot hit is reduced into its row at once, anything else joins
+// the slow queue.
+template <uint32_t kRows, uint32_t kColdQ>
+__device__ __forceinline__ void cold_consume(Queue<kColdQ>& q, uint32_t count, const uint4* probe, Queue<kSlowQ>& slow,
+                                             const AccTable& t, const Shared& s, const EpEntry* __restrict__ ep,
+                                             uint32_t ep_mask, uint32_t lane_lt, uint32_t* lost, uint32_t* unresolved) {
+  const uint32_t lane = threadIdx.x & 31u;
+  cp_async_wait_all();
+  const bool valid = lane < count;
+  uint64_t key = 0, dur = 0;
+  uint32_t meta = 0;
+  uint4 ent = make_uint4(0u, 0u, kNoRow, 0u);
+  if (valid) { q.get(lane, &key, &dur, &meta); ent = probe[lane]; }
+  const bool home = valid && ent.x == (uint32_t)key && ent.y == (uint32_t)(key >> 32) && ent.z < kDropRow && key != kEmptyKey;
+  if (home) {
+    red_add_u32(&t.hist[(size_t)ent.z * ALZ_NB + (meta & 0x3Fu)], 1u);
+    red_add_u64(&t.lat_sum[ent.z], dur);
+    if (meta & 0x200u) red_add_u64(&t.err5xx[ent.z], 1ull);
+  }
+  slow.push(valid && !home, key, dur, meta, lane_lt);
   __syncwarp();
   q.pop(count);
-  return p;
-}
-// cold tier, step 2 (one batch later, so the L2 round trip of the probes is off the critical path): a home-slot
-// hit is reduced into its row at once, anything else joins the slow queue
-template <uint32_t kRows>
-__device__ __forceinline__ void cold_consume(const Probe& p, Queue<kSlowQ>& slow, const AccTable& t, const Shared& s,
-                                             const EpEntry* __restrict__ ep, uint32_t ep_mask, uint32_t lane_lt,
-                                             uint32_t* lost, uint32_t* unresolved) {
-  const bool valid = (p.meta & 0x80000000u) != 0u;
-  const bool home = valid && p.ent.x == (uint32_t)p.key && p.ent.y == (uint32_t)(p.key >> 32) && p.ent.z < kDropRow &&
-                    p.key != kEmptyKey;
-  if (home) {
-    red_add_u32(&t.hist[(size_t)p.ent.z * ALZ_NB + (p.meta & 0x3Fu)], 1u);
-    red_add_u64(&t.lat_sum[p.ent.z], p.dur);
-    if (p.meta & 0x200u) red_add_u64(&t.err5xx[p.ent.z], 1ull);
-  }
-  slow.push(valid && !home, p.key, p.dur, p.meta & 0x3FFu, lane_lt);
-  __syncwarp();
   if (slow.count >= 32u) slow_batch<kRows>(slow, 32u, t, s, ep, ep_mask, lost, unresolved);
 }
 
@@ -315,6 +333,9 @@ ingest_pairs_v6_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
   Queue<kSlowQ> slow;
   cold.bind(smem_raw + L::kColdOff + (size_t)warp * kColdQ * kQBytes);
   slow.bind(smem_raw + L::kSlowOff + (size_t)warp * kSlowQ * kQBytes);
+  const uint4* probe = reinterpret_cast<const uint4*>(smem_raw + L::kProbeOff + (size_t)warp * 512u);
+  const uint32_t probe_a = smem_u32(probe);
+  const uint32_t rows_a = smem_u32(s.rows);
   const uint8_t* ring = smem_raw + (size_t)warp * 2u * L::kChunkBytes;
   const uint32_t ring_a = smem_u32(ring);
   const uint32_t bar_a = smem_u32(smem_raw + L::kBars + warp * 16u);
@@ -331,9 +352,11 @@ ingest_pairs_v6_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
   uint32_t c_next = c_first;
   const uint32_t* src_next = recs + (uint64_t)c_first * (L::kChunk * kRecWords);
   const uint64_t src_step = (uint64_t)c_stride * (L::kChunk * kRecWords);        // in words
-  auto issue = [&](uint32_t stage) {   // one lane; requests chunk c_next if there is one
+  // `dep` is always 0 but computed from the words just loaded out of the stage (see the main loop): the copy cannot
+  // be issued before those loads have returned
+  auto issue = [&](uint32_t stage, uint32_t dep) {   // one lane; requests chunk c_next if there is one
     if (c_next < n_chunks) {
-      const uint32_t bytes = (c_next == n_chunks - 1u ? tail : L::kChunk) * (uint32_t)kRecWords * 4u;
+      const uint32_t bytes = (c_next == n_chunks - 1u ? tail : L::kChunk) * (uint32_t)kRecWords * 4u + dep;
       mbar_expect_tx(bar_a + stage * 8u, bytes);
       tma_load(ring_a + stage * L::kChunkBytes, src_next, bytes, bar_a + stage * 8u, policy);
     }
@@ -344,9 +367,9 @@ ingest_pairs_v6_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
     mbar_init(bar_a + 8u, 1u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    issue(0u);
+    issue(0u, 0u);
     c_next += c_stride; src_next += src_step;
-    issue(1u);
+    issue(1u, 0u);
   }
   c_next += 2u * c_stride - (lane == 0 ? c_stride : 0u);   // every lane tracks the producer state, so any lane can be elected
   src_next += 2u * src_step - (lane == 0 ? src_step : 0u);
@@ -373,10 +396,9 @@ ingest_pairs_v6_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
   }
   __syncthreads();
 
+  const uint32_t zero = (uint32_t)(n >> 63);   // n < 2^37
   uint32_t lost = 0, unresolved = 0;
-  Probe pend;                          // probes issued, not yet consumed (lanes without an event: meta = 0)
-  pend.ent = make_uint4(0u, 0u, kNoRow, 0u);
-  pend.key = 0; pend.dur = 0; pend.meta = 0;
+  uint32_t probing = 0;                // events at the head of the cold queue whose probes are in flight
   uint32_t it = 0, n_hit = 0, n_live = 0, n_cold = 0;
   for (uint32_t c = c_first; c < n_chunks; c += c_stride, ++it) {
     const uint32_t stage = it & 1u;
@@ -384,23 +406,32 @@ ingest_pairs_v6_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
     // records of this chunk into registers (lane l takes records l, l + 32, ...)
     uint32_t w[kU][kRecWords];
     const uint8_t* st = ring + stage * L::kChunkBytes;
+    uint32_t seen = 0;
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const uint4* p = reinterpret_cast<const uint4*>(st + ((size_t)u * 32u + lane) * (kRecWords * 4u));
       const uint4 a = p[0];
       w[u][0] = a.x; w[u][1] = a.y; w[u][2] = a.z; w[u][3] = a.w;
+      seen ^= a.x;
       if (kRecWords == 8) {
         const uint2 b = *reinterpret_cast<const uint2*>(p + 1);   // duration; write_time is not read here
         w[u][4] = b.x; w[u][5] = b.y;
+        seen ^= b.x;
       }
     }
-    __syncwarp();   // every lane has its records: the stage goes back to the TMA
-    if (elect_one()) issue(stage);
+    // The stage goes back to the TMA only when the loads above have RETURNED: the byte count of the copy is made
+    // to depend on the loaded words (`zero` is a run-time 0 the compiler cannot see through), so the copy's issue
+    // waits on their scoreboard. A __syncwarp() alone orders the instructions, not the completion of the
+    // shared-memory loads, and under load the TMA write of the next chunk overtook the duration loads of this one
+    // (right keys with the wrong latencies).
+    __syncwarp();
+    if (elect_one()) issue(stage, seen & zero);
     c_next += c_stride; src_next += src_step;
     const uint32_t n_here = (c == n_chunks - 1u) ? tail : L::kChunk;
     n_live += n_here;
 
-    // hot tier for all kU events of the lane (independent chains), then one pass over the cold queue
+    // hot tier for all kU events of the lane: straight-line code (independent chains), then one pass over the
+    // cold queue
     uint64_t key[kU], dur[kU];
     uint32_t meta[kU];
     bool coldf[kU];
@@ -428,33 +459,37 @@ ingest_pairs_v6_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
       const uint32_t x = s.tab[h >> kTabShift] ^ tab_fp(h);
       const uint32_t r = min(x, kRows);
       const bool hit = act && !rv && x < kRows && s.rowkey[r] == key[u];
-      if (hit) {
-        ++n_hit;
-        uint32_t* row = s.rows + r * kRowWords;
-        atomicAdd(&row[bucket], 1u);
-        uint32_t* lat = row + ALZ_NB + 2u * (lane & (kLatSub - 1u));
-        const uint32_t lo = (uint32_t)dur[u], dhi = (uint32_t)(dur[u] >> 32);
-        const uint32_t old = atomicAdd(&lat[0], lo);
-        if (old > ~lo || dhi != 0u) atomicAdd(&lat[1], dhi + (old > ~lo ? 1u : 0u));   // carry out of the low word
-        if (err) atomicAdd(&row[ALZ_NB + 2 * kLatSub], 1u);
-      }
+      // the row's reductions, each under the hit predicate
+      const uint32_t row_a = rows_a + r * (kRowWords * 4u);
+      const uint32_t lat_a = row_a + (ALZ_NB + 2u * (lane & (kLatSub - 1u))) * 4u;
+      const uint32_t lo = (uint32_t)dur[u], dhi = (uint32_t)(dur[u] >> 32);
+      red_shared_add_if(hit, row_a + bucket * 4u, 1u);
+      const uint32_t old = atom_shared_add_if(hit, lat_a, lo);
+      const bool carry = old > ~lo;                                  // out of the low word
+      red_shared_add_if(hit && (carry || dhi != 0u), lat_a + 4u, dhi + (carry ? 1u : 0u));
+      red_shared_add_if(hit && err, row_a + (ALZ_NB + 2 * kLatSub) * 4u, 1u);
+      n_hit += hit ? 1u : 0u;
       coldf[u] = act && !hit;
     }
 #pragma unroll
     for (int u = 0; u < kU; ++u) n_cold += cold.push(coldf[u], key[u], dur[u], meta[u], lane_lt);
     __syncwarp();
-    while (cold.count >= 32u) {
-      const Probe now = cold_issue(cold, 32u, pairs);
-      cold_consume<kRows>(pend, slow, pairs, s, ep, ep_mask, lane_lt, &lost, &unresolved);
-      pend = now;
+    // a batch is consumed when the next one is ready to be requested
+    while (cold.count - probing >= 32u) {
+      if (probing) {
+        cold_consume<kRows>(cold, probing, probe, slow, pairs, s, ep, ep_mask, lane_lt, &lost, &unresolved);
+        probing = 0;
+      }
+      cold_issue(cold, 32u, pairs, probe_a);
+      probing = 32u;
     }
   }
+  if (probing) cold_consume<kRows>(cold, probing, probe, slow, pairs, s, ep, ep_mask, lane_lt, &lost, &unresolved);
   if (cold.count) {
-    const Probe now = cold_issue(cold, cold.count, pairs);
-    cold_consume<kRows>(pend, slow, pairs, s, ep, ep_mask, lane_lt, &lost, &unresolved);
-    pend = now;
+    const uint32_t rest = cold.count;
+    cold_issue(cold, rest, pairs, probe_a);
+    cold_consume<kRows>(cold, rest, probe, slow, pairs, s, ep, ep_mask, lane_lt, &lost, &unresolved);
   }
-  cold_consume<kRows>(pend, slow, pairs, s, ep, ep_mask, lane_lt, &lost, &unresolved);
   while (slow.count) slow_batch<kRows>(slow, min(slow.count, 32u), pairs, s, ep, ep_mask, &lost, &unresolved);
   __syncthreads();
   smem_drain<kRows>(s, pairs, ep, ep_mask, &lost, &unresolved);

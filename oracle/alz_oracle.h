@@ -77,6 +77,16 @@ void orc_sockmaps_process_tcp(orc_sockmaps* m, const alz_tcp_rec* recs, size_t n
 void orc_sockmaps_lookup(orc_sockmaps* m, const alz_sock_query* q, size_t n,
                          alz_sock_result* out);
 
+/* ---- "fair" CPU arm (alz_fastcpu.c): same results, integer keys, flat tables, pinned threads ---- */
+typedef struct orc_fast orc_fast;
+orc_fast* orc_fast_create(uint32_t max_endpoints);
+void orc_fast_destroy(orc_fast* f);
+void orc_fast_table_upsert(orc_fast* f, int table, uint32_t ipv4, uint32_t id);
+void orc_fast_process(orc_fast* f, const alz_l7_rec* recs, size_t n, int nthreads);
+size_t orc_fast_edges(orc_fast* f, alz_edge_out* out, size_t cap);
+void orc_fast_reset(orc_fast* f);
+void orc_fast_stats(orc_fast* f, alz_stats* st);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
 
 
 def build(force=False):
-    src = [os.path.join(ROOT, "oracle", "alz_oracle.c"),
+    src = [os.path.join(ROOT, "oracle", "alz_oracle.c"), os.path.join(ROOT, "oracle", "alz_fastcpu.c"),
            os.path.join(ROOT, "oracle", "alz_oracle.h"),
            os.path.join(ROOT, "alaz_b200", "synth", "alz_synth_topo.c"),
            os.path.join(ROOT, "alaz_b200", "synth", "alz_synth.h"),
@@ -64,6 +64,15 @@ def lib():
         L.orc_sockmaps_destroy.argtypes = [vp]
         L.orc_sockmaps_process_tcp.argtypes = [vp, vp, sz, C.POINTER(u64)]
         L.orc_sockmaps_lookup.argtypes = [vp, vp, sz, vp]
+        L.orc_fast_create.argtypes = [u32]
+        L.orc_fast_create.restype = vp
+        L.orc_fast_destroy.argtypes = [vp]
+        L.orc_fast_table_upsert.argtypes = [vp, C.c_int, u32, u32]
+        L.orc_fast_process.argtypes = [vp, vp, sz, C.c_int]
+        L.orc_fast_edges.argtypes = [vp, vp, sz]
+        L.orc_fast_edges.restype = sz
+        L.orc_fast_reset.argtypes = [vp]
+        L.orc_fast_stats.argtypes = [vp, C.POINTER(abi.Stats)]
         L.alz_synth_topo_create.argtypes = [u32, u64, u32]
         L.alz_synth_topo_create.restype = C.POINTER(abi.SynthTopo)
         L.alz_synth_topo_destroy.argtypes = [C.POINTER(abi.SynthTopo)]
@@ -120,6 +129,50 @@ class Oracle:
     def stats(self):
         st = abi.Stats()
         self.L.orc_stats(self.h, C.byref(st))
+        return st.as_dict()
+
+
+class FastCpu:
+    """The "fair" CPU arm (oracle/alz_fastcpu.c): integer keys, flat tables, per-thread accumulators."""
+
+    def __init__(self, max_endpoints=1 << 16):
+        self.L = lib()
+        self.h = self.L.orc_fast_create(int(max_endpoints))
+
+    def close(self):
+        if self.h:
+            self.L.orc_fast_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def load_tables(self, pod_ip, svc_ip):
+        for k, v in enumerate(pod_ip):
+            self.L.orc_fast_table_upsert(self.h, abi.TABLE_POD, int(v), k)
+        for k, v in enumerate(svc_ip):
+            self.L.orc_fast_table_upsert(self.h, abi.TABLE_SVC, int(v), k)
+
+    def upsert(self, table, ip, id_):
+        self.L.orc_fast_table_upsert(self.h, table, int(ip), int(id_))
+
+    def process(self, recs, nthreads=1):
+        recs = np.ascontiguousarray(recs, dtype=abi.L7_REC)
+        self.L.orc_fast_process(self.h, _ptr(recs), len(recs), nthreads)
+
+    def edges(self):
+        n = self.L.orc_fast_edges(self.h, None, 0)
+        out = np.zeros(n, dtype=abi.EDGE_OUT)
+        if n:
+            self.L.orc_fast_edges(self.h, _ptr(out), n)
+        return out
+
+    def reset_window(self):
+        self.L.orc_fast_reset(self.h)
+
+    def stats(self):
+        st = abi.Stats()
+        self.L.orc_fast_stats(self.h, C.byref(st))
         return st.as_dict()
 
 

@@ -88,6 +88,22 @@ def test_multithreaded_oracle_is_identical():
     assert a.stats() == b.stats()
 
 
+@pytest.mark.parametrize("mix", [abi.MIX_SURVEY, abi.MIX_ALL])
+def test_fair_cpu_arm_is_bit_exact_to_the_faithful_port(mix):
+    # oracle/alz_fastcpu.c (bench's second cpu_baseline) against oracle/alz_oracle.c, single- and multi-threaded
+    t = ol.Topo(300, seed=99 + mix, mix=mix)
+    ev = t.events(0, 300_000)
+    o = ol.Oracle(); o.load_tables(t.pod_ip, t.svc_ip); o.process(ev, 3)
+    for nt in (1, 5):
+        f = ol.FastCpu(4 * 300); f.load_tables(t.pod_ip, t.svc_ip); f.process(ev, nt)
+        got, exp = f.edges(), o.edges()
+        assert edges_equal(got, exp), explain_diff(got, exp)
+        fs, os_ = f.stats(), o.stats()
+        for k in ("events_in", "rows_emitted", "not_request", "src_unresolved"):
+            assert fs[k] == os_[k]
+        f.close()
+
+
 def test_table_erase_and_update_follow_persist_go():
     # persist.go:55-71: UPDATE overwrites, DELETE removes
     o = ol.Oracle()
@@ -179,22 +195,32 @@ class _Line:
         return self.L.orc_sockline_len(self.h)
 
 
+def _sockline_kat():
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sockline_kat.json")) as f:
+        return json.load(f)
+
+
 def test_kat_TestSocketLine():
-    # aggregator/sock_line_test.go:11-349: 309 opens with identical (empty)
-    # SockInfo collapse to the first; GetValue(33835107729129) must succeed.
-    ts_list = [33805065332163, 33805065990716, 33805066400606, 33805066937463,
-               33805067507004, 33805068082621, 33805068543449, 33805069106660,
-               33805069572630, 33805070210774, 33805070772370, 33805071162619,
-               33805071625600, 33805073482028, 33805073841739, 33805074342888,
-               33805074573808, 33805075080976, 33805075542978, 33805076175534,
-               33807002886899, 33807004747817, 33815077484050, 33945231235604,
-               33945232859491, 33945234961387, 33945235683085, 33945236269094,
-               33945236611501, 33947002331172, 33947004517045]
+    # aggregator/sock_line_test.go:11-349, replayed in full: every timestamp of the reference's tsList
+    # (tests/golden/sockline_kat.json, extracted by tests/golden/make_sockline_fixture.py) is added as an
+    # open with the same (empty) SockInfo; AddValue's dedupe collapses them to the first
+    # (sock_num_line.go:70-78); GetValue(33835107729129) must succeed (sock_line_test.go:342-347).
+    kat = _sockline_kat()
+    assert len(kat["ts_list"]) >= 300 and kat["query"] == 33835107729129
     ln = _Line()
-    for ts in ts_list:
+    for ts in kat["ts_list"]:
         ln.add(ts, _SI())
-    assert len(ln) == 1           # dedupe at sock_num_line.go:72-77
-    assert ln.get(33835107729129) is not None   # sock_line_test.go:342-347
+    assert len(ln) == 1
+    assert ln.get(kat["query"]) is not None
+    # the same inserts with DISTINCT sockets keep every entry, sorted, and the query lands on the last open
+    # socket at or before it (sock_num_line.go:90-92, :121)
+    ln2 = _Line()
+    for i, ts in enumerate(kat["ts_list"]):
+        ln2.add(ts, _SI(saddr=i + 1))
+    assert len(ln2) == len(set(kat["ts_list"]))
+    before = max(i for i, ts in enumerate(kat["ts_list"]) if ts < kat["query"])
+    assert ln2.get(kat["query"]).saddr == before + 1
 
 
 def test_kat_TestXxx_open_close_pairs():
