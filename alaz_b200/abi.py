@@ -80,7 +80,9 @@ class Stats(C.Structure):
         ("pairs_live", C.c_uint64), ("edges_live", C.c_uint64),
         ("tcp_events_in", C.c_uint64), ("tcp_localhost_dropped", C.c_uint64),
         ("capacity_events", C.c_uint64), ("windows", C.c_uint64),
-        ("_reserved", C.c_uint64 * 6),
+        ("kernel_launches", C.c_uint64), ("collective_bytes_last", C.c_uint64),
+        ("flush_local_us_last", C.c_uint64), ("merge_us_last", C.c_uint64),
+        ("_reserved", C.c_uint64 * 2),
     ]
 
     def as_dict(self):

@@ -30,20 +30,23 @@ def needs_build():
     return any(os.path.getmtime(p) > t for p in _deps())
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, prof=False):
+    """prof=True: libalazgpu_prof.so with per-section cycle counters in the ingest kernel (ALZ_LIB_PATH selects it)."""
+    out = LIB.replace("libalazgpu.so", "libalazgpu_prof.so") if prof else LIB
+    if not force and not prof and not needs_build():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
     srcs = [os.path.join(CSRC, s) for s in SOURCES] + EXTRA
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + srcs + ["-o", LIB, "-ldl"]
+    cmd = [nvcc] + NVCC_FLAGS + (["-DALZ_INGEST_PROF"] if prof else []) + (["-Xptxas", "-v"] if verbose else []) + \
+        srcs + ["-o", out, "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("nvcc failed building libalazgpu.so")
     if verbose:
         sys.stderr.write(r.stderr)
-    return LIB
+    return out
 
 
 SIM_TEST = os.path.join(LIB_DIR, "alaz_sim_test")
@@ -85,4 +88,4 @@ def build_host_unit_test():
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, prof="--prof" in sys.argv))

@@ -20,7 +20,7 @@ _lib = None
 # every symbol include/alazgpu.h declares (tests/test_abi.py checks the header against this)
 EXPORTS = [
     "alz_create", "alz_destroy", "alz_strerror", "alz_last_cuda_error", "alz_set_stream", "alz_sync",
-    "alz_table_upsert", "alz_table_erase", "alz_table_commit", "alz_submit_l7", "alz_submit_l7_device",
+    "alz_table_upsert", "alz_table_upsert_batch", "alz_table_erase", "alz_table_commit", "alz_submit_l7", "alz_submit_l7_device",
     "alz_submit_l7_packed", "alz_submit_l7_packed_device", "alz_pack_l7",
     "alz_submit_l7_raw", "alz_window_flush", "alz_window_flush_device", "alz_window_fetch", "alz_get_stats", "alz_gnn_score",
     "alz_gnn_score_device", "alz_edge_quantiles", "alz_submit_tcp", "alz_sock_lookup", "alz_comm_unique_id", "alz_comm_init",
@@ -48,6 +48,7 @@ def load(rebuild=False):
         "alz_sync": ([vp], i),
         "alz_table_upsert": ([vp, i, u32, u32], i),
         "alz_table_erase": ([vp, i, u32], i),
+        "alz_table_upsert_batch": ([vp, i, vp, vp, sz], i),
         "alz_table_commit": ([vp], i),
         "alz_submit_l7": ([vp, vp, sz], i),
         "alz_submit_l7_device": ([vp, vp, sz], i),
@@ -86,7 +87,7 @@ def load(rebuild=False):
     }
     if abi.ABI_VERSION < 2:    # A/B timing against a round-1 build (ALZ_LIB_PATH + ALZ_ABI_VERSION=1)
         for k in ("alz_submit_l7_packed", "alz_submit_l7_packed_device", "alz_pack_l7", "alz_window_fetch",
-                  "alz_pinned_alloc_local"):
+                  "alz_pinned_alloc_local", "alz_table_upsert_batch"):
             sig.pop(k)
     for name, (args, res) in sig.items():
         f = getattr(L, name)   # AttributeError = header/library mismatch: loud
@@ -167,11 +168,21 @@ class Handle:
     def commit(self):
         self._ck(self.L.alz_table_commit(self.h), "alz_table_commit")
 
+    def upsert_batch(self, table, ips, ids):
+        ips = np.ascontiguousarray(ips, dtype=np.uint32)
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        assert len(ips) == len(ids)
+        self._ck(self.L.alz_table_upsert_batch(self.h, table, _ptr(ips), _ptr(ids), len(ips)), "alz_table_upsert_batch")
+
     def load_tables(self, pod_ip, svc_ip):
-        for k, v in enumerate(pod_ip):
-            self.upsert(abi.TABLE_POD, int(v), k)
-        for k, v in enumerate(svc_ip):
-            self.upsert(abi.TABLE_SVC, int(v), k)
+        if abi.ABI_VERSION < 2:
+            for k, v in enumerate(pod_ip):
+                self.upsert(abi.TABLE_POD, int(v), k)
+            for k, v in enumerate(svc_ip):
+                self.upsert(abi.TABLE_SVC, int(v), k)
+        else:
+            self.upsert_batch(abi.TABLE_POD, pod_ip, np.arange(len(pod_ip)))
+            self.upsert_batch(abi.TABLE_SVC, svc_ip, np.arange(len(svc_ip)))
         self.commit()
 
     # ---- ingest

@@ -59,7 +59,7 @@ static int alloc_table(alz_handle* h, AccTable* t, uint32_t max_rows, uint32_t* 
   t->n_rows = n_rows_dev;
   const uint32_t dict_cap = next_pow2(2ull * max_rows);
   t->dict_mask = dict_cap - 1;
-  const size_t rows = (size_t)max_rows + 2;
+  const size_t rows = (size_t)max_rows + kPairKinds;
   CK(cudaMalloc(&t->dict, (size_t)dict_cap * sizeof(DictEnt)));
   CK(cudaMalloc(&t->row_key, rows * 8));
   CK(cudaMalloc(&t->lat_sum, rows * 8));
@@ -74,9 +74,14 @@ static int alloc_table(alz_handle* h, AccTable* t, uint32_t max_rows, uint32_t* 
     t->dict_rev_mask = rev_cap - 1;
     CK(cudaMalloc(&t->dict_rev, (size_t)rev_cap * sizeof(DictEnt)));
     CK(cudaMemsetAsync(t->dict_rev, 0xFF, (size_t)rev_cap * sizeof(DictEnt), h->stream));
-    CK(cudaMalloc(&t->row_rev, rows));
-    CK(cudaMemsetAsync(t->row_rev, 0, rows, h->stream));
-    CK(cudaMemsetAsync(t->row_rev + max_rows + 1, 1, 1, h->stream));   // sentinel row of the reversed free-marker key
+    const uint32_t host_cap = std::max<uint32_t>(1024u, dict_cap >> 3);   // host-keyed outbound pairs: rarer still
+    t->dict_host_mask = host_cap - 1;
+    CK(cudaMalloc(&t->dict_host, (size_t)host_cap * sizeof(DictEnt)));
+    CK(cudaMemsetAsync(t->dict_host, 0xFF, (size_t)host_cap * sizeof(DictEnt), h->stream));
+    CK(cudaMalloc(&t->row_kind, rows));
+    CK(cudaMemsetAsync(t->row_kind, 0, rows, h->stream));
+    CK(cudaMemsetAsync(t->row_kind + max_rows + kPairRev, (int)kPairRev, 1, h->stream));   // sentinel rows of the free-marker key
+    CK(cudaMemsetAsync(t->row_kind + max_rows + kPairHost, (int)kPairHost, 1, h->stream));
     CK(cudaMalloc(&t->row_cnt, rows * 4)); CK(cudaMemsetAsync(t->row_cnt, 0, rows * 4, h->stream));
     CK(cudaMalloc(&t->row_aux, rows * 4));
   }
@@ -88,7 +93,7 @@ static int alloc_table(alz_handle* h, AccTable* t, uint32_t max_rows, uint32_t* 
   return ALZ_OK;
 }
 static void free_table(AccTable* t) {
-  cudaFree(t->dict); cudaFree(t->dict_rev); cudaFree(t->row_key); cudaFree(t->row_rev); cudaFree(t->lat_sum);
+  cudaFree(t->dict); cudaFree(t->dict_rev); cudaFree(t->dict_host); cudaFree(t->row_key); cudaFree(t->row_kind); cudaFree(t->lat_sum);
   cudaFree(t->err5xx); cudaFree(t->count); cudaFree(t->row_cnt); cudaFree(t->row_aux); cudaFree(t->hist);
   memset(t, 0, sizeof(*t));
 }
@@ -96,6 +101,7 @@ static void free_table(AccTable* t) {
 static int clear_dict(alz_handle* h, AccTable* t) {
   CK(cudaMemsetAsync(t->dict, 0xFF, ((size_t)t->dict_mask + 1) * sizeof(DictEnt), h->stream));
   if (t->dict_rev) CK(cudaMemsetAsync(t->dict_rev, 0xFF, ((size_t)t->dict_rev_mask + 1) * sizeof(DictEnt), h->stream));
+  if (t->dict_host) CK(cudaMemsetAsync(t->dict_host, 0xFF, ((size_t)t->dict_host_mask + 1) * sizeof(DictEnt), h->stream));
   CK(cudaMemsetAsync(t->n_rows, 0, 4, h->stream));
   return ALZ_OK;
 }
@@ -157,6 +163,7 @@ extern "C" int alz_create(const alz_config* cfg, alz_handle** out) {
   CKC(cudaEventCreateWithFlags(&h->ev_tmp, cudaEventDisableTiming));
   CKC(cudaEventCreateWithFlags(&h->ev_count, cudaEventDisableTiming));
   CKC(cudaEventCreateWithFlags(&h->ev_patch, cudaEventDisableTiming));
+  for (int i = 0; i < 3; ++i) CKC(cudaEventCreate(&h->ev_t[i]));
 
   h->ep_cap = next_pow2(2ull * h->cfg.max_endpoints);
   h->ep_tab.assign(h->ep_cap, EpEntry{0u, 0u, 0u, 0u});
@@ -213,6 +220,7 @@ extern "C" int alz_destroy(alz_handle* h) {
   if (h->ev_tmp) cudaEventDestroy(h->ev_tmp);
   if (h->ev_count) cudaEventDestroy(h->ev_count);
   if (h->ev_patch) cudaEventDestroy(h->ev_patch);
+  for (int i = 0; i < 3; ++i) if (h->ev_t[i]) cudaEventDestroy(h->ev_t[i]);
   cudaFree(h->d_sort_tmp); cudaFree(h->d_out);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -308,9 +316,23 @@ extern "C" int alz_pinned_alloc_local(alz_handle* h, size_t bytes, void** out) {
 }
 
 // ---- join build side -----------------------------------------------------------------
+static int upsert_locked(alz_handle* h, int table, uint32_t ip, uint32_t id);
 extern "C" int alz_table_upsert(alz_handle* h, int table, uint32_t ip, uint32_t id) {
   if (!h || (table != ALZ_TABLE_POD && table != ALZ_TABLE_SVC) || id >= (1u << 29)) return ALZ_E_INVAL;
   std::lock_guard<std::mutex> g(h->mu);
+  return upsert_locked(h, table, ip, id);
+}
+extern "C" int alz_table_upsert_batch(alz_handle* h, int table, const uint32_t* ips, const uint32_t* ids, size_t n) {
+  if (!h || (table != ALZ_TABLE_POD && table != ALZ_TABLE_SVC) || ((!ips || !ids) && n)) return ALZ_E_INVAL;
+  std::lock_guard<std::mutex> g(h->mu);
+  for (size_t i = 0; i < n; ++i) {
+    if (ids[i] >= (1u << 29)) return ALZ_E_INVAL;
+    const int rc = upsert_locked(h, table, ips[i], ids[i]);
+    if (rc != ALZ_OK) return rc;
+  }
+  return ALZ_OK;
+}
+static int upsert_locked(alz_handle* h, int table, uint32_t ip, uint32_t id) {
   auto it = h->ep_host.find(ip);
   if (it == h->ep_host.end()) {
     if (h->ep_host.size() >= h->cfg.max_endpoints) return ALZ_E_CAPACITY;
@@ -409,6 +431,7 @@ extern "C" int alz_table_commit(alz_handle* h) {
   CK(cudaMemcpyAsync(h->d_patch, h->h_patch, n * sizeof(EpPatch), cudaMemcpyHostToDevice, h->stream));
   CK(cudaEventRecord(h->ev_patch, h->stream));
   launch_ep_patch(h->d_ep, h->d_patch, (uint32_t)n, h->sms, h->stream);
+  h->launches += 1;
   CK(cudaGetLastError());
   return ALZ_OK;
 }
@@ -418,12 +441,14 @@ extern "C" int alz_table_commit(alz_handle* h) {
 // (alz_ingest.cu). Split in two so that a flush can read the edge count between the halves.
 static int fold_first_half(alz_handle* h) {
   launch_fold_resolve(h->pairs, h->d_ep, h->ep_cap - 1, h->edges, h->d_ctr, h->d_hot, h->sms, h->stream);
+  h->launches += 1;
   CK(cudaGetLastError());
   return ALZ_OK;
 }
 static int fold_second_half(alz_handle* h) {
   launch_fold_add(h->pairs, h->edges, h->d_ctr, h->d_hot, h->sms, h->stream);
   launch_hot_select(h->pairs, h->d_hot, h->sms, h->stream);
+  h->launches += 2;
   CK(cudaGetLastError());
   int rc = clear_dict(h, &h->pairs);
   h->pending_since_fold = 0;
@@ -454,6 +479,7 @@ static int ingest_device(alz_handle* h, const void* d, uint64_t n, bool rec16, c
                            h->stream);
   }
   CK(cudaGetLastError());
+  h->launches += n ? 1 : 0;
   h->events_in += n;
   h->pending_since_fold += n;
   // pair histograms are u32: fold before any bucket could wrap
@@ -557,8 +583,8 @@ extern "C" long alz_pack_l7(const alz_l7_rec* recs, size_t n, alz_l7_rec16* out,
     const alz_l7_rec& r = recs[i];
     alz_l7_rec16 o;
     o.saddr = r.saddr; o.daddr = r.daddr; o.status = r.status;
-    o.protocol = r.protocol & 0x7Fu; o.method_flags = r.method_flags;
-    if (r.protocol & 0x80u) o.protocol = 0x7Fu;   // no such protocol either way: stays "not a request row"
+    o.protocol = r.protocol & 0x7Fu; o.method_flags = r.method_flags;   // keeps ALZ_PROTO_F_HOSTKEY
+    if (r.protocol & 0x80u) o.protocol = 0x3Fu;   // no such protocol either way: stays "not a request row"
     if (r.duration_ns >> 32) {
       if (k >= cap_ovf || !ovf) return -1;
       ovf[k] = r.duration_ns;
@@ -602,6 +628,7 @@ extern "C" int alz_submit_l7_raw(alz_handle* h, const void* raw, size_t n) {
       CK(cudaEventRecord(s.copied, h->copy_stream));
       CK(cudaStreamWaitEvent(h->stream, s.copied, 0));
       launch_compact_raw((const uint8_t*)s.d, m, (alz_l7_rec*)s.d_aux, h->sms, h->stream);
+      h->launches += 1;
       rc = ingest_device(h, s.d_aux, m, false, nullptr);
       if (rc != ALZ_OK) return rc;
       CK(cudaEventRecord(s.consumed, h->stream));
@@ -633,6 +660,7 @@ static int prepare_flush(alz_handle* h, bool* overflow) {
   if (h->h_ctr->capacity_events != h->lost_reported) { h->lost_reported = h->h_ctr->capacity_events; *overflow = true; }
   if (h->n_live) {
     launch_iota(h->d_rows[0], h->n_live, h->sms, h->stream);
+    h->launches += 1;
     sort_pairs(h->d_sort_tmp, h->sort_tmp_bytes, h->edges.row_key, h->d_keys[1], h->d_rows[0], h->d_rows[1],
                h->n_live, h->stream);
     CK(cudaGetLastError());
@@ -642,6 +670,7 @@ static int prepare_flush(alz_handle* h, bool* overflow) {
 
 static int finish_flush(alz_handle* h) {
   launch_gather_edges(h->edges, h->d_keys[1], h->d_rows[1], h->n_live, h->d_out, true, h->sms, h->stream);
+  h->launches += h->n_live ? 1 : 0;
   CK(cudaGetLastError());
   int rc = clear_dict(h, &h->edges);
   if (rc != ALZ_OK) return rc;
@@ -652,13 +681,17 @@ static int finish_flush(alz_handle* h) {
 
 static int flush_device_locked(alz_handle* h, const alz_edge_out** dev_edges, size_t* n_out) {
   bool overflow = false;
+  CK(cudaEventRecord(h->ev_t[0], h->stream));
   int rc = prepare_flush(h, &overflow);
   *n_out = h->n_live;
-  int mrc = alz_internal_merge_ranks(h, rc);  // multi-GPU: canonical merge + one collective (alz_comm.cu)
+  CK(cudaEventRecord(h->ev_t[1], h->stream));
+  int mrc = alz_internal_merge_ranks(h, rc);  // multi-GPU: one collective over the ranks' edge rows (alz_comm.cu)
   if (mrc == ALZ_E_UNSUPPORTED) {             // single rank
     if (rc != ALZ_OK) return rc;
     mrc = finish_flush(h);
   }
+  CK(cudaEventRecord(h->ev_t[2], h->stream));
+  h->ev_t_valid = true;
   if (mrc != ALZ_OK) return mrc;
   *n_out = h->last_n_edges;
   if (dev_edges) *dev_edges = h->d_out;
@@ -733,6 +766,13 @@ extern "C" int alz_get_stats(alz_handle* h, alz_stats* st) {
   st->tcp_localhost_dropped = h->tcp_localhost_dropped;
   st->capacity_events = lost;
   st->windows = h->windows;
+  st->kernel_launches = h->launches;
+  st->collective_bytes_last = h->collective_bytes_last;
+  if (h->ev_t_valid) {   // the stream was synchronised above, so the events have completed
+    float a = 0.f, b = 0.f;
+    if (cudaEventElapsedTime(&a, h->ev_t[0], h->ev_t[1]) == cudaSuccess) st->flush_local_us_last = (uint64_t)(a * 1000.f);
+    if (cudaEventElapsedTime(&b, h->ev_t[1], h->ev_t[2]) == cudaSuccess) st->merge_us_last = (uint64_t)(b * 1000.f);
+  }
   return ALZ_OK;
 }
 

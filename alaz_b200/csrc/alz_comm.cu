@@ -1,17 +1,27 @@
 // alz_comm.cu — multi-GPU window merge: one rank per GPU, events
-// pre-partitioned by alz_owner_rank(saddr), tables replicated. At flush every
-// rank contributes its live edges and ONE ncclAllReduce sums the per-edge
-// accumulators, after which every rank holds the whole graph in canonical
-// (ascending packed key) order — integer sums, so bit-exact for any rank count.
+// pre-partitioned by alz_owner_rank(saddr), tables replicated. Every event of an edge
+// reaches one rank, so the ranks' edge sets are disjoint and a rank's accumulators are
+// already final: what the flush has to do is hand every rank every other rank's rows.
 //
-//   1. all-gather the local edge counts, then the local sorted keys (padded)
-//   2. sort + unique the gathered keys  -> canonical dictionary, same on all ranks
-//   3. scatter local rows into a zeroed canonical array [n_can x 35 u64]
-//        word 0..2  = count, err5xx, lat_sum ;  word 3..34 = hist cells packed 2 x u32
-//      (an edge is owned by one rank, every other rank adds 0, so the packed u32
-//       halves cannot carry into each other)
-//   4. ncclAllReduce(sum, u64) on that array   <- the single exchange step
-//   5. unpack into alz_edge_out rows
+// Default path — ONE collective, no host round trip before it:
+//   1. each rank writes its sorted live rows behind a one-row header {count, status} in a
+//      send buffer; the per-rank block size of the collective comes from the previous
+//      window's counts (+25 %), so no count exchange is needed
+//   2. ncclAllGather of the blocks                      <- the single exchange step
+//   3. every rank merges the R sorted, disjoint lists: a row's place in the canonical
+//      (ascending packed key) order is its index in its own list plus its lower bounds
+//      in the other lists. The same kernel notices a key present on two ranks, a rank
+//      whose rows did not fit its block, or a rank that reported a local error — all
+//      ranks see the same headers, so all ranks take the same decision.
+//   4. one device->host read of {total, flags}: the only synchronisation, and the one the
+//      API needs anyway to return the edge count.
+// A block that was too small (traffic grew by more than 25 % in one window) is sent
+// again, larger; the local rows are only reset after a successful merge.
+//
+// General path (a key present on several ranks: the caller did not partition by
+// alz_owner_rank): canonical dictionary by all-gather + sort + unique, local rows
+// scattered into a zeroed canonical array, ONE ncclAllReduce(sum) on the accumulators.
+// Integer sums either way, so bit-exact for any rank count.
 //
 // NCCL is loaded lazily with dlopen so that single-GPU users (and the Go agent
 // on a box without NCCL) never need libnccl.so.2.
@@ -60,7 +70,22 @@ bool load_nccl() {
   return true;
 }
 
-constexpr int kCanWords = 3 + ALZ_NB / 2;  // u64 words per canonical edge row
+constexpr int kCanWords = 3 + ALZ_NB;      // u64 words per canonical edge row of the general path: count, err5xx,
+                                           // lat_sum and one word per histogram cell (a cell is u32 modulo 2^32: the
+                                           // low halves of the sums are taken, nothing can carry between cells)
+constexpr uint32_t kRowBytes = sizeof(alz_edge_out);   // 296 = 37 x 8
+constexpr uint32_t kRowWords64 = kRowBytes / 8;
+constexpr uint32_t kHdrMagic = 0xA1A2C0DEu;
+struct BlockHeader {      // first row of a rank's block
+  uint32_t magic, count;
+  int32_t status;
+  uint32_t pad;
+};
+struct MergeInfo {        // written by the merge kernel, read by the host
+  uint32_t total, dup, overflow, max_count;
+  int32_t peer_status;
+  uint32_t pad[3];
+};
 
 // out[i] = keys[i] for i < n, kEmptyKey padding up to n_pad
 __global__ void pad_keys_kernel(const uint64_t* __restrict__ keys, uint32_t n, uint64_t* __restrict__ out,
@@ -124,11 +149,10 @@ __global__ void __launch_bounds__(256) scatter_canonical_kernel(AccTable edges, 
     const uint32_t row = rows[i];
     const uint32_t pos = lower_bound_u64(can_keys, n_can, keys[i]);   // always present
     uint64_t* dst = can + (size_t)pos * kCanWords;
-    const uint32_t c0 = edges.hist[(size_t)row * ALZ_NB + 2 * lane];
-    const uint32_t c1 = edges.hist[(size_t)row * ALZ_NB + 2 * lane + 1];
-    dst[3 + lane] = ((uint64_t)c1 << 32) | c0;
-    edges.hist[(size_t)row * ALZ_NB + 2 * lane] = 0u;
-    edges.hist[(size_t)row * ALZ_NB + 2 * lane + 1] = 0u;
+    dst[3 + lane] = edges.hist[(size_t)row * ALZ_NB + lane];
+    dst[3 + 32 + lane] = edges.hist[(size_t)row * ALZ_NB + 32 + lane];
+    edges.hist[(size_t)row * ALZ_NB + lane] = 0u;
+    edges.hist[(size_t)row * ALZ_NB + 32 + lane] = 0u;
     if (lane == 0) {
       dst[0] = edges.count[row]; dst[1] = edges.err5xx[row]; dst[2] = edges.lat_sum[row];
       edges.count[row] = 0ull; edges.err5xx[row] = 0ull; edges.lat_sum[row] = 0ull;
@@ -144,9 +168,8 @@ __global__ void __launch_bounds__(256) unpack_canonical_kernel(const uint64_t* _
   for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_can; i += warps_per_grid) {
     const uint64_t* src = can + (size_t)i * kCanWords;
     alz_edge_out* o = &out[i];
-    const uint64_t w = src[3 + lane];
-    o->hist[2 * lane] = (uint32_t)w;
-    o->hist[2 * lane + 1] = (uint32_t)(w >> 32);
+    o->hist[lane] = (uint32_t)src[3 + lane];
+    o->hist[32 + lane] = (uint32_t)src[3 + 32 + lane];
     if (lane == 0) {
       uint8_t ft, tt; uint32_t f, t;
       unpack_edge_key(can_keys[i], &ft, &f, &tt, &t);
@@ -155,6 +178,90 @@ __global__ void __launch_bounds__(256) unpack_canonical_kernel(const uint64_t* _
       o->from = f; o->to = t;
       o->count = src[0]; o->err5xx = src[1]; o->lat_sum_ns = src[2];
     }
+  }
+}
+
+// packed edge key of an output row (inverse of unpack_edge_key)
+__device__ __forceinline__ uint64_t row_key_of(const alz_edge_out* r) {
+  const uint4 hd = *reinterpret_cast<const uint4*>(r);   // from_type, to_type, pad | pad | from | to
+  const uint32_t ft = hd.x & 0xFFu, tt = (hd.x >> 8) & 0xFFu;
+  if (ft == ALZ_NODE_POD) return ((uint64_t)tt << 61) | ((uint64_t)(hd.z & 0x1FFFFFFFu) << 32) | hd.w;
+  return (1ull << 63) | ((uint64_t)ft << 61) | ((uint64_t)(hd.w & 0x1FFFFFFFu) << 32) | hd.z;
+}
+__device__ __forceinline__ uint32_t lower_bound_rows(const alz_edge_out* rows, uint32_t n, uint64_t k, bool* equal) {
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (row_key_of(rows + mid) < k) lo = mid + 1; else hi = mid; }
+  *equal = lo < n && row_key_of(rows + lo) == k;
+  return lo;
+}
+
+// Merge of the gathered blocks: block q = header row + cap rows, of which header.count are live and sorted.
+// Eight lanes per row: the lanes split the other ranks' binary searches among them, then copy the row.
+__global__ void __launch_bounds__(256) merge_blocks_kernel(const alz_edge_out* __restrict__ recv, uint32_t cap, uint32_t R,
+                                                           alz_edge_out* __restrict__ out, uint32_t out_cap,
+                                                           MergeInfo* __restrict__ info) {
+  __shared__ uint32_t s_cnt[64];
+  __shared__ uint32_t s_bad;
+  const size_t stride_rows = (size_t)cap + 1;
+  if (threadIdx.x == 0) s_bad = 0u;
+  __syncthreads();
+  if (threadIdx.x < R) {
+    const BlockHeader* hd = reinterpret_cast<const BlockHeader*>(recv + threadIdx.x * stride_rows);
+    uint32_t cnt = hd->count;
+    if (hd->magic != kHdrMagic || hd->status != ALZ_OK) {
+      atomicOr(&s_bad, 1u);
+      if (blockIdx.x == 0) info->peer_status = hd->magic != kHdrMagic ? (int32_t)ALZ_E_STATE : hd->status;
+      cnt = 0;
+    }
+    if (cnt > cap) { atomicOr(&s_bad, 2u); if (blockIdx.x == 0) { info->overflow = 1u; atomicMax(&info->max_count, cnt); } }
+    if (blockIdx.x == 0) atomicMax(&info->max_count, cnt);
+    s_cnt[threadIdx.x] = cnt;
+  }
+  __syncthreads();
+  uint32_t total = 0;
+  for (uint32_t q = 0; q < R; ++q) total += s_cnt[q];
+  if (blockIdx.x == 0 && threadIdx.x == 0) info->total = total;
+  if (s_bad != 0u || total > out_cap) { if (blockIdx.x == 0 && threadIdx.x == 0 && total > out_cap) info->overflow = 2u; return; }
+  const uint32_t sl = threadIdx.x & 7u;
+  const uint32_t groups = (gridDim.x * blockDim.x) >> 3;
+  const uint32_t n_iter = (total + groups - 1) / groups;
+  uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  for (uint32_t it = 0; it < n_iter; ++it, g += groups) {
+    const bool valid = g < total;
+    // (q, i) of flat index g
+    uint32_t q = 0, i = valid ? g : 0u;
+    while (valid && i >= s_cnt[q]) { i -= s_cnt[q]; ++q; }
+    const alz_edge_out* src = recv + q * stride_rows + 1 + i;
+    const uint64_t key = valid ? row_key_of(src) : 0ull;
+    uint32_t part = 0;
+    bool dup = false;
+    for (uint32_t p = sl; p < R; p += 8u) {
+      if (!valid || p == q) continue;
+      bool eq;
+      part += lower_bound_rows(recv + p * stride_rows + 1, s_cnt[p], key, &eq);
+      dup |= eq;
+    }
+    part += __shfl_xor_sync(0xFFFFFFFFu, part, 1);
+    part += __shfl_xor_sync(0xFFFFFFFFu, part, 2);
+    part += __shfl_xor_sync(0xFFFFFFFFu, part, 4);
+    if (dup) info->dup = 1u;
+    if (!valid) continue;
+    const uint64_t* s64 = reinterpret_cast<const uint64_t*>(src);
+    uint64_t* d64 = reinterpret_cast<uint64_t*>(out + (i + part));
+    for (uint32_t w = sl; w < kRowWords64; w += 8u) d64[w] = s64[w];
+  }
+}
+
+// a successful merge consumes the window: zero the local edge rows that were sent
+__global__ void __launch_bounds__(256) zero_edge_rows_kernel(AccTable edges, const uint32_t* __restrict__ rows, uint32_t n) {
+  const uint32_t sl = threadIdx.x & 7u;
+  const uint32_t groups = (gridDim.x * blockDim.x) >> 3;
+  for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; i < n; i += groups) {
+    const uint32_t row = rows[i];
+    uint4* cells = reinterpret_cast<uint4*>(edges.hist + (size_t)row * ALZ_NB + sl * 8u);
+    cells[0] = make_uint4(0u, 0u, 0u, 0u);
+    cells[1] = make_uint4(0u, 0u, 0u, 0u);
+    if (sl == 0) { edges.count[row] = 0ull; edges.err5xx[row] = 0ull; edges.lat_sum[row] = 0ull; }
   }
 }
 
@@ -175,7 +282,14 @@ struct alz_comm_state {
   void* d_tmp = nullptr;
   size_t tmp_bytes = 0;
   size_t gather_cap = 0;          // keys
-  uint64_t allreduce_bytes = 0;   // of the last window
+  // default path
+  alz_edge_out* d_send = nullptr; // [1 + max_edges]: header row + local sorted rows
+  alz_edge_out* d_recv = nullptr; // [R * (1 + cap_r)]
+  size_t recv_rows = 0;           // allocated rows of d_recv
+  uint32_t cap_r = 0;             // rows per rank block of the next collective (0 = not known yet)
+  BlockHeader* h_hdr = nullptr;   // pinned
+  MergeInfo* d_info = nullptr;
+  MergeInfo* h_info = nullptr;    // pinned
 };
 
 #define CK(expr)                                                                       \
@@ -234,6 +348,10 @@ extern "C" int alz_comm_init(alz_handle* h, int nranks, int rank, const void* id
   CK(cudaMalloc(&c->d_vals, me * 4));
   c->tmp_bytes = std::max(sort_pairs_temp_bytes((uint32_t)me), scan_temp_bytes((uint32_t)me));
   CK(cudaMalloc(&c->d_tmp, c->tmp_bytes));
+  CK(cudaMalloc(&c->d_send, (me + 1) * sizeof(alz_edge_out)));
+  CK(cudaMallocHost(&c->h_hdr, sizeof(alz_edge_out)));
+  CK(cudaMalloc(&c->d_info, sizeof(MergeInfo)));
+  CK(cudaMallocHost(&c->h_info, sizeof(MergeInfo)));
   return ALZ_OK;
 }
 
@@ -244,16 +362,16 @@ void alz_internal_free_comm(alz_handle* h) {
   cudaFree(c->d_counts); if (c->h_counts) cudaFreeHost(c->h_counts);
   cudaFree(c->d_gather); cudaFree(c->d_flags); cudaFree(c->d_pos); cudaFree(c->d_can_keys);
   cudaFree(c->d_can); cudaFree(c->d_iota); cudaFree(c->d_vals); cudaFree(c->d_tmp);
+  cudaFree(c->d_send); cudaFree(c->d_recv); cudaFree(c->d_info);
+  if (c->h_hdr) cudaFreeHost(c->h_hdr);
+  if (c->h_info) cudaFreeHost(c->h_info);
   delete c;
   h->comm = nullptr;
 }
 
-// Called by alz_window_flush_device after prepare_flush(): local live edges are
-// sorted in d_keys[1] (keys) / d_rows[1] (rows), h->n_live of them.
-int alz_internal_merge_ranks(alz_handle* h, int local_rc) {
+// General path: keys may live on several ranks. Local live edges are sorted in d_keys[1] / d_rows[1].
+static int merge_allreduce(alz_handle* h) {
   alz_comm_state* c = h->comm;
-  if (!c || h->comm_nranks <= 1) return ALZ_E_UNSUPPORTED;
-  if (local_rc != ALZ_OK) return local_rc;
   const int R = h->comm_nranks;
   cudaStream_t s = h->stream;
   const unsigned grid = (unsigned)h->sms * 4;
@@ -310,7 +428,8 @@ int alz_internal_merge_ranks(alz_handle* h, int local_rc) {
                                                       c->d_can_keys, n_can, c->d_can);
   // 4. the single exchange step
   NK(g_nccl.AllReduce(c->d_can, c->d_can, (size_t)n_can * kCanWords, ncclUint64, ncclSum, c->comm, s));
-  c->allreduce_bytes = can_bytes;
+  h->collective_bytes_last += can_bytes;
+  h->launches += 5;
   // 5. unpack; local edge table back to empty
   unpack_canonical_kernel<<<grid * 2, 256, 0, s>>>(c->d_can_keys, c->d_can, n_can, h->d_out);
   CK(cudaGetLastError());
@@ -319,4 +438,74 @@ int alz_internal_merge_ranks(alz_handle* h, int local_rc) {
   h->last_n_edges = n_can;
   h->windows++;
   return ALZ_OK;
+}
+
+static uint32_t block_rows_for(uint64_t max_count) {   // +25 % head room, in steps of 1024 rows
+  const uint64_t want = max_count + max_count / 4 + 1024;
+  return (uint32_t)((want + 1023) / 1024 * 1024);
+}
+
+// Called by the flush after prepare_flush(): local live edges are sorted in d_keys[1] (keys) / d_rows[1]
+// (rows), h->n_live of them; local_rc is this rank's status so far. Every rank enters the collective whatever
+// its own status, so nobody is left waiting in NCCL, and all ranks return the same failure.
+int alz_internal_merge_ranks(alz_handle* h, int local_rc) {
+  alz_comm_state* c = h->comm;
+  if (!c || h->comm_nranks <= 1) return ALZ_E_UNSUPPORTED;
+  const int R = h->comm_nranks;
+  if (R > 64) return ALZ_E_UNSUPPORTED;
+  cudaStream_t s = h->stream;
+  const unsigned grid = (unsigned)h->sms * 4;
+  const uint32_t n_local = local_rc == ALZ_OK ? h->n_live : 0u;
+  h->collective_bytes_last = 0;
+
+  if (c->cap_r == 0) {   // first window: nothing to size the blocks from, exchange the counts once
+    CK(cudaMemcpyAsync(c->d_counts + h->comm_rank, &n_local, 4, cudaMemcpyHostToDevice, s));
+    NK(g_nccl.AllGather(c->d_counts + h->comm_rank, c->d_counts, 1, ncclUint32, c->comm, s));
+    CK(cudaMemcpyAsync(c->h_counts, c->d_counts, 4 * R, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    uint32_t mx = 0;
+    for (int r = 0; r < R; ++r) mx = std::max(mx, c->h_counts[r]);
+    c->cap_r = block_rows_for(mx);
+  }
+  // local rows behind the header, in canonical order; the window is NOT reset yet
+  if (n_local) {
+    launch_gather_edges(h->edges, h->d_keys[1], h->d_rows[1], n_local, c->d_send + 1, false, h->sms, s);
+    h->launches += 1;
+  }
+  for (int attempt = 0; attempt < 4; ++attempt) {
+    memset(c->h_hdr, 0, sizeof(alz_edge_out));
+    c->h_hdr->magic = kHdrMagic; c->h_hdr->count = n_local; c->h_hdr->status = local_rc;
+    CK(cudaMemcpyAsync(c->d_send, c->h_hdr, sizeof(alz_edge_out), cudaMemcpyHostToDevice, s));
+    const size_t block_rows = (size_t)c->cap_r + 1;
+    if (block_rows * R > c->recv_rows) {
+      CK(cudaStreamSynchronize(s));
+      cudaFree(c->d_recv);
+      c->d_recv = nullptr;
+      c->recv_rows = block_rows * R;
+      CK(cudaMalloc(&c->d_recv, c->recv_rows * sizeof(alz_edge_out)));
+    }
+    CK(cudaMemsetAsync(c->d_info, 0, sizeof(MergeInfo), s));
+    // the single exchange step: every rank's header + its first cap_r rows
+    NK(g_nccl.AllGather(c->d_send, c->d_recv, block_rows * kRowWords64, ncclUint64, c->comm, s));
+    h->collective_bytes_last += (uint64_t)block_rows * R * kRowBytes;
+    merge_blocks_kernel<<<grid, 256, 0, s>>>(c->d_recv, c->cap_r, (uint32_t)R, h->d_out, h->cfg.max_edges, c->d_info);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(c->h_info, c->d_info, sizeof(MergeInfo), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));   // the flush's one synchronisation: the caller needs the edge count
+    const MergeInfo inf = *c->h_info;
+    if (inf.peer_status != ALZ_OK) return local_rc != ALZ_OK ? local_rc : inf.peer_status;   // the window stays intact
+    if (inf.overflow == 1u) { c->cap_r = block_rows_for(inf.max_count); continue; }   // every rank sees the same headers
+    if (inf.overflow == 2u) return ALZ_E_CAPACITY;                                    // merged graph larger than max_edges
+    c->cap_r = block_rows_for(inf.max_count);                                         // next window's block size
+    if (inf.dup) return merge_allreduce(h);                                           // not partitioned by owner: general path
+    // success: the window is consumed
+    if (n_local) { zero_edge_rows_kernel<<<grid, 256, 0, s>>>(h->edges, h->d_rows[1], n_local); h->launches += 1; }
+    CK(cudaMemsetAsync(h->edges.dict, 0xFF, ((size_t)h->edges.dict_mask + 1) * sizeof(DictEnt), s));
+    CK(cudaMemsetAsync(h->edges.n_rows, 0, 4, s));
+    h->last_n_edges = inf.total;
+    h->windows++;
+    return ALZ_OK;
+  }
+  return ALZ_E_CAPACITY;
 }

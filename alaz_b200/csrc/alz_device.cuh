@@ -125,24 +125,29 @@ struct __align__(16) DictEnt {
 constexpr uint32_t kNoRow = 0xFFFFFFFFu;
 constexpr uint32_t kLostRow = 0xFFFFFFFEu;  // dictionary or row pool exhausted
 
+constexpr uint32_t kPairFwd = 0u, kPairRev = 1u, kPairHost = 2u, kPairKinds = 3u;
+
 struct AccTable {
   DictEnt* dict;      // [dict_mask + 1]
   uint32_t dict_mask;
-  // pair table only: second dictionary for the socket pairs of reversed rows (AMQP DELIVER, REDIS
-  // PUSHED_EVENT). Both dictionaries hand out rows of the same pool; row_rev[row] says which one.
+  // pair table only: further dictionaries for the socket pairs of reversed rows (kind 1: AMQP DELIVER, REDIS
+  // PUSHED_EVENT) and for host-keyed outbound events (kind 2: the key's high word is a Host-header id, not a
+  // daddr; ALZ_PROTO_F_HOSTKEY). All dictionaries hand out rows of the same pool; row_kind[row] says which one.
   DictEnt* dict_rev;
   uint32_t dict_rev_mask;
-  uint32_t max_rows;  // rows [0, max_rows) are allocatable; rows max_rows, max_rows + 1 are the sentinel rows of the
-                      // key that equals the free marker (forward / reversed); every per-row array has max_rows + 2 entries
+  DictEnt* dict_host;
+  uint32_t dict_host_mask;
+  uint32_t max_rows;  // rows [0, max_rows) are allocatable; rows max_rows + kind are the sentinel rows of the key that
+                      // equals the free marker (one per kind); every per-row array has max_rows + kPairKinds entries
   uint32_t* n_rows;   // device counter of allocated rows
-  uint64_t* row_key;  // [max_rows + 2]
-  uint8_t* row_rev;   // [max_rows + 2] (pair table only)
-  uint64_t* lat_sum;  // [max_rows + 2]
-  uint64_t* err5xx;   // [max_rows + 2]
-  uint64_t* count;    // [max_rows + 2] (edge table only; the pair table derives it from hist)
-  uint32_t* row_cnt;  // [max_rows + 2] (pair table only) events of the row at the last fold, saturated
-  uint32_t* row_aux;  // [max_rows + 2] (pair table only) edge row found by fold_resolve_kernel
-  uint32_t* hist;     // [(max_rows + 2) * ALZ_NB]
+  uint64_t* row_key;  // [max_rows + 3]
+  uint8_t* row_kind;  // [max_rows + 3] (pair table only) kPairFwd / kPairRev / kPairHost
+  uint64_t* lat_sum;  // [max_rows + 3]
+  uint64_t* err5xx;   // [max_rows + 3]
+  uint64_t* count;    // [max_rows + 3] (edge table only; the pair table derives it from hist)
+  uint32_t* row_cnt;  // [max_rows + 3] (pair table only) events of the row at the last fold, saturated
+  uint32_t* row_aux;  // [max_rows + 3] (pair table only) edge row found by fold_resolve_kernel
+  uint32_t* hist;     // [(max_rows + 3) * ALZ_NB]
 };
 
 // row of `key`, inserting it if absent; >= kLostRow when capacity is exhausted
@@ -194,12 +199,12 @@ __device__ __forceinline__ uint32_t ep_lookup(const EpEntry* __restrict__ tab, u
 // (profiles/r1_v4_ingest_ncu.txt: 890k row allocations per 100M events, 190k of them real).
 // Existing pairs are found without touching the endpoint table. Returns kDropRow for a rejected pair.
 constexpr uint32_t kDropRow = 0xFFFFFFFDu;
-__device__ __forceinline__ uint32_t find_or_insert_pair(const AccTable& t, uint64_t key, bool rev,
+__device__ __forceinline__ uint32_t find_or_insert_pair(const AccTable& t, uint64_t key, uint32_t kind,
                                                         const EpEntry* __restrict__ ep, uint32_t ep_mask) {
-  // the one key that collides with the free marker has fixed rows: max_rows (forward), max_rows + 1 (reversed)
-  if (key == kEmptyKey) return t.max_rows + (rev ? 1u : 0u);
-  DictEnt* const dict = rev ? t.dict_rev : t.dict;
-  const uint32_t mask = rev ? t.dict_rev_mask : t.dict_mask;
+  // the one key that collides with the free marker has a fixed row per kind
+  if (key == kEmptyKey) return t.max_rows + kind;
+  DictEnt* const dict = kind == kPairFwd ? t.dict : kind == kPairRev ? t.dict_rev : t.dict_host;
+  const uint32_t mask = kind == kPairFwd ? t.dict_mask : kind == kPairRev ? t.dict_rev_mask : t.dict_host_mask;
   uint32_t slot = pair_hash(key) & mask;
   bool checked = false;
 #pragma unroll 1
@@ -217,7 +222,7 @@ __device__ __forceinline__ uint32_t find_or_insert_pair(const AccTable& t, uint6
                                      (unsigned long long)key);
       if (old == kEmptyKey) {
         row = atomicAdd(t.n_rows, 1u);
-        if (row >= t.max_rows) row = kLostRow; else { t.row_key[row] = key; t.row_rev[row] = rev ? 1u : 0u; }
+        if (row >= t.max_rows) row = kLostRow; else { t.row_key[row] = key; t.row_kind[row] = (uint8_t)kind; }
         *reinterpret_cast<volatile uint32_t*>(&dict[slot].row) = row;
         return row;
       }
@@ -249,6 +254,16 @@ __device__ __forceinline__ bool resolve_edge(const EpEntry* __restrict__ tab, ui
   return true;
 }
 
+// host-keyed outbound pair (ALZ_PROTO_F_HOSTKEY): the caller has already established that the destination is
+// neither service nor pod, and HTTP rows are never reversed; only the drop rule is left (data.go:829-832, :851-854)
+__device__ __forceinline__ bool resolve_edge_hostkey(const EpEntry* __restrict__ tab, uint32_t mask, uint32_t saddr,
+                                                     uint32_t host_id, uint64_t* edge_key) {
+  uint32_t pod, svc;
+  if ((ep_lookup(tab, mask, saddr, &pod, &svc) & kEpPod) == 0u) return false;
+  *edge_key = make_edge_key(pod, ALZ_NODE_OUTBOUND_HOST, host_id, false);
+  return true;
+}
+
 // 32-byte record, one 256-bit load (LDG.E.256 on sm_100a), streaming: bypass L1
 struct Rec { uint32_t w[8]; };
 __device__ __forceinline__ Rec load_rec(const alz_l7_rec* p) {
@@ -263,7 +278,8 @@ __device__ __forceinline__ Rec load_rec(const alz_l7_rec* p) {
 __device__ __forceinline__ uint32_t rec_saddr(const Rec& r) { return r.w[0]; }
 __device__ __forceinline__ uint32_t rec_daddr(const Rec& r) { return r.w[1]; }
 __device__ __forceinline__ uint32_t rec_status(const Rec& r) { return r.w[3] & 0xFFFFu; }
-__device__ __forceinline__ uint32_t rec_protocol(const Rec& r) { return (r.w[3] >> 16) & 0xFFu; }
+__device__ __forceinline__ uint32_t rec_protocol(const Rec& r) { return (r.w[3] >> 16) & 0x3Fu; }   // without the flag bits
+__device__ __forceinline__ bool rec_hostkey(const Rec& r) { return (r.w[3] & ((uint32_t)ALZ_PROTO_F_HOSTKEY << 16)) != 0u; }
 __device__ __forceinline__ uint32_t rec_mflags(const Rec& r) { return r.w[3] >> 24; }
 __device__ __forceinline__ uint64_t rec_duration(const Rec& r) { return ((uint64_t)r.w[5] << 32) | r.w[4]; }
 

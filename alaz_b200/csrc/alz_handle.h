@@ -79,6 +79,10 @@ struct alz_handle {
   uint64_t lost_reported = 0;             // capacity_events already reported by an earlier flush
 
   uint64_t events_in = 0, pending_since_fold = 0, windows = 0;
+  uint64_t launches = 0;                  // own kernels launched (stats)
+  cudaEvent_t ev_t[3] = {nullptr, nullptr, nullptr};   // flush start / local part done / merge done (timing events)
+  bool ev_t_valid = false;
+  uint64_t collective_bytes_last = 0;
   uint64_t tcp_events_in = 0, tcp_localhost_dropped = 0;
 
   int comm_nranks = 1, comm_rank = 0;

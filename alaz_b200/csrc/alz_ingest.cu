@@ -36,6 +36,23 @@
 
 namespace alz {
 
+// Cycle accounting per section of the main loop, summed over warps (profiling build only: -DALZ_INGEST_PROF,
+// alaz_b200/build.py --prof -> libalazgpu_prof.so; read with alz_debug_ingest_prof). Tells where a warp's time
+// goes in a REAL run — ncu's kernel replay flushes the caches between passes and so shows every dictionary
+// probe as a DRAM miss.
+#ifdef ALZ_INGEST_PROF
+__device__ unsigned long long g_ingest_prof[8];
+#define PROF_DECL unsigned long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pc0 = 0, pc1 = 0; (void)pc0; (void)pc1
+#define PROF_NOW() clock64()
+#define PROF_ADD(i, v) pt[i] += (unsigned long long)(v)
+#define PROF_FLUSH() do { if ((threadIdx.x & 31u) == 0) for (int i_ = 0; i_ < 8; ++i_) atomicAdd(&g_ingest_prof[i_], pt[i_]); } while (0)
+#else
+#define PROF_DECL long long pc0 = 0, pc1 = 0; (void)pc0; (void)pc1
+#define PROF_NOW() 0ll
+#define PROF_ADD(i, v)
+#define PROF_FLUSH()
+#endif
+
 namespace {
 
 constexpr int kLatSub = 4;                 // latency sub-accumulators per row, picked by lane: every event of a pair adds to
@@ -178,7 +195,7 @@ __device__ __forceinline__ bool smem_admit(const Shared& s, uint64_t key, uint32
 }
 
 // one warp's queue of deferred events in shared memory: a ring of 24-byte entries {key u64, dur u64, meta u32}
-// filled by ballot compaction. meta: bits 0..5 latency bucket, bit 8 reversed row, bit 9 counts as 5xx
+// filled by ballot compaction. meta: bits 0..5 latency bucket, bit 8 reversed row, bit 9 counts as 5xx, bit 10 host-keyed
 template <uint32_t kCap>
 struct Queue {
   uint8_t* base;
@@ -219,15 +236,15 @@ __device__ __forceinline__ void slow_batch(Queue<kSlowQ>& q, uint32_t count, con
     uint64_t key, dur;
     uint32_t meta;
     q.get(lane, &key, &dur, &meta);
-    const bool rv = (meta & 0x100u) != 0u;
-    const uint32_t row = find_or_insert_pair(t, key, rv, ep, ep_mask);
+    const uint32_t kind = (meta >> 8) & 1u ? kPairRev : (meta & 0x400u) ? kPairHost : kPairFwd;
+    const uint32_t row = find_or_insert_pair(t, key, kind, ep, ep_mask);
     if (row >= kDropRow) { if (row == kDropRow) *unresolved += 1u; else *lost += 1u; }
     else {
       red_add_u32(&t.hist[(size_t)row * ALZ_NB + (meta & 0x3Fu)], 1u);
       red_add_u64(&t.lat_sum[row], dur);
       if (meta & 0x200u) red_add_u64(&t.err5xx[row], 1ull);
       // a pair the dictionary did not know yet: give it a private row while some are left (first-come)
-      if (!rv && key != kEmptyKey && *reinterpret_cast<volatile uint32_t*>(s.n_rows) < kRows)
+      if (kind == kPairFwd && key != kEmptyKey && *reinterpret_cast<volatile uint32_t*>(s.n_rows) < kRows)
         smem_admit(s, key, table_hash(key), kRows, true);
     }
   }
@@ -247,9 +264,9 @@ __device__ __forceinline__ void cold_issue(const Queue<kColdQ>& q, uint32_t coun
     uint64_t key, dur;
     uint32_t meta;
     q.get(lane, &key, &dur, &meta);
-    const bool rv = (meta & 0x100u) != 0u;
-    const DictEnt* dict = rv ? t.dict_rev : t.dict;
-    const uint32_t mask = rv ? t.dict_rev_mask : t.dict_mask;
+    const bool rv = (meta & 0x100u) != 0u, hk = (meta & 0x400u) != 0u;
+    const DictEnt* dict = rv ? t.dict_rev : hk ? t.dict_host : t.dict;
+    const uint32_t mask = rv ? t.dict_rev_mask : hk ? t.dict_host_mask : t.dict_mask;
     cp_async16(probe_a + lane * 16u, &dict[pair_hash(key) & mask]);
   }
   cp_async_commit();
@@ -259,9 +276,12 @@ __device__ __forceinline__ void cold_issue(const Queue<kColdQ>& q, uint32_t coun
 template <uint32_t kRows, uint32_t kColdQ>
 __device__ __forceinline__ void cold_consume(Queue<kColdQ>& q, uint32_t count, const uint4* probe, Queue<kSlowQ>& slow,
                                              const AccTable& t, const Shared& s, const EpEntry* __restrict__ ep,
-                                             uint32_t ep_mask, uint32_t lane_lt, uint32_t* lost, uint32_t* unresolved) {
+                                             uint32_t ep_mask, uint32_t lane_lt, uint32_t* lost, uint32_t* unresolved,
+                                             unsigned long long* t_wait, unsigned long long* t_slow) {
   const uint32_t lane = threadIdx.x & 31u;
+  const long long w0 = PROF_NOW();
   cp_async_wait_all();
+  *t_wait += (unsigned long long)(PROF_NOW() - w0);
   const bool valid = lane < count;
   uint64_t key = 0, dur = 0;
   uint32_t meta = 0;
@@ -273,10 +293,14 @@ __device__ __forceinline__ void cold_consume(Queue<kColdQ>& q, uint32_t count, c
     red_add_u64(&t.lat_sum[ent.z], dur);
     if (meta & 0x200u) red_add_u64(&t.err5xx[ent.z], 1ull);
   }
-  slow.push(valid && !home, key, dur, meta, lane_lt);
+  slow.push(valid && !home, key, dur, meta & 0x7FFu, lane_lt);
   __syncwarp();
   q.pop(count);
-  if (slow.count >= 32u) slow_batch<kRows>(slow, 32u, t, s, ep, ep_mask, lost, unresolved);
+  if (slow.count >= 32u) {
+    const long long s0 = PROF_NOW();
+    slow_batch<kRows>(slow, 32u, t, s, ep, ep_mask, lost, unresolved);
+    *t_slow += (unsigned long long)(PROF_NOW() - s0);
+  }
 }
 
 // private rows into the global table; a warp per row
@@ -294,7 +318,7 @@ __device__ __forceinline__ void smem_drain(const Shared& s, const AccTable& g, c
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
     if (c == 0u) continue;            // preloaded but never hit in this launch: no global row needed
     uint32_t grow = 0;
-    if (lane == 0) grow = find_or_insert_pair(g, key, false, ep, ep_mask);
+    if (lane == 0) grow = find_or_insert_pair(g, key, kPairFwd, ep, ep_mask);
     grow = __shfl_sync(0xFFFFFFFFu, grow, 0);
     if (grow >= kDropRow) {   // source is not a pod (dropped like the reference does) or capacity
       if (lane == 0) { if (grow == kDropRow) *unresolved += c; else *lost += c; }
@@ -400,9 +424,16 @@ ingest_pairs_v6_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
   uint32_t lost = 0, unresolved = 0;
   uint32_t probing = 0;                // events at the head of the cold queue whose probes are in flight
   uint32_t it = 0, n_hit = 0, n_live = 0, n_cold = 0;
+  PROF_DECL;
+  unsigned long long t_wait = 0, t_slow = 0;
+  const long long p_begin = PROF_NOW();
   for (uint32_t c = c_first; c < n_chunks; c += c_stride, ++it) {
     const uint32_t stage = it & 1u;
+    pc0 = PROF_NOW();
     mbar_wait(bar_a + stage * 8u, (it >> 1) & 1u);
+    pc1 = PROF_NOW();
+    PROF_ADD(1, pc1 - pc0);
+    PROF_ADD(6, 1);
     // records of this chunk into registers (lane l takes records l, l + 32, ...)
     uint32_t w[kU][kRecWords];
     const uint8_t* st = ring + stage * L::kChunkBytes;
@@ -439,12 +470,14 @@ ingest_pairs_v6_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
     for (int u = 0; u < kU; ++u) {
       const bool live = (uint32_t)u * 32u + lane < n_here;
       const uint32_t mw = (kRecWords == 8) ? w[u][3] : w[u][2];   // status | protocol << 16 | method_flags << 24
-      uint32_t p = __byte_perm(mw, 0u, 0x4442u);                  // protocol byte
+      uint32_t p = __byte_perm(mw, 0u, 0x4442u);                  // protocol byte, flag bits still on
       if (kRecWords == 8) dur[u] = ((uint64_t)w[u][5] << 32) | w[u][4];
       else {
         dur[u] = w[u][3];
-        if (p & 0x80u) { dur[u] = live ? __ldg(&dur_ovf[w[u][3]]) : 0ull; p &= 0x7Fu; }
+        if (p & ALZ_REC16_DUR_OVERFLOW) dur[u] = live ? __ldg(&dur_ovf[w[u][3]]) : 0ull;
       }
+      const bool hk = (p & ALZ_PROTO_F_HOSTKEY) != 0u;             // daddr is a Host-header id: own key space, cold tier
+      p &= 0x3Fu;
       const uint32_t cls = shr_clamp(kProtoLut, 3u * p);
       // a row is built unless the class says "payload parser decides" and the parser said no (bit 30 of mw)
       const bool act = live && (cls & 1u) && !((cls & 2u) && (mw & ((uint32_t)ALZ_MF_PAYLOAD_REJECT << 24)));
@@ -452,13 +485,13 @@ ingest_pairs_v6_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
       const bool err = p == ALZ_PROTO_HTTP && ((mw & 0xFFFFu) - 500u) < 100u;
       key[u] = ((uint64_t)w[u][1] << 32) | w[u][0];               // make_pair_key: the record's first two words as they lie
       const uint32_t bucket = latency_bucket_rz(dur[u]);
-      meta[u] = bucket | (rv ? 0x100u : 0u) | (err ? 0x200u : 0u);
+      meta[u] = bucket | (rv ? 0x100u : 0u) | (err ? 0x200u : 0u) | (hk ? 0x400u : 0u);
 
       // direct-mapped probe, verified against the row's key
       const uint32_t h = table_hash(key[u]);
       const uint32_t x = s.tab[h >> kTabShift] ^ tab_fp(h);
       const uint32_t r = min(x, kRows);
-      const bool hit = act && !rv && x < kRows && s.rowkey[r] == key[u];
+      const bool hit = act && !rv && !hk && x < kRows && s.rowkey[r] == key[u];
       // the row's reductions, each under the hit predicate
       const uint32_t row_a = rows_a + r * (kRowWords * 4u);
       const uint32_t lat_a = row_a + (ALZ_NB + 2u * (lane & (kLatSub - 1u))) * 4u;
@@ -474,22 +507,30 @@ ingest_pairs_v6_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
 #pragma unroll
     for (int u = 0; u < kU; ++u) n_cold += cold.push(coldf[u], key[u], dur[u], meta[u], lane_lt);
     __syncwarp();
+    pc0 = PROF_NOW();
+    PROF_ADD(5, pc0 - pc1);
     // a batch is consumed when the next one is ready to be requested
     while (cold.count - probing >= 32u) {
       if (probing) {
-        cold_consume<kRows>(cold, probing, probe, slow, pairs, s, ep, ep_mask, lane_lt, &lost, &unresolved);
+        cold_consume<kRows>(cold, probing, probe, slow, pairs, s, ep, ep_mask, lane_lt, &lost, &unresolved, &t_wait, &t_slow);
         probing = 0;
+        PROF_ADD(7, 1);
       }
       cold_issue(cold, 32u, pairs, probe_a);
       probing = 32u;
     }
+    PROF_ADD(3, PROF_NOW() - pc0);
   }
-  if (probing) cold_consume<kRows>(cold, probing, probe, slow, pairs, s, ep, ep_mask, lane_lt, &lost, &unresolved);
+  if (probing) cold_consume<kRows>(cold, probing, probe, slow, pairs, s, ep, ep_mask, lane_lt, &lost, &unresolved, &t_wait, &t_slow);
   if (cold.count) {
     const uint32_t rest = cold.count;
     cold_issue(cold, rest, pairs, probe_a);
-    cold_consume<kRows>(cold, rest, probe, slow, pairs, s, ep, ep_mask, lane_lt, &lost, &unresolved);
+    cold_consume<kRows>(cold, rest, probe, slow, pairs, s, ep, ep_mask, lane_lt, &lost, &unresolved, &t_wait, &t_slow);
   }
+  PROF_ADD(0, PROF_NOW() - p_begin);
+  PROF_ADD(2, t_wait);
+  PROF_ADD(4, t_slow);
+  PROF_FLUSH();
   while (slow.count) slow_batch<kRows>(slow, min(slow.count, 32u), pairs, s, ep, ep_mask, &lost, &unresolved);
   __syncthreads();
   smem_drain<kRows>(s, pairs, ep, ep_mask, &lost, &unresolved);
@@ -529,7 +570,7 @@ __global__ void __launch_bounds__(256) hot_emit_kernel(AccTable pairs, HotState*
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t row = blockIdx.x * blockDim.x + threadIdx.x; row < n_rows; row += stride) {
     const uint32_t c = pairs.row_cnt[row];
-    if (c == 0u || pairs.row_rev[row]) continue;     // reversed rows never enter the per-CTA table
+    if (c == 0u || pairs.row_kind[row] != kPairFwd) continue;   // only forward pairs enter the per-CTA table
     const uint32_t b = count_bin(c);
     if (b >= thr_a) {
       const uint32_t p = atomicAdd(&hot->n_a, 1u);
@@ -582,3 +623,17 @@ void launch_hot_select(const AccTable& pairs, HotState* hot, int sms, cudaStream
 }
 
 }  // namespace alz
+
+// profiling build only: cycles per section of the ingest main loop since the last call (see g_ingest_prof)
+extern "C" int alz_debug_ingest_prof(unsigned long long* out8) {
+#ifdef ALZ_INGEST_PROF
+  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (cudaDeviceSynchronize() != cudaSuccess) return ALZ_E_CUDA;
+  if (cudaMemcpyFromSymbol(out8, alz::g_ingest_prof, sizeof(z)) != cudaSuccess) return ALZ_E_CUDA;
+  if (cudaMemcpyToSymbol(alz::g_ingest_prof, z, sizeof(z)) != cudaSuccess) return ALZ_E_CUDA;
+  return ALZ_OK;
+#else
+  (void)out8;
+  return ALZ_E_UNSUPPORTED;
+#endif
+}

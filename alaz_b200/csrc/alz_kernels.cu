@@ -28,12 +28,14 @@ struct Ev {
   bool act;       // the reference would hand a row to PersistRequest (before resolve)
   bool rev;       // ReverseDirection applies
   bool err;       // counts as 5xx
+  bool hostkey;   // daddr is a Host-header id (ALZ_PROTO_F_HOSTKEY)
 };
 __device__ __forceinline__ Ev decode(const Rec& r, bool live) {
   Ev e;
   const uint32_t proto = rec_protocol(r), mf = rec_mflags(r);
   e.act = live && emits_request_row(proto, mf);
   e.rev = is_reversed(proto, mf);
+  e.hostkey = rec_hostkey(r);
   e.key = make_pair_key(rec_saddr(r), rec_daddr(r));
   e.dur = rec_duration(r);
   e.bucket = latency_bucket(e.dur);
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(256) ingest_pairs_kernel(const alz_l7_rec* __r
       const Ev e = decode(r[u], live[u]);
       not_request += (live[u] && !e.act) ? 1u : 0u;
       uint32_t row = kLostRow;
-      if (e.act) row = find_or_insert_pair(pairs, e.key, e.rev, ep, ep_mask);
+      if (e.act) row = find_or_insert_pair(pairs, e.key, e.hostkey ? kPairHost : e.rev ? kPairRev : kPairFwd, ep, ep_mask);
       __syncwarp();
       if (e.act) {
         if (row == kDropRow) ++unresolved;
@@ -116,7 +118,8 @@ __global__ void __launch_bounds__(256) ingest_eager_kernel(const alz_l7_rec* __r
     not_request += (live && !e.act) ? 1u : 0u;
     uint64_t ekey = 0;
     bool ok = false;
-    if (e.act) ok = resolve_edge(ep, ep_mask, pair_saddr(e.key), pair_daddr(e.key), e.rev, &ekey);
+    if (e.act) ok = e.hostkey ? resolve_edge_hostkey(ep, ep_mask, pair_saddr(e.key), pair_daddr(e.key), &ekey)
+                              : resolve_edge(ep, ep_mask, pair_saddr(e.key), pair_daddr(e.key), e.rev, &ekey);
     __syncwarp();
     unresolved += (e.act && !ok) ? 1u : 0u;
     uint32_t row = kLostRow;
@@ -151,12 +154,12 @@ __global__ void __launch_bounds__(256) fold_resolve_kernel(AccTable pairs, const
   }
   const uint32_t n_rows = min(*pairs.n_rows, pairs.max_rows);
   const uint32_t stride = gridDim.x * blockDim.x;
-  // rows [0, n_rows) plus the two sentinel rows (index n_rows + k stands for row max_rows + k)
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rows + 2u; i += stride) {
+  // rows [0, n_rows) plus the sentinel rows (index n_rows + kind stands for row max_rows + kind)
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rows + kPairKinds; i += stride) {
     const bool sentinel = i >= n_rows;
     const uint32_t row = sentinel ? pairs.max_rows + (i - n_rows) : i;
     const uint64_t key = sentinel ? kEmptyKey : pairs.row_key[row];
-    const bool rev = sentinel ? (i - n_rows) != 0u : pairs.row_rev[row] != 0u;
+    const uint32_t kind = sentinel ? (i - n_rows) : pairs.row_kind[row];
     if (sentinel) {                                            // the sentinel rows exist even when unused
       uint32_t any = 0;
       for (int b = 0; b < ALZ_NB; ++b) any |= pairs.hist[(size_t)row * ALZ_NB + b];
@@ -164,7 +167,9 @@ __global__ void __launch_bounds__(256) fold_resolve_kernel(AccTable pairs, const
     }
     uint64_t ekey = 0;
     uint32_t erow = kDropRow;                                  // source is not a pod: data.go:829-832
-    if (resolve_edge(ep, ep_mask, pair_saddr(key), pair_daddr(key), rev, &ekey)) erow = find_or_insert(edges, ekey);
+    const bool ok = kind == kPairHost ? resolve_edge_hostkey(ep, ep_mask, pair_saddr(key), pair_daddr(key), &ekey)
+                                      : resolve_edge(ep, ep_mask, pair_saddr(key), pair_daddr(key), kind == kPairRev, &ekey);
+    if (ok) erow = find_or_insert(edges, ekey);
     pairs.row_aux[row] = erow;
   }
 }
@@ -177,11 +182,11 @@ __global__ void __launch_bounds__(256) fold_pairs_kernel(AccTable pairs, AccTabl
   const uint32_t lane = threadIdx.x & 31u, sl = lane & 7u;
   const uint32_t groups_per_grid = (gridDim.x * blockDim.x) >> 3;
   const uint32_t n_rows = min(*pairs.n_rows, pairs.max_rows);
-  const uint32_t n_iter = (n_rows + 2u + groups_per_grid - 1u) / groups_per_grid;   // same trip count for every lane
+  const uint32_t n_iter = (n_rows + kPairKinds + groups_per_grid - 1u) / groups_per_grid;   // same trip count for every lane
   uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-  // rows [0, n_rows) plus the two sentinel rows (index n_rows + k stands for row max_rows + k)
+  // rows [0, n_rows) plus the sentinel rows (index n_rows + kind stands for row max_rows + kind)
   for (uint32_t it = 0; it < n_iter; ++it, i += groups_per_grid) {
-    const bool valid = i < n_rows + 2u;
+    const bool valid = i < n_rows + kPairKinds;
     const uint32_t row = !valid ? 0u : (i >= n_rows) ? pairs.max_rows + (i - n_rows) : i;
     uint4* cells = reinterpret_cast<uint4*>(pairs.hist + (size_t)row * ALZ_NB + sl * 8u);
     uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
@@ -194,7 +199,7 @@ __global__ void __launch_bounds__(256) fold_pairs_kernel(AccTable pairs, AccTabl
     if (sl == 0 && row < pairs.max_rows && pairs.row_cnt != nullptr) {    // feedback for the next ingest
       const uint32_t c32 = cnt > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)cnt;
       pairs.row_cnt[row] = c32;
-      if (hot_bins != nullptr && !pairs.row_rev[row]) atomicAdd(&hot_bins[count_bin(c32)], 1u);
+      if (hot_bins != nullptr && pairs.row_kind[row] == kPairFwd) atomicAdd(&hot_bins[count_bin(c32)], 1u);
     }
     const uint32_t erow = pairs.row_aux[row];
     if (erow < kDropRow) {

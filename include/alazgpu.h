@@ -60,8 +60,18 @@ enum { ALZ_REDIS_COMMAND = 1, ALZ_REDIS_PUSHED_EVENT = 2, ALZ_REDIS_PING = 3 };
                                        1495-1497), Mongo parse failure (:1252-1255) */
 #define ALZ_MF_TLS 0x80u
 
+/* protocol byte of alz_l7_rec: bit 6 says "daddr holds a host id, not an address". The caller sets it for an
+ * HTTP event whose payload carried a Host header AND whose daddr is neither a service nor a pod in the
+ * tables as committed so far — the case in which setFromToV2 keys the destination by the header
+ * (aggregator/data.go:851-854). The caller owns both the payload parser and the interner of header strings
+ * (strings never cross this ABI), and it owns the tables it upserts here, so it can decide this exactly
+ * as the reference does; the device keeps such events in their own key space. */
+#define ALZ_PROTO_F_HOSTKEY 0x40u
+
 /* node kinds of an edge end (aggregator/data.go POD/SVC/OUTBOUND) */
-enum { ALZ_NODE_POD = 0, ALZ_NODE_SVC = 1, ALZ_NODE_OUTBOUND = 2 };
+enum { ALZ_NODE_POD = 0, ALZ_NODE_SVC = 1, ALZ_NODE_OUTBOUND = 2,
+       ALZ_NODE_OUTBOUND_HOST = 3 /* outbound destination keyed by the HTTP Host header (aggregator/data.go:851-854);
+                                     value = the caller's dense id of the header string */ };
 /* tables of the join's build side (aggregator/cluster.go:15-16) */
 enum { ALZ_TABLE_POD = 0, ALZ_TABLE_SVC = 1 };
 
@@ -179,7 +189,11 @@ typedef struct alz_stats {
   uint64_t tcp_localhost_dropped; /* aggregator/data.go:409, 455 */
   uint64_t capacity_events;  /* events lost to an exhausted pair/edge table (cumulative) */
   uint64_t windows;          /* windows flushed */
-  uint64_t _reserved[6];
+  uint64_t kernel_launches;  /* kernels of this library launched so far (CUB passes, memsets, copies not counted) */
+  uint64_t collective_bytes_last; /* bytes this rank contributed to / received from the last window's collective */
+  uint64_t flush_local_us_last;   /* device time of the last flush up to the cross-rank merge */
+  uint64_t merge_us_last;         /* device time of the last cross-rank merge (0 on one rank) */
+  uint64_t _reserved[2];
 } alz_stats;
 
 typedef struct alz_handle alz_handle;
@@ -202,6 +216,8 @@ int alz_sync(alz_handle* h);
  * each event is resolved by the tables in force when it was submitted. */
 int alz_table_upsert(alz_handle* h, int table, uint32_t ipv4, uint32_t id);
 int alz_table_erase(alz_handle* h, int table, uint32_t ipv4);
+/* n upserts in one call (informer resync / initial list: k8s/informer.go hands the whole cluster at start) */
+int alz_table_upsert_batch(alz_handle* h, int table, const uint32_t* ipv4, const uint32_t* ids, size_t n);
 int alz_table_commit(alz_handle* h);
 
 /* ---- event ingest: replaces processL7 .. PersistRequest --------------------

@@ -91,6 +91,8 @@ typedef struct acc {
 } acc;
 
 struct orc {
+  const char* const* host_names; /* id -> Host header text, for orc_edges (set by orc_process_l7_hosts) */
+  size_t n_host_names;
   smap pod_ip_to_uid; /* ClusterInfo.PodIPToPodUid, cluster.go:15 */
   smap svc_ip_to_uid; /* ClusterInfo.ServiceIPToServiceUid, cluster.go:16 */
   smap groups[NSHARD]; /* "ftype|fuid|ttype|tuid" -> acc*, sharded by key hash so that the
@@ -166,7 +168,7 @@ typedef struct request {
   uint64_t latency;
   char from_ip[16], to_ip[16];
   const char* from_type; const char* to_type;
-  char from_uid[24], to_uid[24];
+  char from_uid[72], to_uid[72]; /* UID, or a host name / dotted quad for outbound */
   uint16_t from_port, to_port;
   const char* protocol;
   uint32_t status_code;
@@ -176,17 +178,17 @@ typedef struct request {
 
 /* Request.ReverseDirection, datastore/dto.go:246-251 */
 static void reverse_direction(request* r) {
-  char t[24];
+  char t[72];
   memcpy(t, r->from_ip, 16); memcpy(r->from_ip, r->to_ip, 16); memcpy(r->to_ip, t, 16);
   uint16_t p = r->from_port; r->from_port = r->to_port; r->to_port = p;
-  memcpy(t, r->from_uid, 24); memcpy(r->from_uid, r->to_uid, 24); memcpy(r->to_uid, t, 24);
+  memcpy(t, r->from_uid, 72); memcpy(r->from_uid, r->to_uid, 72); memcpy(r->to_uid, t, 72);
   const char* ty = r->from_type; r->from_type = r->to_type; r->to_type = ty;
 }
 
 /* setFromToV2, aggregator/data.go:827-870. hostHeader is always "" for compact
  * records (no payload) and reverse DNS (getHostnameFromIP, :1386-1405) is
  * treated as failing, so the outbound key is the raw daddr string (:862). */
-static int set_from_to_v2(const orc* o, request* r) {
+static int set_from_to_v2(const orc* o, request* r, const char* host_header) {
   smap_ent* pod = smap_find(&o->pod_ip_to_uid, r->from_ip); /* getPodWithIP :812-817 */
   if (!pod) return -1;                                        /* :829-832 */
   snprintf(r->from_uid, sizeof r->from_uid, "%s", (const char*)pod->val);
@@ -201,7 +203,8 @@ static int set_from_to_v2(const orc* o, request* r) {
       snprintf(r->to_uid, sizeof r->to_uid, "%s", (const char*)dpod->val);
       r->to_type = POD;
     } else {
-      snprintf(r->to_uid, sizeof r->to_uid, "%s", r->to_ip); /* :862 */
+      if (host_header && host_header[0]) snprintf(r->to_uid, sizeof r->to_uid, "%s", host_header); /* :851-854 */
+      else snprintf(r->to_uid, sizeof r->to_uid, "%s", r->to_ip); /* :862 (reverse DNS treated as failing) */
       r->to_type = OUTBOUND;
     }
   }
@@ -221,7 +224,7 @@ uint32_t orc_bucket(uint64_t d) {
 
 /* PersistRequest stand-in: fold the emitted row into its (From,To) group */
 static void persist_request(smap* shards, const request* r, alz_stats* st) {
-  char key[96];
+  char key[192];
   snprintf(key, sizeof key, "%s|%s|%s|%s", r->from_type, r->from_uid, r->to_type, r->to_uid);
   smap* groups = &shards[str_hash(key) % NSHARD];
   smap_ent* g = smap_find(groups, key);
@@ -238,7 +241,7 @@ static void persist_request(smap* shards, const request* r, alz_stats* st) {
 }
 
 /* processL7 (aggregator/data.go:1364-1383) for one compact record */
-static void process_l7(const orc* o, const alz_l7_rec* d, smap* groups, alz_stats* st) {
+static void process_l7(const orc* o, const alz_l7_rec* d, smap* groups, alz_stats* st, const char* host_header) {
   st->events_in++;
   const char* protocol = protocol_string(d->protocol);
   const uint8_t m = d->method_flags & ALZ_MF_METHOD_MASK;
@@ -269,7 +272,8 @@ static void process_l7(const orc* o, const alz_l7_rec* d, smap* groups, alz_stat
   r->from_port = d->sport; r->to_port = d->dport;
   r->protocol = protocol; r->tls = tls; r->status_code = d->status; r->method = method;
 
-  if (set_from_to_v2(o, r) != 0) { st->src_unresolved++; free(r); return; }
+  /* only processHttpEvent parses a Host header out of the payload (:1213); the other handlers pass "" */
+  if (set_from_to_v2(o, r, is_http ? host_header : NULL) != 0) { st->src_unresolved++; free(r); return; }
 
   /* :1110-1112 AMQP DELIVER, :1151-1153 REDIS PUSHED_EVENT */
   if (is_amqp && !strcmp(method, "DELIVER")) reverse_direction(r);
@@ -292,7 +296,7 @@ typedef struct worker {
 } worker;
 static void* worker_main(void* p) {
   worker* w = (worker*)p;
-  for (size_t i = 0; i < w->n; i++) process_l7(w->o, &w->recs[i], w->groups, &w->st);
+  for (size_t i = 0; i < w->n; i++) process_l7(w->o, &w->recs[i], w->groups, &w->st, NULL);
   return NULL;
 }
 static void merge_acc(acc* dst, const acc* src);
@@ -321,7 +325,7 @@ static void merge_acc(acc* dst, const acc* src) {
 
 void orc_process_l7(orc* o, const alz_l7_rec* recs, size_t n, int nthreads) {
   if (nthreads <= 1) {
-    for (size_t i = 0; i < n; i++) process_l7(o, &recs[i], o->groups, &o->st);
+    for (size_t i = 0; i < n; i++) process_l7(o, &recs[i], o->groups, &o->st, NULL);
     return;
   }
   worker* w = (worker*)calloc((size_t)nthreads, sizeof(worker));
@@ -344,13 +348,61 @@ void orc_process_l7(orc* o, const alz_l7_rec* recs, size_t n, int nthreads) {
   free(w); free(th);
 }
 
-static int parse_node(const char* type, const char* uid, uint8_t* t, uint32_t* v) {
+void orc_process_l7_hosts(orc* o, const alz_l7_rec* recs, size_t n, const uint32_t* host_idx,
+                          const char* const* names, size_t n_names) {
+  o->host_names = names; o->n_host_names = n_names;
+  for (size_t i = 0; i < n; i++) {
+    const char* hh = (host_idx && host_idx[i]) ? names[host_idx[i] - 1] : NULL;
+    process_l7(o, &recs[i], o->groups, &o->st, hh);
+  }
+}
+
+/* parseHttpPayload, aggregator/data.go:508-531, the hostHeader part: lines = Split(request, "\n"); for the
+ * lines after the first, the first one that HasPrefix "Host:" AND splits (on single spaces) into >= 2 parts
+ * gives parts[1] without a trailing "\r". A "Host:" line with fewer parts is skipped and the scan goes on. */
+size_t orc_parse_http_host(const char* payload, size_t n, char* out, size_t cap) {
+  if (cap) out[0] = 0;
+  size_t i = 0;
+  while (i < n && payload[i] != '\n') i++; /* lines[0] */
+  while (i < n) {
+    i++; /* past the '\n' */
+    size_t b = i;
+    while (i < n && payload[i] != '\n') i++;
+    const char* line = payload + b; size_t len = i - b;
+    if (len >= 5 && !memcmp(line, "Host:", 5)) {
+      /* strings.Split(line, " "): parts[0] ends at the first space, parts[1] at the second (or the end) */
+      size_t sp = 0;
+      while (sp < len && line[sp] != ' ') sp++;
+      if (sp < len) { /* at least two parts */
+        size_t q = sp + 1, e = q;
+        while (e < len && line[e] != ' ') e++;
+        size_t hl = e - q;
+        if (hl > 0 && line[q + hl - 1] == '\r') hl--; /* TrimSuffix(hostHeader, "\r") */
+        if (hl >= cap) hl = cap ? cap - 1 : 0;
+        if (cap) { memcpy(out, line + q, hl); out[hl] = 0; }
+        return hl;
+      }
+    }
+  }
+  return 0;
+}
+
+uint64_t orc_epoch(uint64_t first_kernel_ns, uint64_t first_user_ns, uint64_t window_ns, uint64_t write_time_ns) {
+  const uint64_t user = first_user_ns - (first_kernel_ns - write_time_ns); /* data.go:1740-1743, uint64 arithmetic */
+  return window_ns ? user / window_ns : 0;
+}
+
+static int parse_node(const orc* o, const char* type, const char* uid, uint8_t* t, uint32_t* v) {
   if (!strcmp(type, "pod")) { *t = ALZ_NODE_POD; *v = (uint32_t)strtoul(uid + 4, NULL, 10); return 0; }
   if (!strcmp(type, "service")) { *t = ALZ_NODE_SVC; *v = (uint32_t)strtoul(uid + 4, NULL, 10); return 0; }
-  unsigned a, b, c, d;
-  if (sscanf(uid, "%u.%u.%u.%u", &a, &b, &c, &d) != 4) return -1;
-  *t = ALZ_NODE_OUTBOUND; *v = (a << 24) | (b << 16) | (c << 8) | d;
-  return 0;
+  unsigned a, b, c, d; char tail;
+  if (sscanf(uid, "%u.%u.%u.%u%c", &a, &b, &c, &d, &tail) == 4 && a < 256 && b < 256 && c < 256 && d < 256) {
+    *t = ALZ_NODE_OUTBOUND; *v = (a << 24) | (b << 16) | (c << 8) | d;
+    return 0;
+  }
+  for (size_t i = 0; i < o->n_host_names; i++)
+    if (!strcmp(o->host_names[i], uid)) { *t = ALZ_NODE_OUTBOUND_HOST; *v = (uint32_t)i; return 0; }
+  return -1;
 }
 static int edge_cmp(const void* pa, const void* pb) {
   const alz_edge_out* a = (const alz_edge_out*)pa; const alz_edge_out* b = (const alz_edge_out*)pb;
@@ -367,12 +419,12 @@ size_t orc_edges(orc* o, alz_edge_out* out, size_t cap) {
     smap_ent* e = &o->groups[sh].e[i];
     if (!e->key || e->key == TOMB) continue;
     if (n < cap) {
-      char k[96]; snprintf(k, sizeof k, "%s", e->key);
+      char k[192]; snprintf(k, sizeof k, "%s", e->key);
       char* ft = strtok(k, "|"); char* fu = strtok(NULL, "|");
       char* tt = strtok(NULL, "|"); char* tu = strtok(NULL, "|");
       alz_edge_out* r = &out[n]; memset(r, 0, sizeof *r);
-      parse_node(ft, fu, &r->from_type, &r->from);
-      parse_node(tt, tu, &r->to_type, &r->to);
+      parse_node(o, ft, fu, &r->from_type, &r->from);
+      parse_node(o, tt, tu, &r->to_type, &r->to);
       const acc* a = (const acc*)e->val;
       r->count = a->count; r->err5xx = a->err5xx; r->lat_sum_ns = a->lat_sum;
       memcpy(r->hist, a->hist, sizeof r->hist);

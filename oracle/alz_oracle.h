@@ -39,6 +39,21 @@ void orc_table_erase(orc* o, int table, uint32_t ipv4);
  * groups merged at the end. */
 void orc_process_l7(orc* o, const alz_l7_rec* recs, size_t n, int nthreads);
 
+/* Same with the HTTP Host header of each event: host_idx[i] = 0 for "no Host header",
+ * else 1 + index into names[]. An outbound destination is then keyed by the header instead of the raw
+ * daddr (setFromToV2, aggregator/data.go:851-854). Edges to such a node come out with
+ * to_type = ALZ_NODE_OUTBOUND_HOST and to = the index into names[] — unless the header text is itself a
+ * dotted quad, which the reference cannot tell from a raw-daddr key (same ToUID string): those come out
+ * as ALZ_NODE_OUTBOUND with that address. */
+void orc_process_l7_hosts(orc* o, const alz_l7_rec* recs, size_t n, const uint32_t* host_idx,
+                          const char* const* names, size_t n_names);
+/* parseHttpPayload's hostHeader (aggregator/data.go:508-531) on a payload of n bytes; writes a
+ * NUL-terminated string into out (cap bytes), "" when the reference finds none. Returns its length. */
+size_t orc_parse_http_host(const char* payload, size_t n, char* out, size_t cap);
+/* convertKernelTimeToUserspaceTime (aggregator/data.go:1740-1743) followed by the window key of
+ * docs/SPEC.md §8: epoch = userspace_ns / window_ns */
+uint64_t orc_epoch(uint64_t first_kernel_ns, uint64_t first_user_ns, uint64_t window_ns, uint64_t write_time_ns);
+
 /* live edges sorted by (from_type,from,to_type,to); returns count (<= cap
  * written). */
 size_t orc_edges(orc* o, alz_edge_out* out, size_t cap);
