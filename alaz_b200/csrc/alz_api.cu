@@ -83,6 +83,7 @@ static int alloc_table(alz_handle* h, AccTable* t, uint32_t max_rows, uint32_t* 
     CK(cudaMemsetAsync(t->row_kind + max_rows + kPairRev, (int)kPairRev, 1, h->stream));   // sentinel rows of the free-marker key
     CK(cudaMemsetAsync(t->row_kind + max_rows + kPairHost, (int)kPairHost, 1, h->stream));
     CK(cudaMalloc(&t->row_cnt, rows * 4)); CK(cudaMemsetAsync(t->row_cnt, 0, rows * 4, h->stream));
+    CK(cudaMalloc(&t->row_base, rows)); CK(cudaMemsetAsync(t->row_base, 0, rows, h->stream));
     CK(cudaMalloc(&t->row_aux, rows * 4));
   }
   CK(cudaMalloc(&t->hist, rows * ALZ_NB * 4));
@@ -94,7 +95,7 @@ static int alloc_table(alz_handle* h, AccTable* t, uint32_t max_rows, uint32_t* 
 }
 static void free_table(AccTable* t) {
   cudaFree(t->dict); cudaFree(t->dict_rev); cudaFree(t->dict_host); cudaFree(t->row_key); cudaFree(t->row_kind); cudaFree(t->lat_sum);
-  cudaFree(t->err5xx); cudaFree(t->count); cudaFree(t->row_cnt); cudaFree(t->row_aux); cudaFree(t->hist);
+  cudaFree(t->err5xx); cudaFree(t->count); cudaFree(t->row_cnt); cudaFree(t->row_base); cudaFree(t->row_aux); cudaFree(t->hist);
   memset(t, 0, sizeof(*t));
 }
 // all keys out of the dictionaries, row allocator back to zero (rows were zeroed by fold / gather)
@@ -468,14 +469,14 @@ int alz_internal_fold(alz_handle* h) { return fold_locked(h); }
 static int ingest_device(alz_handle* h, const void* d, uint64_t n, bool rec16, const uint64_t* d_ovf) {
   if (rec16) {
     if (h->cfg.flags & (ALZ_CFG_EAGER_JOIN | ALZ_CFG_NO_SMEM_CACHE)) return ALZ_E_UNSUPPORTED;
-    launch_ingest_pairs_v6_rec16((const alz_l7_rec16*)d, n, d_ovf, h->pairs, h->d_ctr, h->d_hot, h->d_ep, h->ep_cap - 1,
+    launch_ingest_pairs_rec16((const alz_l7_rec16*)d, n, d_ovf, h->pairs, h->d_ctr, h->d_hot, h->d_ep, h->ep_cap - 1,
                                  h->sms, h->stream);
   } else if (h->cfg.flags & ALZ_CFG_EAGER_JOIN) {
     launch_ingest_eager((const alz_l7_rec*)d, n, h->d_ep, h->ep_cap - 1, h->edges, h->d_ctr, h->sms, h->stream);
   } else if (h->cfg.flags & ALZ_CFG_NO_SMEM_CACHE) {
     launch_ingest_pairs_v1((const alz_l7_rec*)d, n, h->pairs, h->d_ctr, h->d_ep, h->ep_cap - 1, h->sms, h->stream);
   } else {
-    launch_ingest_pairs_v6((const alz_l7_rec*)d, n, h->pairs, h->d_ctr, h->d_hot, h->d_ep, h->ep_cap - 1, h->sms,
+    launch_ingest_pairs((const alz_l7_rec*)d, n, h->pairs, h->d_ctr, h->d_hot, h->d_ep, h->ep_cap - 1, h->sms,
                            h->stream);
   }
   CK(cudaGetLastError());

@@ -128,7 +128,7 @@ constexpr uint32_t kLostRow = 0xFFFFFFFEu;  // dictionary or row pool exhausted
 constexpr uint32_t kPairFwd = 0u, kPairRev = 1u, kPairHost = 2u, kPairKinds = 3u;
 
 struct AccTable {
-  DictEnt* dict;      // [dict_mask + 1]
+  DictEnt* dict;      // [dict_mask + 1]   (= dicts[kPairFwd])
   uint32_t dict_mask;
   // pair table only: further dictionaries for the socket pairs of reversed rows (kind 1: AMQP DELIVER, REDIS
   // PUSHED_EVENT) and for host-keyed outbound events (kind 2: the key's high word is a Host-header id, not a
@@ -137,6 +137,12 @@ struct AccTable {
   uint32_t dict_rev_mask;
   DictEnt* dict_host;
   uint32_t dict_host_mask;
+  __device__ __forceinline__ DictEnt* dict_of(uint32_t kind) const {
+    return kind == kPairFwd ? dict : kind == kPairRev ? dict_rev : dict_host;
+  }
+  __device__ __forceinline__ uint32_t mask_of(uint32_t kind) const {
+    return kind == kPairFwd ? dict_mask : kind == kPairRev ? dict_rev_mask : dict_host_mask;
+  }
   uint32_t max_rows;  // rows [0, max_rows) are allocatable; rows max_rows + kind are the sentinel rows of the key that
                       // equals the free marker (one per kind); every per-row array has max_rows + kPairKinds entries
   uint32_t* n_rows;   // device counter of allocated rows
@@ -146,6 +152,8 @@ struct AccTable {
   uint64_t* err5xx;   // [max_rows + 3]
   uint64_t* count;    // [max_rows + 3] (edge table only; the pair table derives it from hist)
   uint32_t* row_cnt;  // [max_rows + 3] (pair table only) events of the row at the last fold, saturated
+  uint8_t* row_base;  // [max_rows + 3] (pair table only) first bucket / 4 of the 16-bucket window that held most of
+                      // the row's events at the last fold (the per-CTA table keeps only such a window per pair)
   uint32_t* row_aux;  // [max_rows + 3] (pair table only) edge row found by fold_resolve_kernel
   uint32_t* hist;     // [(max_rows + 3) * ALZ_NB]
 };
@@ -203,8 +211,8 @@ __device__ __forceinline__ uint32_t find_or_insert_pair(const AccTable& t, uint6
                                                         const EpEntry* __restrict__ ep, uint32_t ep_mask) {
   // the one key that collides with the free marker has a fixed row per kind
   if (key == kEmptyKey) return t.max_rows + kind;
-  DictEnt* const dict = kind == kPairFwd ? t.dict : kind == kPairRev ? t.dict_rev : t.dict_host;
-  const uint32_t mask = kind == kPairFwd ? t.dict_mask : kind == kPairRev ? t.dict_rev_mask : t.dict_host_mask;
+  DictEnt* const dict = t.dict_of(kind);
+  const uint32_t mask = t.mask_of(kind);
   uint32_t slot = pair_hash(key) & mask;
   bool checked = false;
 #pragma unroll 1
@@ -284,12 +292,13 @@ __device__ __forceinline__ uint32_t rec_mflags(const Rec& r) { return r.w[3] >> 
 __device__ __forceinline__ uint64_t rec_duration(const Rec& r) { return ((uint64_t)r.w[5] << 32) | r.w[4]; }
 
 // ---- hot-pair feedback (alz_ingest.cu): which socket pairs took the most events last fold ----
-constexpr int kHotMax = 1024;   // capacity of the list; the ingest kernel preloads as many as its table takes
+constexpr int kHotMax = 4096;   // capacity of the list; the ingest kernel preloads as many as its table takes
 struct HotState {
   uint32_t bins[128];          // quarter-octave histogram of per-pair event counts (forward pairs)
   uint32_t thr_a, thr_b;       // lowest bin of tier A (hottest, listed first) / of tier B
   uint32_t n_a, n_b;           // tier A occupies keys[0, n_a), tier B keys[kHotA, kHotA + n_b)
   uint64_t keys[kHotMax];
+  uint8_t base[kHotMax];       // the pair's histogram window (first bucket / 4), see AccTable::row_base
 };
 constexpr int kHotA = 64;
 // monotone bin of a count >= 1: 4 bins per octave

@@ -195,6 +195,20 @@ __global__ void __launch_bounds__(256) fold_pairs_kernel(AccTable pairs, AccTabl
     cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 1);
     cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 2);
     cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 4);
+    if (pairs.row_base != nullptr) {   // every lane of the warp takes part in the shuffles (uniform branch)
+      // the 16-bucket window (aligned to 4 buckets) that holds most of the row's events: group sums of 4 cells,
+      // two candidates per lane, arg-max over the row's eight lanes
+      const uint64_t g0 = (uint64_t)a.x + a.y + a.z + a.w, g1 = (uint64_t)b.x + b.y + b.z + b.w;   // groups 2sl, 2sl+1
+      const uint32_t seg = lane & ~7u;
+      const uint64_t n0 = __shfl_sync(0xFFFFFFFFu, g0, seg | ((sl + 1u) & 7u)), n1 = __shfl_sync(0xFFFFFFFFu, g1, seg | ((sl + 1u) & 7u));
+      const uint64_t m0 = __shfl_sync(0xFFFFFFFFu, g0, seg | ((sl + 2u) & 7u));
+      // candidate j covers groups j..j+3 (j <= 12); lanes past the end contribute nothing
+      uint64_t c0 = sl <= 6u ? g0 + g1 + n0 + n1 : 0ull;                    // j = 2 sl       (sl = 6 -> j = 12)
+      uint64_t c1 = sl <= 5u ? g1 + n0 + n1 + m0 : 0ull;                    // j = 2 sl + 1   (sl = 5 -> j = 11)
+      uint64_t best = c0 >= c1 ? (c0 << 4) | (2u * sl) : (c1 << 4) | (2u * sl + 1u);   // counts < 2^37: room for 4 index bits
+      for (int o = 1; o < 8; o <<= 1) { const uint64_t x = __shfl_xor_sync(0xFFFFFFFFu, best, o); best = x > best ? x : best; }
+      if (sl == 0 && valid && row < pairs.max_rows) pairs.row_base[row] = (uint8_t)(best & 15u);
+    }
     if (!valid || cnt == 0) continue;  // unused sentinel row (allocated rows always hold >= 1 event)
     if (sl == 0 && row < pairs.max_rows && pairs.row_cnt != nullptr) {    // feedback for the next ingest
       const uint32_t c32 = cnt > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)cnt;

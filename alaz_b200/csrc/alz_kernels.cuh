@@ -6,9 +6,9 @@
 namespace alz {
 void launch_ingest_pairs_v1(const alz_l7_rec* recs, uint64_t n, const AccTable& pairs, Counters* ctr,
                             const EpEntry* ep, uint32_t ep_mask, int sms, cudaStream_t s);
-void launch_ingest_pairs_v6(const alz_l7_rec* recs, uint64_t n, const AccTable& pairs, Counters* ctr,
+void launch_ingest_pairs(const alz_l7_rec* recs, uint64_t n, const AccTable& pairs, Counters* ctr,
                             const HotState* hot, const EpEntry* ep, uint32_t ep_mask, int sms, cudaStream_t s);
-void launch_ingest_pairs_v6_rec16(const alz_l7_rec16* recs, uint64_t n, const uint64_t* dur_ovf, const AccTable& pairs,
+void launch_ingest_pairs_rec16(const alz_l7_rec16* recs, uint64_t n, const uint64_t* dur_ovf, const AccTable& pairs,
                                   Counters* ctr, const HotState* hot, const EpEntry* ep, uint32_t ep_mask, int sms,
                                   cudaStream_t s);
 uint32_t ingest_table_rows();
