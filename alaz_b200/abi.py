@@ -23,7 +23,8 @@ PROTO_REDIS, PROTO_KAFKA, PROTO_MYSQL, PROTO_MONGO = 5, 6, 7, 8
 AMQP_PUBLISH, AMQP_DELIVER = 1, 2
 REDIS_COMMAND, REDIS_PUSHED_EVENT, REDIS_PING = 1, 2, 3
 MF_METHOD_MASK, MF_PAYLOAD_REJECT, MF_TLS = 0x3F, 0x40, 0x80
-NODE_POD, NODE_SVC, NODE_OUTBOUND = 0, 1, 2
+NODE_POD, NODE_SVC, NODE_OUTBOUND, NODE_OUTBOUND_HOST = 0, 1, 2, 3
+PROTO_F_HOSTKEY = 0x40
 TABLE_POD, TABLE_SVC = 0, 1
 CFG_EAGER_JOIN = 0x1
 CFG_NO_SMEM_CACHE = 0x2
@@ -82,7 +83,7 @@ class Stats(C.Structure):
         ("capacity_events", C.c_uint64), ("windows", C.c_uint64),
         ("kernel_launches", C.c_uint64), ("collective_bytes_last", C.c_uint64),
         ("flush_local_us_last", C.c_uint64), ("merge_us_last", C.c_uint64),
-        ("_reserved", C.c_uint64 * 2),
+        ("late_events", C.c_uint64), ("deferred_events", C.c_uint64),
     ]
 
     def as_dict(self):

@@ -22,7 +22,8 @@ EXPORTS = [
     "alz_create", "alz_destroy", "alz_strerror", "alz_last_cuda_error", "alz_set_stream", "alz_sync",
     "alz_table_upsert", "alz_table_upsert_batch", "alz_table_erase", "alz_table_commit", "alz_submit_l7", "alz_submit_l7_device",
     "alz_submit_l7_packed", "alz_submit_l7_packed_device", "alz_pack_l7",
-    "alz_submit_l7_raw", "alz_window_flush", "alz_window_flush_device", "alz_window_fetch", "alz_get_stats", "alz_gnn_score",
+    "alz_submit_l7_raw", "alz_window_flush", "alz_window_flush_device", "alz_window_fetch", "alz_get_stats",
+    "alz_window_clock", "alz_window_epoch", "alz_gnn_score",
     "alz_gnn_score_device", "alz_edge_quantiles", "alz_submit_tcp", "alz_sock_lookup", "alz_comm_unique_id", "alz_comm_init",
     "alz_owner_rank",
 ]
@@ -57,6 +58,8 @@ def load(rebuild=False):
         "alz_submit_l7_packed_device": ([vp, vp, sz, vp], i),
         "alz_pack_l7": ([vp, sz, vp, vp, sz], C.c_long),
         "alz_window_fetch": ([vp, vp, sz, C.POINTER(sz)], i),
+        "alz_window_clock": ([vp, u64, u64, u64], i),
+        "alz_window_epoch": ([vp, C.POINTER(u64)], i),
         "alz_pinned_alloc_local": ([vp, sz, pp], i),
         "alz_window_flush": ([vp, vp, sz, C.POINTER(sz)], i),
         "alz_window_flush_device": ([vp, pp, C.POINTER(sz)], i),
@@ -87,7 +90,7 @@ def load(rebuild=False):
     }
     if abi.ABI_VERSION < 2:    # A/B timing against a round-1 build (ALZ_LIB_PATH + ALZ_ABI_VERSION=1)
         for k in ("alz_submit_l7_packed", "alz_submit_l7_packed_device", "alz_pack_l7", "alz_window_fetch",
-                  "alz_pinned_alloc_local", "alz_table_upsert_batch"):
+                  "alz_pinned_alloc_local", "alz_table_upsert_batch", "alz_window_clock", "alz_window_epoch"):
             sig.pop(k)
     for name, (args, res) in sig.items():
         f = getattr(L, name)   # AttributeError = header/library mismatch: loud
@@ -232,6 +235,15 @@ class Handle:
         st = abi.Stats()
         self._ck(self.L.alz_get_stats(self.h, C.byref(st)), "alz_get_stats")
         return st.as_dict()
+
+    def window_clock(self, first_kernel_ns, first_user_ns, window_ns):
+        self._ck(self.L.alz_window_clock(self.h, int(first_kernel_ns), int(first_user_ns), int(window_ns)),
+                 "alz_window_clock")
+
+    def window_epoch(self):
+        e = C.c_uint64(0)
+        self._ck(self.L.alz_window_epoch(self.h, C.byref(e)), "alz_window_epoch")
+        return e.value
 
     def fold(self):
         self._ck(self.L.alz_fold(self.h), "alz_fold")

@@ -171,6 +171,10 @@ extern "C" int alz_create(const alz_config* cfg, alz_handle** out) {
   h->ep_touched.assign(h->ep_cap, 0);
   CKC(cudaMalloc(&h->d_ep, (size_t)h->ep_cap * sizeof(EpEntry)));
   CKC(cudaMemsetAsync(h->d_ep, 0, (size_t)h->ep_cap * sizeof(EpEntry), h->stream));
+  h->bloom_cnt.assign(ALZ_BLOOM_WORDS * 32u, 0);
+  CKC(cudaMalloc(&h->d_bloom, ALZ_BLOOM_WORDS * 4u));
+  CKC(cudaMemsetAsync(h->d_bloom, 0, ALZ_BLOOM_WORDS * 4u, h->stream));   // no pods yet: every source is unresolvable
+  CKC(cudaMallocHost(&h->h_bloom, ALZ_BLOOM_WORDS * 4u));
   CKC(cudaMalloc(&h->d_ctr, sizeof(Counters)));
   CKC(cudaMemsetAsync(h->d_ctr, 0, sizeof(Counters), h->stream));
   CKC(cudaMalloc(&h->d_hot, sizeof(HotState)));
@@ -213,6 +217,8 @@ extern "C" int alz_destroy(alz_handle* h) {
   alz_internal_free_sock(h);
   free_table(&h->pairs); free_table(&h->edges);
   cudaFree(h->d_ep); cudaFree(h->d_ctr); cudaFree(h->d_hot); cudaFree(h->d_patch);
+  cudaFree(h->d_win); cudaFree(h->d_defer[0]); cudaFree(h->d_defer[1]); cudaFree(h->d_bloom);
+  if (h->h_bloom) cudaFreeHost(h->h_bloom);
   if (h->h_patch) cudaFreeHost(h->h_patch);
   if (h->h_ctr) cudaFreeHost(h->h_ctr);
   for (int b = 0; b < 2; ++b) { cudaFree(h->d_keys[b]); cudaFree(h->d_rows[b]); }
@@ -333,6 +339,17 @@ extern "C" int alz_table_upsert_batch(alz_handle* h, int table, const uint32_t* 
   }
   return ALZ_OK;
 }
+// the pod-address filter follows the pod table: counters per bit, so that a delete takes back exactly what the add set
+static void bloom_update(alz_handle* h, uint32_t ip, int delta) {
+  const uint32_t hh = hash32(ip);
+  const uint32_t bits[2] = {hh & (ALZ_BLOOM_WORDS * 32u - 1u), (hh >> 15) & (ALZ_BLOOM_WORDS * 32u - 1u)};
+  for (int k = 0; k < 2; ++k) {
+    uint8_t& c = h->bloom_cnt[bits[k]];
+    if (delta > 0) { if (c != 255) ++c; }
+    else if (c != 255 && c != 0) --c;      // a saturated counter stays set: the filter may only err towards "maybe"
+  }
+  h->bloom_dirty = true;
+}
 static int upsert_locked(alz_handle* h, int table, uint32_t ip, uint32_t id) {
   auto it = h->ep_host.find(ip);
   if (it == h->ep_host.end()) {
@@ -340,6 +357,7 @@ static int upsert_locked(alz_handle* h, int table, uint32_t ip, uint32_t id) {
     it = h->ep_host.emplace(ip, HostEp{}).first;
   }
   HostEp& e = it->second;
+  if (table == ALZ_TABLE_POD && !(e.state & kEpPod)) bloom_update(h, ip, +1);
   if (table == ALZ_TABLE_POD) { e.state |= kEpPod; e.pod = id; }   // persist.go:55-65
   else { e.state |= kEpSvc; e.svc = id; }                          // persist.go:114-124
   h->ep_dirty_ips.push_back(ip);
@@ -350,6 +368,7 @@ extern "C" int alz_table_erase(alz_handle* h, int table, uint32_t ip) {
   std::lock_guard<std::mutex> g(h->mu);
   auto it = h->ep_host.find(ip);
   if (it == h->ep_host.end()) return ALZ_OK;                       // delete of a missing key: no-op
+  if (table == ALZ_TABLE_POD && (it->second.state & kEpPod)) bloom_update(h, ip, -1);
   it->second.state &= ~(table == ALZ_TABLE_POD ? kEpPod : kEpSvc); // persist.go:66-70, :125-129
   if (it->second.state == 0) h->ep_host.erase(it);
   h->ep_dirty_ips.push_back(ip);
@@ -406,6 +425,17 @@ extern "C" int alz_table_commit(alz_handle* h) {
     if (it == h->ep_host.end()) ep_mirror_del(h, ip); else ep_mirror_put(h, ip, it->second);
   }
   h->ep_dirty_ips.clear();
+  if (h->bloom_dirty) {   // 16 KB, through the pinned staging buffer, in stream order behind the fold above
+    CK(cudaEventSynchronize(h->ev_patch));
+    for (uint32_t w = 0; w < ALZ_BLOOM_WORDS; ++w) {
+      uint32_t v = 0;
+      for (uint32_t b = 0; b < 32; ++b) v |= (h->bloom_cnt[w * 32u + b] ? 1u : 0u) << b;
+      h->h_bloom[w] = v;
+    }
+    CK(cudaMemcpyAsync(h->d_bloom, h->h_bloom, ALZ_BLOOM_WORDS * 4u, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaEventRecord(h->ev_patch, h->stream));
+    h->bloom_dirty = false;
+  }
   // only the slots that changed travel: (slot, entry) records through a pinned buffer, scattered on the
   // device in stream order (an informer burst under churn touches a handful of slots of a table that
   // may hold millions)
@@ -467,17 +497,22 @@ int alz_internal_fold(alz_handle* h) { return fold_locked(h); }
 // ---- ingest ------------------------------------------------------------------------------
 // requires h->mu
 static int ingest_device(alz_handle* h, const void* d, uint64_t n, bool rec16, const uint64_t* d_ovf) {
+  if (h->win_on && (rec16 || (h->cfg.flags & (ALZ_CFG_EAGER_JOIN | ALZ_CFG_NO_SMEM_CACHE)))) return ALZ_E_STATE;
   if (rec16) {
     if (h->cfg.flags & (ALZ_CFG_EAGER_JOIN | ALZ_CFG_NO_SMEM_CACHE)) return ALZ_E_UNSUPPORTED;
     launch_ingest_pairs_rec16((const alz_l7_rec16*)d, n, d_ovf, h->pairs, h->d_ctr, h->d_hot, h->d_ep, h->ep_cap - 1,
-                                 h->sms, h->stream);
+                              h->d_bloom, h->sms, h->stream);
   } else if (h->cfg.flags & ALZ_CFG_EAGER_JOIN) {
     launch_ingest_eager((const alz_l7_rec*)d, n, h->d_ep, h->ep_cap - 1, h->edges, h->d_ctr, h->sms, h->stream);
   } else if (h->cfg.flags & ALZ_CFG_NO_SMEM_CACHE) {
     launch_ingest_pairs_v1((const alz_l7_rec*)d, n, h->pairs, h->d_ctr, h->d_ep, h->ep_cap - 1, h->sms, h->stream);
+  } else if (h->win_on) {
+    launch_ingest_pairs_windowed((const alz_l7_rec*)d, n, h->pairs, h->d_ctr, h->d_hot, h->d_ep, h->ep_cap - 1, h->d_bloom,
+                                 h->d_win, h->win_off, h->d_defer[h->defer_cur], h->defer_cap, h->sms, h->stream);
+    h->launches += 1;
   } else {
-    launch_ingest_pairs((const alz_l7_rec*)d, n, h->pairs, h->d_ctr, h->d_hot, h->d_ep, h->ep_cap - 1, h->sms,
-                           h->stream);
+    launch_ingest_pairs((const alz_l7_rec*)d, n, h->pairs, h->d_ctr, h->d_hot, h->d_ep, h->ep_cap - 1, h->d_bloom, h->sms,
+                        h->stream);
   }
   CK(cudaGetLastError());
   h->launches += n ? 1 : 0;
@@ -680,6 +715,24 @@ static int finish_flush(alz_handle* h) {
   return ALZ_OK;
 }
 
+// time-cut windows: the flushed epoch is closed; open the next one and submit the records that waited for it
+// (those of still later epochs are deferred again, into the other buffer)
+static int window_roll(alz_handle* h) {
+  if (!h->win_on) return ALZ_OK;
+  launch_window_advance(h->d_win, h->stream);
+  h->launches += 1;
+  const uint32_t n_def = std::min<uint32_t>(h->h_ctr->defer_count, h->defer_cap);   // read with the edge count
+  CK(cudaMemsetAsync(&h->d_ctr->defer_count, 0, 4, h->stream));
+  h->deferred_last = 0;
+  if (n_def == 0) return ALZ_OK;
+  const alz_l7_rec* src = h->d_defer[h->defer_cur];
+  h->defer_cur ^= 1;
+  const uint64_t before = h->events_in;
+  const int rc = ingest_device(h, src, n_def, false, nullptr);
+  h->events_in = before;   // they were counted when they were first submitted
+  return rc;
+}
+
 static int flush_device_locked(alz_handle* h, const alz_edge_out** dev_edges, size_t* n_out) {
   bool overflow = false;
   CK(cudaEventRecord(h->ev_t[0], h->stream));
@@ -694,6 +747,7 @@ static int flush_device_locked(alz_handle* h, const alz_edge_out** dev_edges, si
   CK(cudaEventRecord(h->ev_t[2], h->stream));
   h->ev_t_valid = true;
   if (mrc != ALZ_OK) return mrc;
+  if ((mrc = window_roll(h)) != ALZ_OK) return mrc;
   *n_out = h->last_n_edges;
   if (dev_edges) *dev_edges = h->d_out;
   return overflow ? ALZ_E_CAPACITY : ALZ_OK;
@@ -721,6 +775,7 @@ extern "C" int alz_window_flush(alz_handle* h, alz_edge_out* out, size_t cap, si
     if (rc != ALZ_OK) return rc;
     if (h->n_live) CK(cudaMemcpyAsync(out, h->d_out, (size_t)h->n_live * sizeof(alz_edge_out),
                                       cudaMemcpyDeviceToHost, h->stream));
+    if ((rc = window_roll(h)) != ALZ_OK) return rc;
     CK(cudaStreamSynchronize(h->stream));
     return overflow ? ALZ_E_CAPACITY : ALZ_OK;
   }
@@ -760,13 +815,15 @@ extern "C" int alz_get_stats(alz_handle* h, alz_stats* st) {
   st->events_in = h->events_in;
   st->not_request = h->h_ctr->not_request;
   st->src_unresolved = h->h_ctr->src_unresolved;   // complete once pending pairs are folded
-  st->rows_emitted = h->events_in - st->not_request - st->src_unresolved - lost;
+  st->rows_emitted = h->events_in - st->not_request - st->src_unresolved - lost - h->h_ctr->defer_count;   // waiting records are not rows yet
   st->pairs_live = h->h_ctr->pair_rows;
   st->edges_live = h->h_ctr->edge_rows;
   st->tcp_events_in = h->tcp_events_in;
   st->tcp_localhost_dropped = h->tcp_localhost_dropped;
   st->capacity_events = lost;
   st->windows = h->windows;
+  st->late_events = h->h_ctr->late_events;
+  st->deferred_events = h->h_ctr->defer_count;
   st->kernel_launches = h->launches;
   st->collective_bytes_last = h->collective_bytes_last;
   if (h->ev_t_valid) {   // the stream was synchronised above, so the events have completed
@@ -774,6 +831,38 @@ extern "C" int alz_get_stats(alz_handle* h, alz_stats* st) {
     if (cudaEventElapsedTime(&a, h->ev_t[0], h->ev_t[1]) == cudaSuccess) st->flush_local_us_last = (uint64_t)(a * 1000.f);
     if (cudaEventElapsedTime(&b, h->ev_t[1], h->ev_t[2]) == cudaSuccess) st->merge_us_last = (uint64_t)(b * 1000.f);
   }
+  return ALZ_OK;
+}
+
+extern "C" int alz_window_clock(alz_handle* h, uint64_t first_kernel_ns, uint64_t first_user_ns, uint64_t window_ns) {
+  if (!h) return ALZ_E_INVAL;
+  std::lock_guard<std::mutex> g(h->mu);
+  CK(cudaSetDevice(h->device));
+  if (h->pending_since_fold != 0 || h->h_ctr->defer_count != 0) return ALZ_E_STATE;   // only between windows
+  if (window_ns == 0) { h->win_on = false; return ALZ_OK; }
+  if (!h->d_win) {
+    CK(cudaMalloc(&h->d_win, 3 * sizeof(uint64_t)));
+    h->defer_cap = 2u * h->cfg.max_batch;
+    for (int b = 0; b < 2; ++b) CK(cudaMalloc(&h->d_defer[b], (size_t)h->defer_cap * sizeof(alz_l7_rec)));
+  }
+  const uint64_t init[3] = {0ull, window_ns, 0ull};
+  CK(cudaMemcpyAsync(h->d_win, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->win_off = first_user_ns - first_kernel_ns;
+  h->win_len = window_ns;
+  h->win_on = true;
+  return ALZ_OK;
+}
+extern "C" int alz_window_epoch(alz_handle* h, uint64_t* epoch) {
+  if (!h || !epoch) return ALZ_E_INVAL;
+  std::lock_guard<std::mutex> g(h->mu);
+  CK(cudaSetDevice(h->device));
+  if (!h->win_on) return ALZ_E_STATE;
+  uint64_t w[3];
+  CK(cudaMemcpyAsync(w, h->d_win, sizeof(w), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (!w[2]) return ALZ_E_STATE;
+  *epoch = (w[0] + h->win_off) / w[1];
   return ALZ_OK;
 }
 

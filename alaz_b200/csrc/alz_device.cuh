@@ -28,6 +28,11 @@ struct __align__(16) EpEntry {
 };
 constexpr uint32_t kEpOcc = 1u, kEpPod = 2u, kEpSvc = 4u;
 
+// Filter of the pod addresses (two bits per address out of hash32): the ingest kernel keeps a copy in shared memory
+// and drops an event whose source cannot be a pod without touching the dictionary (alz_ingest.cu). The host keeps
+// counters per bit so that deletes are exact (alz_api.cu). A cluster far larger than the filter just saturates it.
+#define ALZ_BLOOM_WORDS 4096u   /* 128 Kbit */
+
 __host__ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
   x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
   return x;
@@ -314,8 +319,10 @@ struct Counters {
   unsigned long long src_unresolved;
   unsigned long long capacity_events;   // events lost at ingest to an exhausted pair dictionary / row pool
   unsigned long long fold_lost_events;  // events lost at fold to an exhausted edge dictionary / row pool
-  uint32_t pair_rows, edge_rows, pad1[2];   // row allocators of the two tables
-  unsigned long long pad2[2];
+  uint32_t pair_rows, edge_rows;            // row allocators of the two tables
+  uint32_t defer_count, pad1;               // time-cut windows: records waiting for their window (alz_ingest.cu)
+  unsigned long long late_events;           // time-cut windows: records older than the open window (reduced into it)
+  unsigned long long pad2;
 };
 
 }  // namespace alz

@@ -58,6 +58,10 @@ struct alz_handle {
   std::vector<uint32_t> ep_touched_list;
   alz::EpEntry* d_ep = nullptr;
   uint32_t ep_cap = 0;
+  std::vector<uint8_t> bloom_cnt;         // per filter bit: how many pod addresses set it (saturating at 255)
+  bool bloom_dirty = false;
+  uint32_t* d_bloom = nullptr;            // ALZ_BLOOM_WORDS words
+  uint32_t* h_bloom = nullptr;            // pinned staging
   void* h_patch = nullptr;                // pinned: (slot, entry) records of one commit
   void* d_patch = nullptr;
   size_t patch_cap = 0;
@@ -77,6 +81,15 @@ struct alz_handle {
   alz_edge_out* d_out = nullptr;
   uint32_t n_live = 0, last_n_edges = 0;
   uint64_t lost_reported = 0;             // capacity_events already reported by an earlier flush
+
+  // time-cut windows (alz_window_clock)
+  bool win_on = false;
+  uint64_t win_off = 0, win_len = 0;      // first_user - first_kernel (mod 2^64), window length
+  uint64_t* d_win = nullptr;              // device WinClock {lo, len, ready}
+  alz_l7_rec* d_defer[2] = {nullptr, nullptr};   // records of later windows (ping-pong)
+  uint32_t defer_cap = 0;
+  int defer_cur = 0;
+  uint64_t deferred_last = 0;
 
   uint64_t events_in = 0, pending_since_fold = 0, windows = 0;
   uint64_t launches = 0;                  // own kernels launched (stats)

@@ -1,27 +1,34 @@
 // alz_ingest.cu — the dominant kernel: l7 events -> per-socket-pair accumulators
 // (DESIGN.md §3 step 1, §5). One persistent CTA per SM.
 //
-// What bounds it (profiles/r2_ingest_sections.txt, measured with the instrumented build on warm
-// caches): neither DRAM nor instruction issue but the SM's load/store path (L1TEX): every shared-
-// memory wavefront and every scattered global request (a dictionary probe, a reduction into L2)
-// takes a slot there, and round 2's first kernel spent ~105 of them per 32 events. This version is
-// organised around spending fewer:
-//   * records come straight from L2 into registers (one 32-byte load per record, evict-first);
-//     the TMA engine is used to PREFETCH the stream into L2 three iterations ahead
-//     (cp.async.bulk.prefetch.L2), so the loads find their lines in L2 and nothing is staged
-//     through shared memory (a staged copy costs a write and a read of the data path per record);
-//   * the per-CTA table of hot socket pairs holds a 16-bucket WINDOW of the latency histogram per
-//     pair in 16-bit cells (52 bytes a row instead of 292), which is where a pair's latencies
-//     fall (the window is chosen from the pair's own histogram at the previous fold); ~2700 pairs
-//     fit instead of 224 and ~80 % of the events end there: a hit is two probes of a 2-choice
-//     direct-mapped index, one key load, two shared reductions;
-//   * everything else (a cold pair, a latency outside the row's window, a reversed or host-keyed
-//     row) goes to the global pair table: one dictionary probe and two reductions (REDG) per event,
-//     issued inline under predicates; only events whose home slot does not hold their pair (new
-//     pair, collision, unresolvable source) are queued in shared memory and walk the dictionary
-//     32 at a time.
-// 16-bit cells stay exact: a cell that reaches 0x7FFF is spilled into the global table by the lane
-// that saw it (bit 15 is head room for the increments that race with the spill).
+// Data movement: every warp owns a two-stage ring in shared memory and streams its chunks of the
+// record array into it with TMA bulk copies (cp.async.bulk + mbarrier complete_tx, issued by one
+// elected lane, L2 evict-first). Lanes copy their records from the ring into registers, the stage
+// goes back to the TMA as soon as those loads have returned, and the next two chunks are in flight
+// while the warp works: no per-lane address arithmetic, no scoreboard stall on the first use of a
+// streamed record (profiles/r2_ingest_sections.txt: 4 % of a warp's time waits on the ring; with
+// plain loads, even prefetched into L2 by the TMA engine, it was 28 %), no cross-warp barrier
+// anywhere in the main loop.
+//
+// Work per event, three tiers:
+//   hot   the event's socket pair is in the CTA's shared-memory table. A row holds a 16-bucket
+//         WINDOW of the latency histogram in 16-bit cells (52 bytes instead of 292: the window is
+//         where the pair's latencies fall, chosen from its own histogram at the previous fold), so
+//         ~1250 pairs fit and ~77 % of the events of a Zipf(1.1) stream end here: two probes of a
+//         2-choice direct-mapped index (fingerprint | window | row), one key load, two shared
+//         reductions. 16-bit cells stay exact: the lane that sees a cell at 0x7FFF spills 0x8000
+//         counts into the global table (bit 15 is head room for the increments racing with it).
+//   cold  everything else (a pair without a row, a latency outside its row's window, a reversed
+//         or host-keyed row) is NOT handled inline: the lane pushes the event onto its warp's
+//         queue (ballot-compacted, no atomics) and the warp runs the cold path for 32 queued
+//         events at a time with all lanes busy — global dictionary probe of the home slot, then
+//         reductions (REDG) into the pair's row in L2. The probes are cp.async copies into shared
+//         memory and are consumed when the next batch is requested, one to three iterations
+//         later, so their L2/DRAM round trip is off the warp's critical path. A source address
+//         that cannot be a pod (a 128-Kbit filter of the pod addresses, built by the host at table
+//         commit) is dropped right there, as setFromToV2 would (aggregator/data.go:829-832).
+//   slow  a cold event whose home slot does not hold its pair (new pair, collision) is queued once
+//         more and 32 of them at a time walk find_or_insert_pair.
 #include <cstdlib>
 
 #include "alz_kernels.cuh"
@@ -48,20 +55,28 @@ namespace {
 
 constexpr uint32_t kRowWords = 13;         // 8 words = 16 x u16 histogram cells, err5xx u32, 2 x (lat_lo, lat_hi); odd stride
 constexpr uint32_t kCellSpill = 0x7FFFu;   // a 16-bit cell seen at this value is spilled (bit 15 = head room)
-constexpr uint32_t kTab = 8192;            // index entries: fingerprint 16 | window base 4 | row 12, two choices per key
-constexpr uint32_t kTabShift = 19;
+constexpr uint32_t kTab = 4096;            // index entries: fingerprint 16 | window base 4 | row 12, two choices per key
+constexpr uint32_t kTabShift = 20;
 constexpr uint32_t kRowMask = 0xFFFu;
 constexpr uint32_t kBusy = kRowMask;       // entry whose row field is no row: claimed, not (or never) published
+constexpr uint32_t kColdQ = 128;           // cold queue entries per warp (ring): up to 31 left over + 32 + 64 new ones
 constexpr uint32_t kSlowQ = 64;            // slow queue entries per warp (ring)
-constexpr uint32_t kQBytes = 16;           // {key u64, dur_lo u32, meta u32}
+constexpr uint32_t kQBytes = 16;           // queue entry {key u64, dur_lo u32, meta u32}
 constexpr uint32_t kSmemMax = 232448;      // 227 KB per CTA on sm_100
-constexpr uint32_t kPrefetchAhead = 3;     // iterations
+constexpr int kU = 2;                      // events per lane per iteration
+constexpr uint32_t kChunk = 32u * kU;      // events per warp per iteration = one TMA copy
 
-template <int kWarps>
+template <int kWarps, int kRecWords>
 struct Layout {
-  static constexpr uint32_t kTabOff = 0;
-  static constexpr uint32_t kSlowOff = kTabOff + kTab * 4u;
-  static constexpr uint32_t kMisc = kSlowOff + (uint32_t)kWarps * kSlowQ * kQBytes;   // row allocator
+  static constexpr uint32_t kChunkBytes = kChunk * kRecWords * 4u;
+  static constexpr uint32_t kRing = (uint32_t)kWarps * 2u * kChunkBytes;
+  static constexpr uint32_t kBars = kRing;                              // kWarps * 2 mbarriers
+  static constexpr uint32_t kTabOff = kBars + (uint32_t)kWarps * 16u;
+  static constexpr uint32_t kBloomOff = kTabOff + kTab * 4u;            // pod-address filter, ALZ_BLOOM_WORDS words
+  static constexpr uint32_t kColdOff = kBloomOff + ALZ_BLOOM_WORDS * 4u;
+  static constexpr uint32_t kSlowOff = kColdOff + (uint32_t)kWarps * kColdQ * kQBytes;
+  static constexpr uint32_t kProbeOff = kSlowOff + (uint32_t)kWarps * kSlowQ * kQBytes;   // per warp: 32 x 16-B DictEnt
+  static constexpr uint32_t kMisc = kProbeOff + (uint32_t)kWarps * 512u;                  // row allocator
   static constexpr uint32_t kRowKeys = kMisc + 16u;
   static constexpr uint32_t kPerRow = 8u + kRowWords * 4u + 1u;         // key, cells, window base
   static constexpr uint32_t kRowsRaw = (kSmemMax - kRowKeys - 64u) / kPerRow - 1u;
@@ -72,6 +87,7 @@ struct Layout {
   static constexpr uint32_t kPreload = kRows - kRows / 8u;              // rows the hot list may take
   static_assert(kBytes <= kSmemMax, "shared memory layout too large");
   static_assert(kRows < kBusy, "row field is 12 bits");
+  static_assert(kRows * 3u <= kTab * 2u, "index too small for the rows");
 };
 
 // ---- PTX helpers ----------------------------------------------------------------------------
@@ -93,20 +109,33 @@ __device__ __forceinline__ uint32_t shr_clamp(uint32_t v, uint32_t by) {   // PT
   asm("shr.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(by));
   return r;
 }
-// the TMA engine pulls `bytes` of the stream into L2 ahead of the loads (no shared memory involved)
-__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes, uint64_t policy) {
-  asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(p), "r"(bytes), "l"(policy) : "memory");
+// ---- TMA / mbarrier / cp.async (PTX) ----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-// streaming load of one 32-byte record: read once, keep it out of L1 and first in line for L2 eviction
-__device__ __forceinline__ void load_rec32(const uint32_t* p, uint64_t policy, uint32_t (&w)[8]) {
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
-               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
-               : "l"(p), "l"(policy));
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void load_rec16(const uint32_t* p, uint64_t policy, uint32_t (&w)[4]) {
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
-               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "l"(p), "l"(policy));
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
 }
+// global -> shared bulk copy, completion counted on the mbarrier; L2 evict-first so that the stream does not
+// push the accumulator rows out of L2
+__device__ __forceinline__ void tma_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+// 16-byte global -> shared copy that no register waits on (LDGSTS); L2 only (the dictionary is written by other CTAs)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // docs/SPEC.md §4 through the float exponent: round-toward-zero keeps floor(log2 d) and the next mantissa bit
 // exact for every u64, so bits >> 22 = 2 * (127 + o) + bit(o-1); one conversion instead of a 64-bit clz chain
@@ -134,11 +163,18 @@ __device__ __forceinline__ uint32_t table_hash(uint64_t key) {
 }
 __device__ __forceinline__ uint32_t tab_idx1(uint32_t h) { return h >> kTabShift; }
 __device__ __forceinline__ uint32_t tab_idx2(uint32_t h) { return (h * 0xC2B2AE35u) >> kTabShift; }
+// the filter of pod addresses (alz_api.cu keeps it in step with the table): false = certainly not a pod
+__device__ __forceinline__ bool maybe_pod(const uint32_t* bloom, uint32_t ip) {
+  const uint32_t h = hash32(ip);
+  const uint32_t b1 = h & (ALZ_BLOOM_WORDS * 32u - 1u), b2 = (h >> 15) & (ALZ_BLOOM_WORDS * 32u - 1u);
+  return ((bloom[b1 >> 5] >> (b1 & 31u)) & (bloom[b2 >> 5] >> (b2 & 31u)) & 1u) != 0u;
+}
 __device__ __forceinline__ uint32_t tab_fp(uint32_t h) { return (h << 16) | 0x10000u; }   // never 0 in bits 31..16
 __device__ __forceinline__ uint32_t tab_entry(uint32_t h, uint32_t base4, uint32_t row) { return tab_fp(h) | (base4 << 12) | row; }
 
 struct Shared {
   uint32_t* tab;      // [kTab]
+  uint32_t* bloom;    // [ALZ_BLOOM_WORDS]
   uint64_t* rowkey;   // [kRows + 1], entry kRows = kEmptyKey (never a hit)
   uint32_t* rows;     // [(kRows + 1) * kRowWords]
   uint8_t* rowbase;   // [kRows + 1] first bucket / 4 of the row's window (also in its index entry)
@@ -165,23 +201,28 @@ __device__ __forceinline__ bool smem_admit(const Shared& s, uint64_t key, uint32
 // window for a pair admitted without history: centred on the bucket of the event that brought it in
 __device__ __forceinline__ uint32_t base4_around(uint32_t bucket) { return (uint32_t)min(max((int)bucket - 6, 0), 48) >> 2; }
 
-// one warp's queue of slow events in shared memory: a ring of 16-byte entries {key u64, dur_lo u32, meta u32}
+// one warp's queue of deferred events in shared memory: a ring of 16-byte entries {key u64, dur_lo u32, meta u32}
 // filled by ballot compaction. meta: bits 0..5 latency bucket, 6..7 pair kind, bit 8 counts as 5xx, bits 9..31
 // the duration's high word (events whose duration does not fit, >= 2^55 ns, are handled on the spot)
-struct SlowQueue {
+template <uint32_t kCap>
+struct Queue {
   uint8_t* base;
   uint32_t head, count;
   __device__ __forceinline__ void bind(uint8_t* b) { base = b; head = 0; count = 0; }
   __device__ __forceinline__ uint4* at(uint32_t i) const {
-    return reinterpret_cast<uint4*>(base + ((head + i) & (kSlowQ - 1u)) * kQBytes);
+    return reinterpret_cast<uint4*>(base + ((head + i) & (kCap - 1u)) * kQBytes);
   }
-  __device__ __forceinline__ void push(bool want, uint64_t k, uint32_t dlo, uint32_t m, uint32_t lane_lt) {
+  __device__ __forceinline__ uint32_t push(bool want, uint64_t k, uint32_t dlo, uint32_t m, uint32_t lane_lt) {
     const uint32_t mask = __ballot_sync(0xFFFFFFFFu, want);
     if (want) *at(count + __popc(mask & lane_lt)) = make_uint4((uint32_t)k, (uint32_t)(k >> 32), dlo, m);
-    count += __popc(mask);
+    const uint32_t added = __popc(mask);
+    count += added;
+    return added;
   }
-  __device__ __forceinline__ void pop(uint32_t n) { head = (head + n) & (kSlowQ - 1u); count -= n; }
+  __device__ __forceinline__ void pop(uint32_t n) { head = (head + n) & (kCap - 1u); count -= n; }
 };
+using SlowQueue = Queue<kSlowQ>;
+using ColdQueue = Queue<kColdQ>;
 
 // the global path for one event whose pair row is known
 __device__ __forceinline__ void global_add(const AccTable& t, uint32_t row, uint32_t bucket, uint64_t dur, bool err) {
@@ -218,45 +259,129 @@ __device__ __forceinline__ void slow_batch(SlowQueue& q, uint32_t count, const A
   q.pop(count);
 }
 
-// kRecWords = 8: alz_l7_rec (32 B). kRecWords = 4: alz_l7_rec16 (16 B; durations >= 2^32 ns sit in dur_ovf)
-template <int kWarps, int kRecWords>
+// cold tier, step 1: request the dictionary home slots of the first `count` queued events — unless the event's
+// source address cannot be a pod, in which case no row would be emitted (aggregator/data.go:829-832): its probe
+// slot is marked instead. The 16-byte entries are copied straight into the warp's probe buffer in shared memory
+// (cp.async): nothing waits on them until the batch is consumed, which happens when the NEXT batch is ready to be
+// requested. (Holding the probes in registers did not work: handing them from one loop trip to the next needs a
+// move, and the move waits for the load.)
+__device__ __forceinline__ void cold_issue(const ColdQueue& q, uint32_t count, const AccTable& t, const Shared& s,
+                                           uint4* probe, uint32_t probe_a) {
+  const uint32_t lane = threadIdx.x & 31u;
+  if (lane < count) {
+    const uint4 e = *q.at(lane);
+    const uint32_t kind = (e.w >> 6) & 3u;
+    if (!maybe_pod(s.bloom, e.x)) probe[lane] = make_uint4(0u, 0u, kDropRow, 1u);      // e.x = the key's low word = saddr
+    else {
+      const uint64_t key = ((uint64_t)e.y << 32) | e.x;
+      cp_async16(probe_a + lane * 16u, &t.dict_of(kind)[pair_hash(key) & t.mask_of(kind)]);
+    }
+  }
+  cp_async_commit();
+}
+// cold tier, step 2: the probes have landed. A home-slot hit is reduced into its row at once, a filtered source is
+// counted, anything else joins the slow queue.
+template <uint32_t kRows>
+__device__ __forceinline__ void cold_consume(ColdQueue& q, uint32_t count, const uint4* probe, SlowQueue& slow,
+                                             const AccTable& t, const Shared& s, const EpEntry* __restrict__ ep,
+                                             uint32_t ep_mask, uint32_t lane_lt, uint32_t* lost, uint32_t* unresolved,
+                                             unsigned long long* t_wait, unsigned long long* t_slow) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const long long w0 = PROF_NOW();
+  cp_async_wait_all();
+  *t_wait += (unsigned long long)(PROF_NOW() - w0);
+  const bool valid = lane < count;
+  uint4 e = make_uint4(0u, 0u, 0u, 0u), ent = make_uint4(0u, 0u, kNoRow, 0u);
+  if (valid) { e = *q.at(lane); ent = probe[lane]; }
+  const bool filtered = valid && ent.z == kDropRow && ent.w == 1u;
+  const bool home = valid && !filtered && ent.x == e.x && ent.y == e.y && ent.z < kDropRow && (e.x & e.y) != 0xFFFFFFFFu;
+  if (home) global_add(t, ent.z, e.w & 0x3Fu, ((uint64_t)(e.w >> 9) << 32) | e.z, (e.w & 0x100u) != 0u);
+  if (filtered) *unresolved += 1u;
+  slow.push(valid && !home && !filtered, ((uint64_t)e.y << 32) | e.x, e.z, e.w, lane_lt);
+  __syncwarp();
+  q.pop(count);
+  if (slow.count >= 32u) {
+    const long long s0 = PROF_NOW();
+    slow_batch<kRows>(slow, 32u, t, s, ep, ep_mask, lost, unresolved);
+    *t_slow += (unsigned long long)(PROF_NOW() - s0);
+  }
+}
+
+// time-cut windows (docs/SPEC.md §8): the open window in the records' own (kernel) clock
+struct WinClock {
+  uint64_t lo;        // first kernel-time ns of the open window
+  uint64_t len;       // window length, ns
+  uint64_t ready;     // lo is set (by win_init_kernel from the first record ever submitted)
+};
+
+// kRecWords = 8: alz_l7_rec (32 B). kRecWords = 4: alz_l7_rec16 (16 B; durations >= 2^32 ns sit in dur_ovf).
+// kWin (32-B records only): an event whose write_time lies beyond the open window is not reduced but appended
+// to `defer_buf` (it is submitted again when its window opens); one that lies before it is late: reduced into
+// the open window and counted.
+template <int kWarps, int kRecWords, bool kWin>
 __global__ void __launch_bounds__(kWarps * 32, 1)
-ingest_pairs_v7_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable pairs, Counters* ctr,
+ingest_pairs_v8_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable pairs, Counters* ctr,
                        const HotState* __restrict__ hot, const EpEntry* __restrict__ ep, uint32_t ep_mask,
-                       const uint64_t* __restrict__ dur_ovf) {
-  using L = Layout<kWarps>;
+                       const uint32_t* __restrict__ bloom_g, const uint64_t* __restrict__ dur_ovf,
+                       const WinClock* __restrict__ win, uint4* __restrict__ defer_buf, uint32_t defer_cap) {
+  using L = Layout<kWarps, kRecWords>;
   constexpr uint32_t kRows = L::kRows;
-  constexpr int kU = 2;
-  constexpr uint32_t kChunk = 32u * kU;                                  // events per warp per iteration
-  extern __shared__ __align__(16) uint8_t smem_raw[];
+  extern __shared__ __align__(128) uint8_t smem_raw[];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t lane_lt = (1u << lane) - 1u;
   Shared s;
   s.tab = reinterpret_cast<uint32_t*>(smem_raw + L::kTabOff);
+  s.bloom = reinterpret_cast<uint32_t*>(smem_raw + L::kBloomOff);
   s.n_rows = reinterpret_cast<uint32_t*>(smem_raw + L::kMisc);
   s.rowkey = reinterpret_cast<uint64_t*>(smem_raw + L::kRowKeys);
   s.rows = reinterpret_cast<uint32_t*>(smem_raw + L::kRowsOff);
   s.rowbase = smem_raw + L::kBaseOff;
+  ColdQueue cold;
   SlowQueue slow;
+  cold.bind(smem_raw + L::kColdOff + (size_t)warp * kColdQ * kQBytes);
   slow.bind(smem_raw + L::kSlowOff + (size_t)warp * kSlowQ * kQBytes);
+  uint4* probe = reinterpret_cast<uint4*>(smem_raw + L::kProbeOff + (size_t)warp * 512u);
+  const uint32_t probe_a = smem_u32(probe);
+  const uint8_t* ring = smem_raw + (size_t)warp * 2u * L::kChunkBytes;
+  const uint32_t ring_a = smem_u32(ring);
+  const uint32_t bar_a = smem_u32(smem_raw + L::kBars + warp * 16u);
 
-  // chunks of this warp: c, c + stride, ... (a chunk = 64 consecutive records); 32-bit chunk numbers:
-  // n < 2^37 events per launch (the ABI layer splits above)
+  // chunks of this warp: c, c + stride, ... (a chunk = 64 consecutive records); all but possibly the last chunk
+  // of the array are full. 32-bit chunk numbers: n < 2^37 events per launch (the ABI layer splits above).
   const uint32_t n_chunks = (uint32_t)((n + kChunk - 1u) / kChunk);
   const uint32_t c_stride = gridDim.x * kWarps;
   const uint32_t c_first = blockIdx.x * kWarps + warp;
   const uint32_t tail = (uint32_t)(n - (uint64_t)(n_chunks - 1u) * kChunk);   // events in the last chunk, 1..kChunk
   uint64_t policy;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-  constexpr uint32_t kChunkWords = kChunk * kRecWords;
-  auto prefetch_chunk = [&](uint32_t c) {   // one lane
-    if (c < n_chunks)
-      prefetch_l2(recs + (uint64_t)c * kChunkWords, (c == n_chunks - 1u ? tail : kChunk) * (uint32_t)kRecWords * 4u, policy);
+  // producer state (used by the elected lane): the chunk two iterations ahead and its address
+  uint32_t c_next = c_first;
+  const uint32_t* src_next = recs + (uint64_t)c_first * (kChunk * kRecWords);
+  const uint64_t src_step = (uint64_t)c_stride * (kChunk * kRecWords);        // in words
+  // `dep` is always 0 but computed from the words just loaded out of the stage (see the main loop): the copy cannot
+  // be issued before those loads have returned
+  auto issue = [&](uint32_t stage, uint32_t dep) {   // one lane; requests chunk c_next if there is one
+    if (c_next < n_chunks) {
+      const uint32_t bytes = (c_next == n_chunks - 1u ? tail : kChunk) * (uint32_t)kRecWords * 4u + dep;
+      mbar_expect_tx(bar_a + stage * 8u, bytes);
+      tma_load(ring_a + stage * L::kChunkBytes, src_next, bytes, bar_a + stage * 8u, policy);
+    }
   };
-  if (lane == 0)
-    for (uint32_t a = 0; a < kPrefetchAhead; ++a) prefetch_chunk(c_first + a * c_stride);
+  // the first two chunks are requested before the table is even built
+  if (lane == 0) {
+    mbar_init(bar_a, 1u);
+    mbar_init(bar_a + 8u, 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    issue(0u, 0u);
+    c_next += c_stride; src_next += src_step;
+    issue(1u, 0u);
+  }
+  c_next += 2u * c_stride - (lane == 0 ? c_stride : 0u);   // every lane tracks the producer state, so any lane can be elected
+  src_next += 2u * src_step - (lane == 0 ? src_step : 0u);
 
   for (uint32_t i = threadIdx.x; i < kTab; i += kWarps * 32) s.tab[i] = 0u;
+  for (uint32_t i = threadIdx.x; i < ALZ_BLOOM_WORDS; i += kWarps * 32) s.bloom[i] = bloom_g ? bloom_g[i] : 0xFFFFFFFFu;
   for (uint32_t i = threadIdx.x; i <= kRows; i += kWarps * 32) { s.rowkey[i] = kEmptyKey; s.rowbase[i] = 0; }
   for (uint32_t i = threadIdx.x; i < (kRows + 1u) * kRowWords; i += kWarps * 32) s.rows[i] = 0u;
   if (threadIdx.x == 0) *s.n_rows = 0u;
@@ -278,41 +403,90 @@ ingest_pairs_v7_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
   }
   __syncthreads();
 
-  uint32_t lost = 0, unresolved = 0, n_hit = 0, n_live = 0, n_cold = 0;
+  const uint32_t zero = (uint32_t)(n >> 63);   // n < 2^37
+  uint32_t lost = 0, unresolved = 0, n_hit = 0, n_live = 0, n_cold = 0, n_late = 0;
+  uint32_t probing = 0;                        // events at the head of the cold queue whose probes are in flight
+  uint64_t win_lo = 0, win_len = ~0ull;
+  if (kWin) { win_lo = win->lo; win_len = win->len; }
   PROF_DECL;
+  unsigned long long t_wait = 0, t_slow = 0;
   const long long p_begin = PROF_NOW();
-  for (uint32_t c = c_first; c < n_chunks; c += c_stride) {
+  uint32_t it = 0;
+  for (uint32_t c = c_first; c < n_chunks; c += c_stride, ++it) {
+    const uint32_t stage = it & 1u;
     pc0 = PROF_NOW();
+    mbar_wait(bar_a + stage * 8u, (it >> 1) & 1u);
+    pc1 = PROF_NOW();
+    PROF_ADD(1, pc1 - pc0);
     PROF_ADD(6, 1);
-    const uint32_t n_here = (c == n_chunks - 1u) ? tail : kChunk;
-    n_live += n_here;
-    if (elect_one()) prefetch_chunk(c + kPrefetchAhead * c_stride);
-    // this iteration's records (lane l takes records l and l + 32 of the chunk)
-    uint32_t w[kU][kRecWords];
+    // records of this chunk into registers (lane l takes records l and l + 32)
+    uint32_t w[kU][8];
+    const uint8_t* st = ring + stage * L::kChunkBytes;
+    uint32_t seen = 0;
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const uint4* p = reinterpret_cast<const uint4*>(st + ((size_t)u * 32u + lane) * (kRecWords * 4u));
+      const uint4 a = p[0];
+      w[u][0] = a.x; w[u][1] = a.y; w[u][2] = a.z; w[u][3] = a.w;
+      seen ^= a.x;
+      w[u][4] = w[u][5] = w[u][6] = w[u][7] = 0u;
+      if (kRecWords == 8) {
+        if (kWin) { const uint4 b = p[1]; w[u][4] = b.x; w[u][5] = b.y; w[u][6] = b.z; w[u][7] = b.w; seen ^= b.x; }
+        else { const uint2 b = *reinterpret_cast<const uint2*>(p + 1); w[u][4] = b.x; w[u][5] = b.y; seen ^= b.x; }
+      }
+    }
+    // The stage goes back to the TMA only when the loads above have RETURNED: the byte count of the copy is made
+    // to depend on the loaded words (`zero` is a run-time 0 the compiler cannot see through), so the copy's issue
+    // waits on their scoreboard. A __syncwarp() alone orders the instructions, not the completion of the
+    // shared-memory loads, and under load the TMA write of the next chunk overtook the duration loads of this one
+    // (right keys with the wrong latencies).
+    __syncwarp();
+    if (elect_one()) issue(stage, seen & zero);
+    c_next += c_stride; src_next += src_step;
+    uint32_t n_here = (c == n_chunks - 1u) ? tail : kChunk;
+
     bool live[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       live[u] = (uint32_t)u * 32u + lane < n_here;
-#pragma unroll
-      for (int k = 0; k < kRecWords; ++k) w[u][k] = 0u;
-      const uint32_t* p = recs + ((uint64_t)c * kChunk + (uint32_t)u * 32u + lane) * kRecWords;
-      if (live[u]) { if constexpr (kRecWords == 8) load_rec32(p, policy, w[u]); else load_rec16(p, policy, w[u]); }
+      if constexpr (kWin && kRecWords == 8) {
+        const uint64_t rel = (((uint64_t)w[u][7] << 32) | w[u][6]) - win_lo;      // write_time relative to the window
+        const bool late = live[u] && (rel >> 63) != 0ull;                          // before the open window
+        const bool future = live[u] && !late && rel >= win_len;
+        n_late += late ? 1u : 0u;
+        const uint32_t fm = __ballot_sync(0xFFFFFFFFu, future);
+        if (fm != 0u) {   // warp-uniform and rare: only around a window boundary
+          uint32_t at = 0;
+          if (lane == (uint32_t)__ffs((int)fm) - 1u) at = atomicAdd(&ctr->defer_count, (uint32_t)__popc(fm));
+          at = __shfl_sync(0xFFFFFFFFu, at, __ffs((int)fm) - 1) + __popc(fm & lane_lt);
+          if (future) {
+            if (at < defer_cap) {
+              defer_buf[2u * at] = make_uint4(w[u][0], w[u][1], w[u][2], w[u][3]);
+              defer_buf[2u * at + 1u] = make_uint4(w[u][4], w[u][5], w[u][6], w[u][7]);
+            } else ++lost;
+            live[u] = false;          // not this window's event
+          }
+          n_live -= (uint32_t)__popc(fm);   // handed on: not this launch's events (see not_request below)
+        }
+      }
     }
+    n_live += n_here;
 
-    // hot tier for both events of the lane, the dictionary probe of a cold one requested right away
-    uint64_t key[kU], dur[kU];
-    uint32_t meta[kU];      // bits 0..5 bucket, 6..7 kind, 8 err, 31 cold
-    uint4 ent[kU];
+    // hot tier for both events of the lane, then one pass over the cold queue
+    uint64_t key[kU];
+    uint32_t dlo[kU], meta[kU];
+    bool coldf[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const uint32_t mw = (kRecWords == 8) ? w[u][3] : w[u][2];   // status | protocol << 16 | method_flags << 24
       uint32_t p = __byte_perm(mw, 0u, 0x4442u);                  // protocol byte, flag bits still on
-      if (kRecWords == 8) dur[u] = ((uint64_t)w[u][5] << 32) | w[u][4];
+      uint64_t dur;
+      if (kRecWords == 8) dur = ((uint64_t)w[u][5] << 32) | w[u][4];
       else {
-        dur[u] = w[u][3];
-        if (p & ALZ_REC16_DUR_OVERFLOW) dur[u] = live[u] ? __ldg(&dur_ovf[w[u][3]]) : 0ull;
+        dur = w[u][3];
+        if (p & ALZ_REC16_DUR_OVERFLOW) dur = live[u] ? __ldg(&dur_ovf[w[u][3]]) : 0ull;
       }
-      const bool hk = (p & ALZ_PROTO_F_HOSTKEY) != 0u;             // daddr is a Host-header id: own key space
+      const bool hk = (p & ALZ_PROTO_F_HOSTKEY) != 0u;             // daddr is a Host-header id: own key space, cold tier
       p &= 0x3Fu;
       const uint32_t cls = shr_clamp(kProtoLut, 3u * p);
       // a row is built unless the class says "payload parser decides" and the parser said no (bit 30 of mw)
@@ -320,8 +494,11 @@ ingest_pairs_v7_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
       const bool rv = (cls & 4u) && (mw & ((uint32_t)ALZ_MF_METHOD_MASK << 24)) == (2u << 24);   // DELIVER / PUSHED_EVENT
       const bool err = p == ALZ_PROTO_HTTP && ((mw & 0xFFFFu) - 500u) < 100u;
       key[u] = ((uint64_t)w[u][1] << 32) | w[u][0];               // make_pair_key: the record's first two words as they lie
-      const uint32_t bucket = latency_bucket_rz(dur[u]);
+      const uint32_t bucket = latency_bucket_rz(dur);
       const uint32_t kind = hk ? kPairHost : rv ? kPairRev : kPairFwd;
+      const uint32_t dhi = (uint32_t)(dur >> 32);
+      dlo[u] = (uint32_t)dur;
+      meta[u] = bucket | (kind << 6) | (err ? 0x100u : 0u) | (dhi << 9);
 
       // per-CTA table: two index probes, the matching entry names the row and its histogram window
       const uint32_t h = table_hash(key[u]);
@@ -344,46 +521,50 @@ ingest_pairs_v7_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
           atomicSub(&row[d >> 1], 0x8000u << sh);
         }
         uint32_t* lat = row + 9u + 2u * (lane & 1u);
-        const uint32_t lo = (uint32_t)dur[u], dhi = (uint32_t)(dur[u] >> 32);
-        const uint32_t oldl = atomicAdd(&lat[0], lo);
-        const bool carry = oldl > ~lo;                                   // out of the low word
+        const uint32_t oldl = atomicAdd(&lat[0], dlo[u]);
+        const bool carry = oldl > ~dlo[u];                               // out of the low word
         if (carry || dhi != 0u) atomicAdd(&lat[1], dhi + (carry ? 1u : 0u));
         if (err) atomicAdd(&row[8], 1u);
         ++n_hit;
       }
-      const bool cold = act && !hit;
-      meta[u] = bucket | (kind << 6) | (err ? 0x100u : 0u) | (cold ? 0x80000000u : 0u);
-      ent[u] = make_uint4(0u, 0u, kNoRow, 0u);
-      if (cold) ent[u] = __ldcg(reinterpret_cast<const uint4*>(&pairs.dict_of(kind)[pair_hash(key[u]) & pairs.mask_of(kind)]));
-    }
-    pc1 = PROF_NOW();
-    PROF_ADD(5, pc1 - pc0);
-    // cold tier: a home-slot hit is reduced into its row at once, anything else joins the slow queue
-#pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const bool cold = (meta[u] & 0x80000000u) != 0u;
-      n_cold += __popc(__ballot_sync(0xFFFFFFFFu, cold));
-      const uint32_t bucket = meta[u] & 0x3Fu, kind = (meta[u] >> 6) & 3u;
-      const bool err = (meta[u] & 0x100u) != 0u;
-      const bool home = cold && ent[u].x == (uint32_t)key[u] && ent[u].y == (uint32_t)(key[u] >> 32) && ent[u].z < kDropRow &&
-                        key[u] != kEmptyKey;
-      if (home) global_add(pairs, ent[u].z, bucket, dur[u], err);
-      const uint32_t dhi = (uint32_t)(dur[u] >> 32);
-      const bool huge = dhi >= (1u << 23);                               // does not fit the queue entry: rare beyond words
-      if (cold && !home && huge) slow_one<kRows>(key[u], dur[u], bucket, kind, err, pairs, s, ep, ep_mask, &lost, &unresolved);
-      slow.push(cold && !home && !huge, key[u], (uint32_t)dur[u], (meta[u] & 0x1FFu) | (dhi << 9), lane_lt);
-      __syncwarp();
-      if (slow.count >= 32u) {
-        const long long s0 = PROF_NOW();
-        slow_batch<kRows>(slow, 32u, pairs, s, ep, ep_mask, &lost, &unresolved);
-        PROF_ADD(4, PROF_NOW() - s0);
-        PROF_ADD(7, 1);
+      coldf[u] = act && !hit;
+      // a duration that does not fit the queue entry (>= 2^55 ns) is handled on the spot: rare beyond words
+      if (coldf[u] && dhi >= (1u << 23)) {
+        ++n_cold;                    // per-lane here, folded into the warp total below
+        slow_one<kRows>(key[u], dur, bucket, kind, err, pairs, s, ep, ep_mask, &lost, &unresolved);
+        coldf[u] = false;
       }
     }
-    PROF_ADD(3, PROF_NOW() - pc1);
+    uint32_t pushed = 0;
+#pragma unroll
+    for (int u = 0; u < kU; ++u) pushed += cold.push(coldf[u], key[u], dlo[u], meta[u], lane_lt);
+    __syncwarp();
+    pc0 = PROF_NOW();
+    PROF_ADD(5, pc0 - pc1);
+    // a batch is consumed when the next one is ready to be requested
+    while (cold.count - probing >= 32u) {
+      if (probing) {
+        cold_consume<kRows>(cold, probing, probe, slow, pairs, s, ep, ep_mask, lane_lt, &lost, &unresolved, &t_wait, &t_slow);
+        probing = 0;
+        PROF_ADD(7, 1);
+      }
+      cold_issue(cold, 32u, pairs, s, probe, probe_a);
+      probing = 32u;
+    }
+    PROF_ADD(3, PROF_NOW() - pc0);
+    // cold pushes are warp totals: keep them in lane 0's counter only
+    if (lane == 0) n_cold += pushed;
+  }
+  if (probing) cold_consume<kRows>(cold, probing, probe, slow, pairs, s, ep, ep_mask, lane_lt, &lost, &unresolved, &t_wait, &t_slow);
+  if (cold.count) {
+    const uint32_t rest = cold.count;
+    cold_issue(cold, rest, pairs, s, probe, probe_a);
+    cold_consume<kRows>(cold, rest, probe, slow, pairs, s, ep, ep_mask, lane_lt, &lost, &unresolved, &t_wait, &t_slow);
   }
   while (slow.count) slow_batch<kRows>(slow, min(slow.count, 32u), pairs, s, ep, ep_mask, &lost, &unresolved);
   PROF_ADD(0, PROF_NOW() - p_begin);
+  PROF_ADD(2, t_wait);
+  PROF_ADD(4, t_slow);
   PROF_FLUSH();
   __syncthreads();
 
@@ -427,16 +608,33 @@ ingest_pairs_v7_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
   }
   for (int o = 16; o > 0; o >>= 1) {
     n_hit += __shfl_xor_sync(0xFFFFFFFFu, n_hit, o);
+    n_cold += __shfl_xor_sync(0xFFFFFFFFu, n_cold, o);
     lost += __shfl_xor_sync(0xFFFFFFFFu, lost, o);
     unresolved += __shfl_xor_sync(0xFFFFFFFFu, unresolved, o);
   }
-  // events that built no request row = events seen - hot hits - cold events (the last two are counted anyway)
+  // events that built no request row = events seen - hot hits - cold events (the last two are counted anyway);
+  // n_live is the same in every lane
   const uint32_t not_request = n_live - n_cold - n_hit;
+  if (kWin) for (int o = 16; o > 0; o >>= 1) n_late += __shfl_xor_sync(0xFFFFFFFFu, n_late, o);
   if (lane == 0) {
     if (not_request) atomicAdd(&ctr->not_request, (unsigned long long)not_request);
     if (lost) atomicAdd(&ctr->capacity_events, (unsigned long long)lost);
     if (unresolved) atomicAdd(&ctr->src_unresolved, (unsigned long long)unresolved);
+    if (kWin && n_late) atomicAdd(&ctr->late_events, (unsigned long long)n_late);
   }
+}
+
+// open the first window on the first record ever submitted: epoch = (write_time + off) / len, docs/SPEC.md §8
+// (off = FirstUserspaceTime - FirstKernelTime, aggregator/data.go:1740-1743)
+__global__ void win_init_kernel(const uint32_t* __restrict__ recs, uint64_t n, WinClock* win, uint64_t off) {
+  if (threadIdx.x != 0 || blockIdx.x != 0 || n == 0 || win->ready) return;
+  const uint64_t wt = ((uint64_t)recs[7] << 32) | recs[6];
+  const uint64_t e = (wt + off) / win->len;
+  win->lo = e * win->len - off;
+  win->ready = 1ull;
+}
+__global__ void win_advance_kernel(WinClock* win) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && win->ready) win->lo += win->len;
 }
 
 // ---- hot-pair feedback: after a fold, pick the pairs that took the most events -----
@@ -473,45 +671,60 @@ __global__ void __launch_bounds__(256) hot_emit_kernel(AccTable pairs, HotState*
   }
 }
 
-template <int kWarps, int kRecWords>
+template <int kWarps, int kRecWords, bool kWin = false>
 void launch_variant(const void* recs, uint64_t n, const AccTable& pairs, Counters* ctr, const HotState* hot,
-                    const EpEntry* ep, uint32_t ep_mask, const uint64_t* dur_ovf, int sms, cudaStream_t s) {
-  using L = Layout<kWarps>;
+                    const EpEntry* ep, uint32_t ep_mask, const uint32_t* bloom, const uint64_t* dur_ovf, int sms,
+                    cudaStream_t s, const WinClock* win = nullptr, void* defer_buf = nullptr, uint32_t defer_cap = 0) {
+  using L = Layout<kWarps, kRecWords>;
   // per device (a process may drive several GPUs), so not cached in a static
-  cudaFuncSetAttribute(ingest_pairs_v7_kernel<kWarps, kRecWords>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaFuncSetAttribute(ingest_pairs_v8_kernel<kWarps, kRecWords, kWin>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)L::kBytes);
-  ingest_pairs_v7_kernel<kWarps, kRecWords><<<(unsigned)sms, kWarps * 32, L::kBytes, s>>>(
-      (const uint32_t*)recs, n, pairs, ctr, hot, ep, ep_mask, dur_ovf);
+  ingest_pairs_v8_kernel<kWarps, kRecWords, kWin><<<(unsigned)sms, kWarps * 32, L::kBytes, s>>>(
+      (const uint32_t*)recs, n, pairs, ctr, hot, ep, ep_mask, bloom, dur_ovf, win, (uint4*)defer_buf, defer_cap);
 }
 
-constexpr int kDefaultWarps = 32;
+constexpr int kDefaultWarps = 16;
 
 }  // namespace
 
-uint32_t ingest_table_rows() { return Layout<kDefaultWarps>::kRows; }
+uint32_t ingest_table_rows() { return Layout<kDefaultWarps, 8>::kRows; }
 
 void launch_ingest_pairs(const alz_l7_rec* recs, uint64_t n, const AccTable& pairs, Counters* ctr,
-                         const HotState* hot, const EpEntry* ep, uint32_t ep_mask, int sms, cudaStream_t s) {
+                         const HotState* hot, const EpEntry* ep, uint32_t ep_mask, const uint32_t* bloom, int sms,
+                         cudaStream_t s) {
   if (n == 0) return;
   // ALZ_INGEST_SHAPE: CTA shape for profiling runs (default = the measured best)
   static const int shape = [] { const char* v = getenv("ALZ_INGEST_SHAPE"); return v ? atoi(v) : 0; }();
   switch (shape) {
-    case 1: launch_variant<24, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, nullptr, sms, s); break;
-    case 2: launch_variant<16, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, nullptr, sms, s); break;
-    default: launch_variant<kDefaultWarps, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, nullptr, sms, s); break;
+    case 1: launch_variant<12, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
+    case 2: launch_variant<20, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
+    case 3: launch_variant<24, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
+    default: launch_variant<kDefaultWarps, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
   }
 }
 
 void launch_ingest_pairs_rec16(const alz_l7_rec16* recs, uint64_t n, const uint64_t* dur_ovf, const AccTable& pairs,
-                               Counters* ctr, const HotState* hot, const EpEntry* ep, uint32_t ep_mask, int sms,
-                               cudaStream_t s) {
+                               Counters* ctr, const HotState* hot, const EpEntry* ep, uint32_t ep_mask,
+                               const uint32_t* bloom, int sms, cudaStream_t s) {
   if (n == 0) return;
-  launch_variant<kDefaultWarps, 4>(recs, n, pairs, ctr, hot, ep, ep_mask, dur_ovf, sms, s);
+  launch_variant<kDefaultWarps, 4>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, dur_ovf, sms, s);
 }
+
+// time-cut windows: `win` = device WinClock {lo, len, ready}; records beyond the open window land in defer_buf
+void launch_ingest_pairs_windowed(const alz_l7_rec* recs, uint64_t n, const AccTable& pairs, Counters* ctr,
+                                  const HotState* hot, const EpEntry* ep, uint32_t ep_mask, const uint32_t* bloom,
+                                  uint64_t* win, uint64_t off, alz_l7_rec* defer_buf, uint32_t defer_cap, int sms,
+                                  cudaStream_t s) {
+  if (n == 0) return;
+  win_init_kernel<<<1, 32, 0, s>>>((const uint32_t*)recs, n, (WinClock*)win, off);
+  launch_variant<kDefaultWarps, 8, true>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s,
+                                         (const WinClock*)win, defer_buf, defer_cap);
+}
+void launch_window_advance(uint64_t* win, cudaStream_t s) { win_advance_kernel<<<1, 32, 0, s>>>((WinClock*)win); }
 
 // after fold_pairs_kernel(pairs, ..., hot->bins): choose next window's hot list
 void launch_hot_select(const AccTable& pairs, HotState* hot, int sms, cudaStream_t s) {
-  hot_emit_kernel<<<(unsigned)sms * 2, 256, 0, s>>>(pairs, hot, Layout<kDefaultWarps>::kPreload);
+  hot_emit_kernel<<<(unsigned)sms * 2, 256, 0, s>>>(pairs, hot, Layout<kDefaultWarps, 8>::kPreload);
 }
 
 }  // namespace alz

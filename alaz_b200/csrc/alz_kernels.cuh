@@ -7,10 +7,16 @@ namespace alz {
 void launch_ingest_pairs_v1(const alz_l7_rec* recs, uint64_t n, const AccTable& pairs, Counters* ctr,
                             const EpEntry* ep, uint32_t ep_mask, int sms, cudaStream_t s);
 void launch_ingest_pairs(const alz_l7_rec* recs, uint64_t n, const AccTable& pairs, Counters* ctr,
-                            const HotState* hot, const EpEntry* ep, uint32_t ep_mask, int sms, cudaStream_t s);
+                         const HotState* hot, const EpEntry* ep, uint32_t ep_mask, const uint32_t* bloom, int sms,
+                         cudaStream_t s);
 void launch_ingest_pairs_rec16(const alz_l7_rec16* recs, uint64_t n, const uint64_t* dur_ovf, const AccTable& pairs,
-                                  Counters* ctr, const HotState* hot, const EpEntry* ep, uint32_t ep_mask, int sms,
+                               Counters* ctr, const HotState* hot, const EpEntry* ep, uint32_t ep_mask,
+                               const uint32_t* bloom, int sms, cudaStream_t s);
+void launch_ingest_pairs_windowed(const alz_l7_rec* recs, uint64_t n, const AccTable& pairs, Counters* ctr,
+                                  const HotState* hot, const EpEntry* ep, uint32_t ep_mask, const uint32_t* bloom,
+                                  uint64_t* win, uint64_t off, alz_l7_rec* defer_buf, uint32_t defer_cap, int sms,
                                   cudaStream_t s);
+void launch_window_advance(uint64_t* win, cudaStream_t s);
 uint32_t ingest_table_rows();
 void launch_hot_select(const AccTable& pairs, HotState* hot, int sms, cudaStream_t s);
 void launch_ingest_eager(const alz_l7_rec* recs, uint64_t n, const EpEntry* ep, uint32_t ep_mask,

@@ -37,7 +37,7 @@ uint8_t MethodEnum(uint8_t proto, const std::string& m) {
     default: return 0;
   }
 }
-const char* NodeTypeName(uint8_t t) {   // aggregator/data.go:42-44
+const char* NodeTypeName(uint8_t t) {   // aggregator/data.go:42-44 (a Host-header keyed destination is OUTBOUND too)
   return t == ALZ_NODE_POD ? "pod" : t == ALZ_NODE_SVC ? "service" : "outbound";
 }
 }  // namespace
@@ -53,6 +53,30 @@ std::string Aggregator::FormatIPv4(uint32_t ip) {
   char buf[16];
   snprintf(buf, sizeof buf, "%u.%u.%u.%u", ip >> 24, (ip >> 16) & 255u, (ip >> 8) & 255u, ip & 255u);
   return buf;
+}
+
+// parseHttpPayload, aggregator/data.go:508-531, the hostHeader part: the request is split on "\n"; among the
+// lines after the first, the first one that starts with "Host:" AND splits on single spaces into >= 2 parts
+// yields parts[1] minus a trailing "\r". A "Host:" line with fewer parts is skipped and the scan goes on.
+std::string Aggregator::ParseHttpHostHeader(const std::string& payload) {
+  size_t i = payload.find('\n');
+  while (i != std::string::npos) {
+    const size_t b = i + 1;
+    const size_t e = payload.find('\n', b);
+    const size_t len = (e == std::string::npos ? payload.size() : e) - b;
+    if (len >= 5 && payload.compare(b, 5, "Host:") == 0) {
+      const size_t sp = payload.find(' ', b);
+      if (sp != std::string::npos && sp < b + len) {            // at least two parts
+        size_t q = sp + 1, end = payload.find(' ', q);
+        if (end == std::string::npos || end > b + len) end = b + len;
+        std::string host = payload.substr(q, end - q);
+        if (!host.empty() && host.back() == '\r') host.pop_back();
+        return host;
+      }
+    }
+    i = e;
+  }
+  return std::string();
 }
 
 Aggregator::Aggregator(DataStore* ds, const AggregatorConfig& cfg) : ds_(ds), cfg_(cfg) {
@@ -174,6 +198,23 @@ void Aggregator::ProcessL7(const L7Event& e) {
                              (e.PayloadRejected ? ALZ_MF_PAYLOAD_REJECT : 0));
   r.duration_ns = e.Duration;
   r.write_time_ns = e.WriteTimeNs;
+  // setFromToV2's third-party branch (data.go:851-854): an HTTP destination that is neither service nor pod is
+  // keyed by the request's Host header when there is one. The maps consulted are this adapter's mirror of the
+  // tables it has upserted, in the same order as the events, so the decision is the reference's.
+  if (r.protocol == ALZ_PROTO_HTTP && !e.Payload.empty() && !svcs_.ip_to_id.count(e.Daddr) && !pods_.ip_to_id.count(e.Daddr)) {
+    const std::string host = ParseHttpHostHeader(e.Payload);
+    if (!host.empty()) {
+      bool is_ip = false;
+      const uint32_t ip = ParseIPv4(host, &is_ip);
+      if (is_ip) r.daddr = ip;   // a header that is itself a dotted quad is the same node as that raw daddr (same ToUID string)
+      else {
+        auto it = host_ids_.find(host);
+        if (it == host_ids_.end()) { it = host_ids_.emplace(host, (uint32_t)host_names_.size()).first; host_names_.push_back(host); }
+        r.daddr = it->second;
+        r.protocol |= ALZ_PROTO_F_HOSTKEY;
+      }
+    }
+  }
   if (batch_n_ >= cfg_.BatchSize) SubmitBatch();
 }
 
@@ -212,6 +253,7 @@ int Aggregator::Flush(bool with_scores) {
     auto uid = [&](uint8_t t, uint32_t v) -> std::string {
       if (t == ALZ_NODE_POD) return v < pods_.names.size() ? pods_.names[v] : std::string("?");
       if (t == ALZ_NODE_SVC) return v < svcs_.names.size() ? svcs_.names[v] : std::string("?");
+      if (t == ALZ_NODE_OUTBOUND_HOST) return v < host_names_.size() ? host_names_[v] : std::string("?");   // data.go:852
       return FormatIPv4(v);   // outbound: the raw daddr string (data.go:862)
     };
     w.FromType = NodeTypeName(o.from_type); w.FromUID = uid(o.from_type, o.from);

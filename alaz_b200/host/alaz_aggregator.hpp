@@ -32,6 +32,7 @@ struct L7Event {
   uint32_t Saddr = 0, Daddr = 0;
   uint16_t Sport = 0, Dport = 0;
   bool PayloadRejected = false;   // the Go-side SQL/Mongo parser returned an error (data.go:1252, 1288, 1328)
+  std::string Payload;            // HTTP only: Payload[0:PayloadSize], read for its Host header (data.go:1213)
 };
 
 // ebpf/tcp_state/tcp.go:75-84
@@ -98,6 +99,8 @@ class Aggregator {
 
   static uint32_t ParseIPv4(const std::string& s, bool* ok);   // "a.b.c.d" -> the integer IntToIPv4 takes
   static std::string FormatIPv4(uint32_t ip);
+  // parseHttpPayload's hostHeader (aggregator/data.go:508-531): "" when the reference finds none
+  static std::string ParseHttpHostHeader(const std::string& payload);
 
  private:
   int SubmitBatch();   // requires mu_
@@ -123,6 +126,8 @@ class Aggregator {
   std::mutex mu_;
   uint64_t dropped_events_ = 0;
   Interner pods_, svcs_;
+  std::unordered_map<std::string, uint32_t> host_ids_;   // Host header text -> dense id (ALZ_NODE_OUTBOUND_HOST)
+  std::vector<std::string> host_names_;
   std::vector<alz_edge_out> out_;
   std::vector<float> scores_;
 };

@@ -193,7 +193,8 @@ typedef struct alz_stats {
   uint64_t collective_bytes_last; /* bytes this rank contributed to / received from the last window's collective */
   uint64_t flush_local_us_last;   /* device time of the last flush up to the cross-rank merge */
   uint64_t merge_us_last;         /* device time of the last cross-rank merge (0 on one rank) */
-  uint64_t _reserved[2];
+  uint64_t late_events;           /* time-cut windows: records older than the open window (cumulative) */
+  uint64_t deferred_events;       /* time-cut windows: records waiting on the device for their window */
 } alz_stats;
 
 typedef struct alz_handle alz_handle;
@@ -257,6 +258,20 @@ int alz_window_flush_device(alz_handle* h, const alz_edge_out** dev_edges, size_
  * and the merged rows stay fetchable here until the next flush. */
 int alz_window_fetch(alz_handle* h, alz_edge_out* out, size_t cap, size_t* n_out);
 int alz_get_stats(alz_handle* h, alz_stats* out);
+
+/* ---- time-cut windows (docs/SPEC.md §8) ---------------------
+ * By default a window is whatever was submitted between two flushes. After alz_window_clock the records' own
+ * write_time decides: epoch(t) = convertKernelTimeToUserspaceTime(t) / window_ns with
+ * convertKernelTimeToUserspaceTime(t) = first_user_ns - (first_kernel_ns - t) (aggregator/data.go:1740-1743;
+ * l7_req.FirstKernelTime / FirstUserspaceTime). The open window is the epoch of the first record submitted
+ * afterwards. A record of a later epoch is kept on the device and submitted again by the flush that opens its
+ * window; a record of an earlier epoch is late: it is reduced into the open window and counted
+ * (alz_stats.late_events). Each alz_window_flush* closes the open epoch and opens the next one. Only 32-byte
+ * records carry a write time: packed submits return ALZ_E_STATE while the clock is set. window_ns = 0 turns
+ * the clock off again. */
+int alz_window_clock(alz_handle* h, uint64_t first_kernel_ns, uint64_t first_user_ns, uint64_t window_ns);
+/* epoch of the open window; ALZ_E_STATE until the first record has been submitted */
+int alz_window_epoch(alz_handle* h, uint64_t* epoch);
 
 /* ---- GNN anomaly pass over the last flushed window (docs/SPEC.md §6) -------- */
 int alz_gnn_score(alz_handle* h, float* edge_scores, size_t cap, size_t* n_out);

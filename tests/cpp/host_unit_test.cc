@@ -23,6 +23,18 @@ int main() {
   CHECK(alaz::Aggregator::FormatIPv4(0x08080808u) == "8.8.8.8");
   for (uint32_t ip : {0u, 0x7F000001u, 0xC0A80164u, 0xFFFFFFFFu})
     CHECK(alaz::Aggregator::ParseIPv4(alaz::Aggregator::FormatIPv4(ip), &ok) == ip && ok);
+  // parseHttpPayload's Host header (aggregator/data.go:508-531); the same vectors pin the oracle in tests/test_oracle.py
+  using A = alaz::Aggregator;
+  CHECK(A::ParseHttpHostHeader("GET /x HTTP/1.1\r\nHost: example.com\r\nAccept: */*\r\n\r\n") == "example.com");
+  CHECK(A::ParseHttpHostHeader("GET /x HTTP/1.1\nHost: a.b:8080\n\n") == "a.b:8080");
+  CHECK(A::ParseHttpHostHeader("GET /x HTTP/1.1\r\nAccept: */*\r\n\r\n") == "");
+  CHECK(A::ParseHttpHostHeader("Host: first.line\r\nX: y\r\n") == "");                   // lines[0] is never looked at
+  CHECK(A::ParseHttpHostHeader("GET / HTTP/1.1\r\nHost:nospace.com\r\nHost: second.com\r\n") == "second.com");
+  CHECK(A::ParseHttpHostHeader("GET / HTTP/1.1\r\nHost:  two.spaces\r\n") == "");          // parts[1] is empty
+  CHECK(A::ParseHttpHostHeader("GET / HTTP/1.1\r\nhost: lower.case\r\n") == "");          // HasPrefix is case-sensitive
+  CHECK(A::ParseHttpHostHeader("GET / HTTP/1.1\r\nHost: h.com extra words\r\n") == "h.com");
+  CHECK(A::ParseHttpHostHeader("GET / HTTP/1.1\r\nX-Host: no\r\nHost: yes.com") == "yes.com"); // last line without newline
+  CHECK(A::ParseHttpHostHeader("") == "");
   NullStore ds;
   alaz::AggregatorConfig cfg;
   alaz::Aggregator a(&ds, cfg);

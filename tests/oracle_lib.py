@@ -44,6 +44,11 @@ def lib():
         L.orc_table_upsert.argtypes = [vp, C.c_int, u32, u32]
         L.orc_table_erase.argtypes = [vp, C.c_int, u32]
         L.orc_process_l7.argtypes = [vp, vp, sz, C.c_int]
+        L.orc_process_l7_hosts.argtypes = [vp, vp, sz, vp, C.POINTER(C.c_char_p), sz]
+        L.orc_parse_http_host.argtypes = [C.c_char_p, sz, C.c_char_p, sz]
+        L.orc_parse_http_host.restype = sz
+        L.orc_epoch.argtypes = [u64, u64, u64, u64]
+        L.orc_epoch.restype = u64
         L.orc_edges.argtypes = [vp, vp, sz]
         L.orc_edges.restype = sz
         L.orc_window_reset.argtypes = [vp]
@@ -116,6 +121,13 @@ class Oracle:
         recs = np.ascontiguousarray(recs, dtype=abi.L7_REC)
         self.L.orc_process_l7(self.h, _ptr(recs), len(recs), nthreads)
 
+    def process_hosts(self, recs, host_idx, names):
+        """Events with their HTTP Host header: host_idx[i] = 0 (none) or 1 + index into names."""
+        recs = np.ascontiguousarray(recs, dtype=abi.L7_REC)
+        host_idx = np.ascontiguousarray(host_idx, dtype=np.uint32)
+        self._names = (C.c_char_p * max(1, len(names)))(*[n.encode() for n in names])   # must outlive edges()
+        self.L.orc_process_l7_hosts(self.h, _ptr(recs), len(recs), _ptr(host_idx), self._names, len(names))
+
     def edges(self):
         n = self.L.orc_edges(self.h, None, 0)
         out = np.zeros(n, dtype=abi.EDGE_OUT)
@@ -174,6 +186,16 @@ class FastCpu:
         st = abi.Stats()
         self.L.orc_fast_stats(self.h, C.byref(st))
         return st.as_dict()
+
+
+def parse_http_host(payload: bytes) -> str:
+    out = C.create_string_buffer(1100)
+    lib().orc_parse_http_host(payload, len(payload), out, len(out))
+    return out.value.decode()
+
+
+def epoch(first_kernel, first_user, window_ns, write_time):
+    return int(lib().orc_epoch(int(first_kernel), int(first_user), int(window_ns), int(write_time)))
 
 
 def bucket(d):

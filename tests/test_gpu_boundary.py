@@ -132,3 +132,46 @@ def test_first_window_and_shifting_traffic():
         assert edges_equal(got, exp), f"window {w}: " + explain_diff(got, exp)
         o.reset_window()
     h.close()
+
+
+def test_host_header_keyed_outbound_nodes():
+    """an HTTP destination that is neither service nor pod is keyed by the request's Host header
+    (setFromToV2, aggregator/data.go:851-854). The caller (the Go adapter; here numpy) decides that from its own
+    copy of the tables and marks the record ALZ_PROTO_F_HOSTKEY with the header's id in `daddr`."""
+    S, N = 300, 300_000
+    t = ol.Topo(S, seed=404, mix=abi.MIX_ALL)
+    ev = t.events(0, N)
+    rng = np.random.default_rng(7)
+    names = [f"host{k}.example.org" for k in range(40)] + ["203.0.113.9", "8.8.8.8"]
+    host_idx = np.where(rng.random(N) < 0.5, rng.integers(1, len(names) + 1, N), 0).astype(np.uint32)
+    o = ol.Oracle(); o.load_tables(t.pod_ip, t.svc_ip)
+    o.process_hosts(ev, host_idx, names)
+    # what the adapter does with each event before it packs the record
+    in_cluster = np.isin(ev["daddr"], np.concatenate([t.pod_ip, t.svc_ip]))
+    use = (host_idx > 0) & (ev["protocol"] == abi.PROTO_HTTP) & ~in_cluster
+    rec = ev.copy()
+    is_ip = np.array([n[0].isdigit() for n in names])
+    name_ip = np.array([abi.ip(n) if n[0].isdigit() else 0 for n in names], dtype=np.uint32)
+    hid = host_idx.astype(np.int64) - 1
+    as_ip = use & is_ip[np.maximum(hid, 0)]
+    as_host = use & ~is_ip[np.maximum(hid, 0)]
+    rec["daddr"][as_ip] = name_ip[hid[as_ip]]
+    rec["daddr"][as_host] = hid[as_host]
+    rec["protocol"][as_host] |= abi.PROTO_F_HOSTKEY
+    assert as_host.sum() > 1000 and as_ip.sum() > 10
+    for flags in (0, abi.CFG_EAGER_JOIN, abi.CFG_NO_SMEM_CACHE):
+        h = capi.Handle(max_endpoints=4 * S, max_pairs=1 << 16, flags=flags)
+        h.load_tables(t.pod_ip, t.svc_ip)
+        h.submit(rec[: N // 2]); h.submit(rec[N // 2:])
+        got, exp = h.flush(), o.edges()
+        assert edges_equal(got, exp), explain_diff(got, exp)
+        assert (got["to_type"] == abi.NODE_OUTBOUND_HOST).sum() > 50
+        h.close()
+    # the same through 16-byte packed records (the flag travels in the protocol byte)
+    r16, ovf = capi.pack_l7(rec)
+    h = capi.Handle(max_endpoints=4 * S, max_pairs=1 << 16)
+    h.load_tables(t.pod_ip, t.svc_ip)
+    h.submit_packed(r16, ovf)
+    got = h.flush()
+    assert edges_equal(got, o.edges()), explain_diff(got, o.edges())
+    h.close()

@@ -76,3 +76,62 @@ def test_accumulator_arithmetic_edges(flags):
         assert int(got["lat_sum_ns"][0]) == sum(durs) % (1 << 64)
         o.reset_window()
     h.close()
+
+
+def test_time_cut_windows_follow_the_records_clock():
+    """SURVEY §8 row R13 / docs/SPEC.md §8: with alz_window_clock set, the window of a record is
+    convertKernelTimeToUserspaceTime(write_time) / window_ns (aggregator/data.go:1740-1743), whatever the batch
+    boundaries: records of later epochs wait on the device, each flush closes one epoch, late records join the
+    open window and are counted."""
+    S, N = 800, 1_200_000
+    t = ol.Topo(S, seed=909, mix=abi.MIX_ALL)
+    ev = t.events(0, N)
+    wt = ev["write_time_ns"].astype(np.uint64)
+    fk, fu = np.uint64(int(wt[0]) - 12345), np.uint64(1_700_000_000_123_456_789)
+    W = np.uint64((int(wt[-1]) - int(wt[0])) // 4 + 1)
+    epoch = (wt + (fu - fk)) // W
+    assert ol.epoch(int(fk), int(fu), int(W), int(wt[777])) == int(epoch[777])
+    e0, e_last = int(epoch.min()), int(epoch.max())
+    assert epoch[0] == e0 and 3 <= e_last - e0 <= 5
+    h = capi.Handle(max_endpoints=4 * S, max_pairs=1 << 16)
+    h.load_tables(t.pod_ip, t.svc_ip)
+    h.window_clock(int(fk), int(fu), int(W))
+    # batches that ignore the window boundaries, one of them from device memory
+    cuts = [0, 100_003, 350_000, 350_001, 900_017, N]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        if a == 350_001:
+            d = h.dev_alloc((b - a) * 32)
+            h.h2d(d, ev[a:b])
+            h.submit_device(d, b - a)
+            h.sync()
+            h.dev_free(d)
+        else:
+            h.submit(ev[a:b])
+    assert h.window_epoch() == e0
+    st = h.stats()
+    assert st["deferred_events"] == int((epoch > e0).sum()) and st["late_events"] == 0
+    late = ev[:5000].copy()            # records of epoch e0 that show up after e0 was closed
+    for k, e in enumerate(range(e0, e_last + 1)):
+        got = h.flush()
+        o = ol.Oracle(); o.load_tables(t.pod_ip, t.svc_ip)
+        o.process(ev[epoch == e], 4)
+        if k == 1:
+            o.process(late)            # late records are reduced into the window that was open when they came
+        exp = o.edges()
+        assert edges_equal(got, exp), f"epoch {e}: " + explain_diff(got, exp)
+        if k == 0:
+            assert h.window_epoch() == e0 + 1
+            h.submit(late)
+            assert h.stats()["late_events"] == len(late)
+    assert len(h.flush()) == 0
+    st = h.stats()
+    assert st["deferred_events"] == 0 and st["events_in"] == N + len(late)
+    # packed records carry no time: refused while the clock is set; the clock can be switched off between windows
+    r16, ovf = capi.pack_l7(ev[:10])
+    with pytest.raises(capi.AlzError) as e:
+        h.submit_packed(r16, ovf)
+    assert e.value.status == abi.E_STATE
+    h.window_clock(0, 0, 0)
+    h.submit_packed(r16, ovf)
+    assert int(h.flush()["count"].sum()) == h.stats()["rows_emitted"] - (st["rows_emitted"])
+    h.close()

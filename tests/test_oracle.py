@@ -104,6 +104,60 @@ def test_fair_cpu_arm_is_bit_exact_to_the_faithful_port(mix):
         f.close()
 
 
+HOST_VECTORS = [   # parseHttpPayload's hostHeader, aggregator/data.go:508-531 (same vectors: tests/cpp/host_unit_test.cc)
+    (b"GET /x HTTP/1.1\r\nHost: example.com\r\nAccept: */*\r\n\r\n", "example.com"),
+    (b"GET /x HTTP/1.1\nHost: a.b:8080\n\n", "a.b:8080"),
+    (b"GET /x HTTP/1.1\r\nAccept: */*\r\n\r\n", ""),
+    (b"Host: first.line\r\nX: y\r\n", ""),
+    (b"GET / HTTP/1.1\r\nHost:nospace.com\r\nHost: second.com\r\n", "second.com"),
+    (b"GET / HTTP/1.1\r\nHost:  two.spaces\r\n", ""),
+    (b"GET / HTTP/1.1\r\nhost: lower.case\r\n", ""),
+    (b"GET / HTTP/1.1\r\nHost: h.com extra words\r\n", "h.com"),
+    (b"GET / HTTP/1.1\r\nX-Host: no\r\nHost: yes.com", "yes.com"),
+    (b"", ""),
+]
+
+
+def test_parse_http_host_header_vectors():
+    for payload, want in HOST_VECTORS:
+        assert ol.parse_http_host(payload) == want, payload
+
+
+def test_host_header_keys_outbound_destinations_only():
+    # setFromToV2 :838-866: service first, then pod, then the Host header, then the raw daddr
+    o = ol.Oracle()
+    o.upsert(abi.TABLE_POD, abi.ip("10.0.0.1"), 1)
+    o.upsert(abi.TABLE_POD, abi.ip("10.0.0.2"), 2)
+    o.upsert(abi.TABLE_SVC, abi.ip("172.16.0.1"), 7)
+    names = ["api.example.com", "8.8.4.4"]
+    recs = np.zeros(6, dtype=abi.L7_REC)
+    recs["saddr"] = abi.ip("10.0.0.1")
+    recs["protocol"] = abi.PROTO_HTTP
+    recs["method_flags"] = 1
+    recs["duration_ns"] = 1000
+    recs["daddr"] = [abi.ip(x) for x in ("9.9.9.9", "9.9.9.9", "172.16.0.1", "10.0.0.2", "9.9.9.9", "8.8.4.4")]
+    recs[4]["protocol"] = abi.PROTO_REDIS            # only HTTP rows carry a Host header
+    host_idx = np.array([1, 0, 1, 1, 1, 2], dtype=np.uint32)
+    o.process_hosts(recs, host_idx, names)
+    e = o.edges()
+    got = {(int(x["to_type"]), int(x["to"])): int(x["count"]) for x in e}
+    assert got == {
+        (abi.NODE_OUTBOUND_HOST, 0): 1,                 # 9.9.9.9 with Host api.example.com
+        (abi.NODE_OUTBOUND, abi.ip("9.9.9.9")): 2,      # no header; and the REDIS row
+        (abi.NODE_SVC, 7): 1, (abi.NODE_POD, 2): 1,     # the header is ignored for in-cluster destinations
+        (abi.NODE_OUTBOUND, abi.ip("8.8.4.4")): 1,      # a header that is a dotted quad = that raw daddr node
+    }
+
+
+def test_epoch_is_the_references_time_conversion():
+    # convertKernelTimeToUserspaceTime (data.go:1740-1743): FirstUserspaceTime - (FirstKernelTime - t), uint64
+    fk, fu, w = 5_000_000_000, 1_700_000_000_000_000_000, 1_000_000_000
+    assert ol.epoch(fk, fu, w, fk) == fu // w
+    assert ol.epoch(fk, fu, w, fk + 999_999_999 - (fu % w)) == fu // w
+    assert ol.epoch(fk, fu, w, fk + w - (fu % w)) == fu // w + 1
+    assert ol.epoch(fk, fu, w, fk - 1) == (fu - 1) // w          # events older than the first sample
+
+
 def test_table_erase_and_update_follow_persist_go():
     # persist.go:55-71: UPDATE overwrites, DELETE removes
     o = ol.Oracle()
