@@ -93,9 +93,17 @@ __device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t* __restrict__
 }
 
 // per node: [out_count, in_count, out_err, in_err, out_lat, in_lat, out_deg, in_deg]
+// the node count stays on the device: every consumer reads it from there, the host never waits for it
+__global__ void node_count_kernel(const uint32_t* __restrict__ pos, const uint32_t* __restrict__ flags, uint32_t n2,
+                                  uint32_t* __restrict__ n_v) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *n_v = n2 ? pos[n2 - 1] + flags[n2 - 1] : 0u;
+}
+
 __global__ void edge_stats_kernel(const alz_edge_out* __restrict__ e, uint32_t n_e, const uint64_t* __restrict__ nodes,
-                                  uint32_t n_v, uint32_t* __restrict__ src_idx, uint64_t* __restrict__ dst_key,
-                                  unsigned long long* __restrict__ stats, uint32_t* __restrict__ in_deg) {
+                                  const uint32_t* __restrict__ n_v_ptr, uint32_t* __restrict__ src_idx,
+                                  uint64_t* __restrict__ dst_key, unsigned long long* __restrict__ stats,
+                                  uint32_t* __restrict__ in_deg) {
+  const uint32_t n_v = *n_v_ptr;
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_e; i += stride) {
     const uint32_t u = lower_bound_u64(nodes, n_v, node_key(e[i].from_type, e[i].from));
@@ -125,7 +133,8 @@ __global__ void csr_cols_kernel(const uint32_t* __restrict__ sorted_edge, const 
 __device__ __forceinline__ double ratio(uint64_t a, uint64_t b) { return b ? (double)a / (double)b : 0.0; }
 
 __global__ void node_features_kernel(const uint64_t* __restrict__ nodes, const unsigned long long* __restrict__ stats,
-                                     uint32_t n_v, float* __restrict__ h0) {
+                                     const uint32_t* __restrict__ n_v_ptr, float* __restrict__ h0) {
+  const uint32_t n_v = *n_v_ptr;
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n_v; v += stride) {
     const unsigned long long* s = stats + (size_t)v * 8;
@@ -142,7 +151,7 @@ __global__ void node_features_kernel(const uint64_t* __restrict__ nodes, const u
     f[7] = (float)log1p((double)s[7]);
     f[8] = kind == ALZ_NODE_POD ? 1.f : 0.f;
     f[9] = kind == ALZ_NODE_SVC ? 1.f : 0.f;
-    f[10] = kind == ALZ_NODE_OUTBOUND ? 1.f : 0.f;
+    f[10] = kind >= ALZ_NODE_OUTBOUND ? 1.f : 0.f;   // outbound, keyed by address or by Host header
     f[11] = 1.f;
     for (int j = 0; j < D; ++j) o[j] = j < 12 ? f[j] : 0.f;
   }
@@ -152,7 +161,8 @@ __global__ void node_features_kernel(const uint64_t* __restrict__ nodes, const u
 __global__ void __launch_bounds__(256) sage_layer_kernel(const float* __restrict__ h_in, float* __restrict__ h_out,
                                                          const uint32_t* __restrict__ rowptr,
                                                          const uint32_t* __restrict__ col, const float* __restrict__ W,
-                                                         const float* __restrict__ b, uint32_t n_v) {
+                                                         const float* __restrict__ b, const uint32_t* __restrict__ n_v_ptr) {
+  const uint32_t n_v = *n_v_ptr;
   __shared__ float sW[128 * D];
   __shared__ float sz[8][128];
   for (int i = threadIdx.x; i < 128 * D; i += blockDim.x) sW[i] = W[i];
@@ -205,7 +215,7 @@ constexpr uint32_t TM = 128, TK = 128, TN = 64;
 constexpr uint32_t A_BYTES = TM * TK * 4, B_BYTES = TN * TK * 4;
 constexpr uint32_t A_LBO = (TM / 8) * 128, A_SBO = 128;   // K-adjacent cores TM/8 cores apart; row groups adjacent
 constexpr uint32_t B_LBO = (TN / 8) * 128, B_SBO = 128;
-constexpr uint32_t SMEM_BYTES = 2 * A_BYTES + 2 * B_BYTES + 64;
+constexpr uint32_t SMEM_BYTES_OPERANDS = 2 * A_BYTES + 2 * B_BYTES;
 
 // byte offset of element (row r, k) in a K-major no-swizzle operand with R rows:
 // core matrix = 8 rows x 16 B; cores of one K-slice are contiguous over the row groups
@@ -240,18 +250,69 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
                : "r"(taddr) : "memory");
 }
 
+// ---- TMA-staged neighbour gather ---------------------------------------------------------
+// A warp builds 16 rows of the tile's operand. Every 256-byte feature row it needs — its nodes' own rows (16
+// consecutive rows of h_in: two bulk copies) and then the rows of their in-neighbours in CSR order — is fetched
+// by the TMA (cp.async.bulk global -> shared, completion on an mbarrier) into a two-slot ring of 8 rows per
+// warp: while the warp sums the rows of one slot, the copies of the next 8 neighbours are in flight, 16 rows
+// per warp regardless of the nodes' degrees (the edge range of the warp's rows is walked as one stream and cut
+// at the row boundaries). No register holds a row in flight, unlike plain loads.
+constexpr uint32_t RING_ROWS = 8, RING_BYTES = RING_ROWS * 256;
+constexpr uint32_t SMEM_TC = 2 * A_BYTES + 2 * B_BYTES + 8 * 2 * RING_BYTES + 256;
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_row(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// operand row r, columns kbase + lane and kbase + 32 + lane <- (z0, z1), split hi/lo in the UMMA layout
+__device__ __forceinline__ void put_pair(uint8_t* sA_hi, uint8_t* sA_lo, uint32_t r, uint32_t kbase, uint32_t lane,
+                                         float z0, float z1) {
+  const float z[2] = {z0, z1};
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const uint32_t k = kbase + (uint32_t)q * 32 + lane;
+    const uint32_t hi = to_tf32(z[q]);
+    const uint32_t lo = to_tf32(z[q] - __uint_as_float(hi));
+    const uint32_t off = op_off(r, k, TM);
+    *reinterpret_cast<uint32_t*>(sA_hi + off) = hi;
+    *reinterpret_cast<uint32_t*>(sA_lo + off) = lo;
+  }
+}
+
 __global__ void __launch_bounds__(256, 1) sage_layer_tc_kernel(const float* __restrict__ h_in, float* __restrict__ h_out,
                                                                const uint32_t* __restrict__ rowptr,
                                                                const uint32_t* __restrict__ col,
                                                                const uint8_t* __restrict__ Wcan,   // B_hi then B_lo
-                                                               const float* __restrict__ bias, uint32_t n_v) {
+                                                               const float* __restrict__ bias,
+                                                               const uint32_t* __restrict__ n_v_ptr) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t n_v = *n_v_ptr;
+  const uint32_t zero_rt = n_v >> 31;                    // node counts are < 2^31
   uint8_t* sA_hi = smem;
   uint8_t* sA_lo = smem + A_BYTES;
   uint8_t* sB = smem + 2 * A_BYTES;                      // B_hi, then B_lo
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + 2 * A_BYTES + 2 * B_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+  uint8_t* rings = smem + 2 * A_BYTES + 2 * B_BYTES;     // per warp: 2 slots of RING_ROWS rows
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rings + 8 * 2 * RING_BYTES);   // [0] MMA done, [1 + 2w + slot] ring slots
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 16);
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+  uint64_t* mbar = bars;
+  const float* ring = reinterpret_cast<const float*>(rings + warp * 2 * RING_BYTES);
+  const uint32_t ring_a = smem_u32(ring);
+  const uint32_t rbar = smem_u32(bars + 1 + 2 * warp);
+  uint32_t ring_uses[2] = {0u, 0u};
 
   for (uint32_t i = tid; i < 2 * B_BYTES / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(sB)[i] = reinterpret_cast<const uint4*>(Wcan)[i];
@@ -259,10 +320,10 @@ __global__ void __launch_bounds__(256, 1) sage_layer_tc_kernel(const float* __re
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" :: "r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(mbar)) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
+  if (tid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(mbar)) : "memory");
+  if (lane == 0) { mbar_init(rbar, 1u); mbar_init(rbar + 8u, 1u); }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -271,30 +332,71 @@ __global__ void __launch_bounds__(256, 1) sage_layer_tc_kernel(const float* __re
 
   for (uint32_t tile = blockIdx.x; tile * TM < n_v; tile += gridDim.x) {
     // ---- gather: warp w builds rows 16w .. 16w+15 of the operand (hi and lo parts)
-    for (uint32_t rr = 0; rr < 16; ++rr) {
-      const uint32_t r = warp * 16 + rr, v = tile * TM + r;
-      float z[4] = {0.f, 0.f, 0.f, 0.f};
-      if (v < n_v) {
-        const uint32_t beg = rowptr[v], end = rowptr[v + 1];
-        float m0 = 0.f, m1 = 0.f;
-        for (uint32_t p = beg; p < end; ++p) {          // CSR order: deterministic sum
-          const float* hu = h_in + (size_t)col[p] * D;
-          m0 += hu[lane];
-          m1 += hu[32 + lane];
-        }
-        const float inv = end > beg ? 1.0f / (float)(end - beg) : 0.f;
-        const float* hv = h_in + (size_t)v * D;
-        z[0] = hv[lane]; z[1] = hv[32 + lane]; z[2] = m0 * inv; z[3] = m1 * inv;
+    const uint32_t v0 = tile * TM + warp * 16;
+    const uint32_t n_rows = v0 < n_v ? min(16u, n_v - v0) : 0u;
+    // (1) the nodes' own rows: two bulk copies of up to 8 consecutive rows each
+    for (uint32_t half = 0; half < 2; ++half) {
+      const uint32_t cnt = n_rows > half * 8 ? min(8u, n_rows - half * 8) : 0u;
+      if (lane == 0 && cnt) {
+        mbar_expect_tx(rbar + half * 8u, cnt * 256u);
+        tma_row(ring_a + half * RING_BYTES, h_in + (size_t)(v0 + half * 8) * D, cnt * 256u, rbar + half * 8u);
       }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint32_t k = (uint32_t)q * 32 + lane;
-        const uint32_t hi = to_tf32(z[q]);
-        const uint32_t lo = to_tf32(z[q] - __uint_as_float(hi));
-        const uint32_t off = op_off(r, k, TM);
-        *reinterpret_cast<uint32_t*>(sA_hi + off) = hi;
-        *reinterpret_cast<uint32_t*>(sA_lo + off) = lo;
+    }
+    for (uint32_t half = 0; half < 2; ++half) {
+      const uint32_t cnt = n_rows > half * 8 ? min(8u, n_rows - half * 8) : 0u;
+      if (cnt) { mbar_wait(rbar + half * 8u, ring_uses[half] & 1u); ring_uses[half]++; }
+      for (uint32_t j = 0; j < 8; ++j) {
+        const float* row = ring + (half * RING_ROWS + j) * D;
+        const bool on = j < cnt;
+        put_pair(sA_hi, sA_lo, warp * 16 + half * 8 + j, 0u, lane, on ? row[lane] : 0.f, on ? row[32 + lane] : 0.f);
       }
+      __syncwarp();
+    }
+    // (2) the in-neighbours of the warp's rows, as one stream of edges cut at the row boundaries
+    const uint32_t e_beg = n_rows ? rowptr[v0] : 0u, e_end = n_rows ? rowptr[v0 + n_rows] : 0u;
+    const uint32_t n_chunks = (e_end - e_beg + RING_ROWS - 1) / RING_ROWS;
+    // `dep` is always 0 but derived from the last word this lane read out of the slot (zero_rt is a run-time 0 the
+    // compiler cannot see through): the copies that refill a slot cannot be issued before its reads have returned
+    auto issue = [&](uint32_t c, uint32_t dep) {
+      const uint32_t slot = c & 1u, first = e_beg + c * RING_ROWS, cnt = min(RING_ROWS, e_end - first);
+      if (lane == 0) mbar_expect_tx(rbar + slot * 8u, cnt * 256u + dep);
+      __syncwarp();
+      if (lane < cnt) tma_row(ring_a + (slot * RING_ROWS + lane) * 256u, h_in + (size_t)col[first + lane] * D, 256u + dep, rbar + slot * 8u);
+    };
+    if (n_chunks > 0) issue(0, 0u);
+    if (n_chunks > 1) issue(1, 0u);
+    uint32_t r = 0;                                   // current row of the warp
+    uint32_t row_end = n_rows ? rowptr[v0 + 1] : 0u, row_beg = e_beg;
+    float m0 = 0.f, m1 = 0.f;
+    auto close_rows_until = [&](uint32_t e) {         // rows that end at or before edge e are complete
+      while (r < n_rows && row_end <= e) {
+        const float inv = row_end > row_beg ? 1.0f / (float)(row_end - row_beg) : 0.f;
+        put_pair(sA_hi, sA_lo, warp * 16 + r, 64u, lane, m0 * inv, m1 * inv);
+        m0 = m1 = 0.f;
+        ++r;
+        row_beg = row_end;
+        if (r < n_rows) row_end = rowptr[v0 + r + 1];
+      }
+    };
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+      const uint32_t slot = c & 1u, first = e_beg + c * RING_ROWS, cnt = min(RING_ROWS, e_end - first);
+      mbar_wait(rbar + slot * 8u, ring_uses[slot] & 1u);
+      ring_uses[slot]++;
+      float last = 0.f;
+      for (uint32_t j = 0; j < cnt; ++j) {          // CSR order: deterministic sum
+        close_rows_until(first + j);
+        const float* row = ring + (slot * RING_ROWS + j) * D;
+        last = row[lane];
+        m0 += last;
+        m1 += row[32 + lane];
+      }
+      __syncwarp();
+      if (c + 2 < n_chunks) issue(c + 2, __float_as_uint(last) & zero_rt);   // the slot goes back to the TMA
+    }
+    close_rows_until(e_end);                          // the last rows, and rows without in-edges
+    for (uint32_t rr = n_rows; rr < 16; ++rr) {       // rows past the end of the graph: zeros
+      put_pair(sA_hi, sA_lo, warp * 16 + rr, 0u, lane, 0.f, 0.f);
+      put_pair(sA_hi, sA_lo, warp * 16 + rr, 64u, lane, 0.f, 0.f);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor-core (async proxy) reads
     __syncthreads();
@@ -432,6 +534,8 @@ struct alz_gnn_state {
   void* d_tmp = nullptr;
   size_t tmp_bytes = 0;
   uint32_t n_v = 0, n_e = 0;
+  bool n_v_known = true;
+  uint32_t* d_nv = nullptr;      // node count of the last pass, on the device
 };
 
 #define CK(expr)                                                                       \
@@ -466,6 +570,7 @@ static int gnn_init_impl(alz_handle* h) {
   CK(cudaMalloc(&g->d_stats, V * 8 * 8));
   for (int i = 0; i < 3; ++i) CK(cudaMalloc(&g->d_h[i], V * D * 4));
   CK(cudaMalloc(&g->d_scores, E * 4));
+  CK(cudaMalloc(&g->d_nv, 4));
   g->tmp_bytes = std::max(sort_pairs_temp_bytes((uint32_t)V), scan_temp_bytes((uint32_t)V + 1));
   CK(cudaMalloc(&g->d_tmp, g->tmp_bytes));
   const Weights w = make_weights();
@@ -492,7 +597,7 @@ static int gnn_init_impl(alz_handle* h) {
       CK(cudaMemcpyAsync(g->d_Wcan[l], can.data(), 2 * tc::B_BYTES, cudaMemcpyHostToDevice, h->stream));
       CK(cudaStreamSynchronize(h->stream));   // `can` is rewritten for the next layer
     }
-    CK(cudaFuncSetAttribute(tc::sage_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::sage_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_TC));
   }
   CK(cudaMalloc(&g->d_a, 132 * 4));
   CK(cudaMemcpyAsync(g->d_a, w.a.data(), 132 * 4, cudaMemcpyHostToDevice, h->stream));
@@ -518,12 +623,16 @@ void alz_internal_free_gnn(alz_handle* h) {
   cudaFree(g->d_in_deg); cudaFree(g->d_rowptr); cudaFree(g->d_col); cudaFree(g->d_sorted_edge); cudaFree(g->d_stats);
   for (int i = 0; i < 3; ++i) cudaFree(g->d_h[i]);
   for (int l = 0; l < 2; ++l) { cudaFree(g->d_W[l]); cudaFree(g->d_b[l]); cudaFree(g->d_Wcan[l]); }
-  cudaFree(g->d_a); cudaFree(g->d_scores); cudaFree(g->d_tmp);
+  cudaFree(g->d_a); cudaFree(g->d_scores); cudaFree(g->d_tmp); cudaFree(g->d_nv);
   delete g;
   h->gnn = nullptr;
 }
 
-// CSR build + 2 layers + scoring over the last flushed window (h->d_out)
+// CSR build + 2 layers + scoring over the last flushed window (h->d_out). Nothing here waits for the device:
+// the node count lives in device memory and every kernel reads it there; buffers and grids are sized by the
+// bound 2 * n_e the host knows. Sorts only cover the key bits that can differ.
+static int bits_for(uint64_t x) { int b = 1; while (b < 64 && (x >> b) != 0) ++b; return b; }
+
 static int gnn_run(alz_handle* h) {
   int rc = gnn_init(h);
   if (rc != ALZ_OK) return rc;
@@ -532,45 +641,42 @@ static int gnn_run(alz_handle* h) {
   const uint32_t n_e = h->last_n_edges;
   g->n_e = n_e;
   g->n_v = 0;
-  if (n_e == 0) return ALZ_OK;
+  g->n_v_known = n_e == 0;
+  if (n_e == 0) { CK(cudaMemsetAsync(g->d_nv, 0, 4, s)); return ALZ_OK; }
   if (n_e > g->cap_e) return ALZ_E_CAPACITY;
   const unsigned grid = (unsigned)h->sms * 4;
-  const uint32_t n2 = 2 * n_e;
-  // nodes
+  const uint32_t n2 = 2 * n_e;   // bound on the node count
+  // nodes: (kind 2 bits << 32 | value 32 bits): 34 key bits
   edge_node_keys_kernel<<<grid, 256, 0, s>>>(h->d_out, n_e, g->d_nk);
   launch_iota(g->d_iota, n2, h->sms, s);
-  sort_pairs(g->d_tmp, g->tmp_bytes, g->d_nk, g->d_nk_sorted, g->d_iota, g->d_vals, n2, s);
+  sort_pairs(g->d_tmp, g->tmp_bytes, g->d_nk, g->d_nk_sorted, g->d_iota, g->d_vals, n2, s, 34);
   flag_heads_kernel<<<grid, 256, 0, s>>>(g->d_nk_sorted, n2, g->d_flags);
   exclusive_scan_u32(g->d_tmp, g->tmp_bytes, g->d_flags, g->d_pos, n2, s);
   scatter_heads_kernel<<<grid, 256, 0, s>>>(g->d_nk_sorted, g->d_flags, g->d_pos, n2, g->d_nodes);
-  uint32_t last[2];
-  CK(cudaMemcpyAsync(&last[0], g->d_pos + (n2 - 1), 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(&last[1], g->d_flags + (n2 - 1), 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
-  const uint32_t n_v = last[0] + last[1];
-  g->n_v = n_v;
-  // stats + CSR by destination
-  CK(cudaMemsetAsync(g->d_stats, 0, (size_t)n_v * 64, s));
-  CK(cudaMemsetAsync(g->d_in_deg, 0, ((size_t)n_v + 1) * 4, s));
-  edge_stats_kernel<<<grid, 256, 0, s>>>(h->d_out, n_e, g->d_nodes, n_v, g->d_src_idx, g->d_dst_key, g->d_stats,
+  node_count_kernel<<<1, 32, 0, s>>>(g->d_pos, g->d_flags, n2, g->d_nv);
+  // stats + CSR by destination (destination index < n2)
+  CK(cudaMemsetAsync(g->d_stats, 0, (size_t)n2 * 64, s));
+  CK(cudaMemsetAsync(g->d_in_deg, 0, ((size_t)n2 + 1) * 4, s));
+  edge_stats_kernel<<<grid, 256, 0, s>>>(h->d_out, n_e, g->d_nodes, g->d_nv, g->d_src_idx, g->d_dst_key, g->d_stats,
                                          g->d_in_deg);
   launch_iota(g->d_iota, n_e, h->sms, s);
-  sort_pairs(g->d_tmp, g->tmp_bytes, g->d_dst_key, g->d_dst_sorted, g->d_iota, g->d_sorted_edge, n_e, s);
+  sort_pairs(g->d_tmp, g->tmp_bytes, g->d_dst_key, g->d_dst_sorted, g->d_iota, g->d_sorted_edge, n_e, s, bits_for(n2));
   csr_cols_kernel<<<grid, 256, 0, s>>>(g->d_sorted_edge, g->d_src_idx, n_e, g->d_col);
-  exclusive_scan_u32(g->d_tmp, g->tmp_bytes, g->d_in_deg, g->d_rowptr, n_v + 1, s);
+  exclusive_scan_u32(g->d_tmp, g->tmp_bytes, g->d_in_deg, g->d_rowptr, n2 + 1, s);
   // features, layers, scores
-  node_features_kernel<<<grid, 256, 0, s>>>(g->d_nodes, g->d_stats, n_v, g->d_h[0]);
+  node_features_kernel<<<grid, 256, 0, s>>>(g->d_nodes, g->d_stats, g->d_nv, g->d_h[0]);
   for (int l = 0; l < 2; ++l) {
     if (g->use_tc) {
-      const unsigned tiles = (n_v + tc::TM - 1) / tc::TM;
-      tc::sage_layer_tc_kernel<<<std::min<unsigned>(tiles, (unsigned)h->sms), 256, tc::SMEM_BYTES, s>>>(
-          g->d_h[l], g->d_h[l + 1], g->d_rowptr, g->d_col, g->d_Wcan[l], g->d_b[l], n_v);
+      const unsigned tiles = (n2 + tc::TM - 1) / tc::TM;
+      tc::sage_layer_tc_kernel<<<std::min<unsigned>(tiles, (unsigned)h->sms), 256, tc::SMEM_TC, s>>>(
+          g->d_h[l], g->d_h[l + 1], g->d_rowptr, g->d_col, g->d_Wcan[l], g->d_b[l], g->d_nv);
     } else {
-      sage_layer_kernel<<<grid, 256, 0, s>>>(g->d_h[l], g->d_h[l + 1], g->d_rowptr, g->d_col, g->d_W[l], g->d_b[l], n_v);
+      sage_layer_kernel<<<grid, 256, 0, s>>>(g->d_h[l], g->d_h[l + 1], g->d_rowptr, g->d_col, g->d_W[l], g->d_b[l], g->d_nv);
     }
   }
   edge_score_kernel<<<grid, 256, 0, s>>>(h->d_out, n_e, g->d_src_idx, g->d_dst_key, g->d_h[2], g->d_a, g->c,
                                          g->d_scores);
+  h->launches += 12;
   CK(cudaGetLastError());
   return ALZ_OK;
 }
@@ -608,6 +714,11 @@ extern "C" int alz_gnn_nodes(alz_handle* h, uint64_t* node_keys, float* h2, size
   std::lock_guard<std::mutex> g(h->mu);
   if (!h->gnn) return ALZ_E_STATE;
   CK(cudaSetDevice(h->device));
+  if (!h->gnn->n_v_known) {   // the pass itself never needed the count on the host
+    CK(cudaMemcpyAsync(&h->gnn->n_v, h->gnn->d_nv, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->gnn->n_v_known = true;
+  }
   *n_out = h->gnn->n_v;
   if (h->gnn->n_v > cap) return ALZ_E_CAPACITY;
   if (h->gnn->n_v) {

@@ -99,6 +99,16 @@ __device__ __forceinline__ void red_add_u32(uint32_t* p, uint32_t v) {
 __device__ __forceinline__ void red_add_u64(uint64_t* p, uint64_t v) {
   asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// the same with an L2 eviction-priority hint: the pair dictionary and the pair rows are the kernel's random-access
+// working set (~100 MB against 126 MB of L2, with 3.2 GB of records streaming through): marked evict-last they
+// stay resident (profiles/r2_ingest_v8_ncu.txt: 11 % of the dictionary probes went to DRAM without the hint,
+// enough for nearly every batch of 32 probes to wait for one)
+__device__ __forceinline__ void red_add_u32_keep(uint32_t* p, uint32_t v, uint64_t pol) {
+  asm volatile("red.relaxed.gpu.global.add.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void red_add_u64_keep(uint64_t* p, uint64_t v, uint64_t pol) {
+  asm volatile("red.relaxed.gpu.global.add.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
+}
 __device__ __forceinline__ bool elect_one() {   // one lane of the (converged) warp
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -131,8 +141,8 @@ __device__ __forceinline__ void tma_load(uint32_t dst, const void* src, uint32_t
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
 }
 // 16-byte global -> shared copy that no register waits on (LDGSTS); L2 only (the dictionary is written by other CTAs)
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint64_t pol) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -225,10 +235,18 @@ using SlowQueue = Queue<kSlowQ>;
 using ColdQueue = Queue<kColdQ>;
 
 // the global path for one event whose pair row is known
+__constant__ int c_keep_hint = 1;   // ALZ_INGEST_KEEP=0 turns the eviction-priority hint off (A/B runs)
+__device__ __forceinline__ uint64_t keep_policy() {
+  uint64_t p;
+  if (c_keep_hint) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ void global_add(const AccTable& t, uint32_t row, uint32_t bucket, uint64_t dur, bool err) {
-  red_add_u32(&t.hist[(size_t)row * ALZ_NB + bucket], 1u);
-  red_add_u64(&t.lat_sum[row], dur);
-  if (err) red_add_u64(&t.err5xx[row], 1ull);
+  const uint64_t pol = keep_policy();
+  red_add_u32_keep(&t.hist[(size_t)row * ALZ_NB + bucket], 1u, pol);
+  red_add_u64_keep(&t.lat_sum[row], dur, pol);
+  if (err) red_add_u64_keep(&t.err5xx[row], 1ull, pol);
 }
 
 // slow tier for one event (walks the dictionary): the pair is new to it, or its home slot is taken by another
@@ -274,7 +292,7 @@ __device__ __forceinline__ void cold_issue(const ColdQueue& q, uint32_t count, c
     if (!maybe_pod(s.bloom, e.x)) probe[lane] = make_uint4(0u, 0u, kDropRow, 1u);      // e.x = the key's low word = saddr
     else {
       const uint64_t key = ((uint64_t)e.y << 32) | e.x;
-      cp_async16(probe_a + lane * 16u, &t.dict_of(kind)[pair_hash(key) & t.mask_of(kind)]);
+      cp_async16(probe_a + lane * 16u, &t.dict_of(kind)[pair_hash(key) & t.mask_of(kind)], keep_policy());
     }
   }
   cp_async_commit();
@@ -695,6 +713,13 @@ void launch_ingest_pairs(const alz_l7_rec* recs, uint64_t n, const AccTable& pai
   if (n == 0) return;
   // ALZ_INGEST_SHAPE: CTA shape for profiling runs (default = the measured best)
   static const int shape = [] { const char* v = getenv("ALZ_INGEST_SHAPE"); return v ? atoi(v) : 0; }();
+  static const int keep = [] {
+    const char* v = getenv("ALZ_INGEST_KEEP");
+    const int k = v ? atoi(v) : 1;
+    if (!k) cudaMemcpyToSymbol(c_keep_hint, &k, sizeof(k));
+    return k;
+  }();
+  (void)keep;
   switch (shape) {
     case 1: launch_variant<12, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
     case 2: launch_variant<20, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;

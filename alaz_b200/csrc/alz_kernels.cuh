@@ -36,7 +36,7 @@ void launch_synth_owned(const alz_synth_view& v, uint64_t first, uint64_t n, uin
 // radix sort of (edge key, row) pairs by key (alz_sort.cu)
 size_t sort_pairs_temp_bytes(uint32_t n);
 void sort_pairs(void* temp, size_t temp_bytes, const uint64_t* keys_in, uint64_t* keys_out,
-                const uint32_t* vals_in, uint32_t* vals_out, uint32_t n, cudaStream_t s);
+                const uint32_t* vals_in, uint32_t* vals_out, uint32_t n, cudaStream_t s, int end_bit = 64);
 size_t scan_temp_bytes(uint32_t n);
 void exclusive_scan_u32(void* temp, size_t temp_bytes, const uint32_t* in, uint32_t* out, uint32_t n, cudaStream_t s);
 }  // namespace alz

@@ -67,6 +67,28 @@ def quantile(hist, q):
     return bucket_hi(63)
 
 
+_LO = np.array([bucket_lo(b) for b in range(64)])
+_HI = np.array([bucket_hi(b) for b in range(64)])
+
+
+def quantiles_vec(hist, q):
+    """quantile() for every row of hist at once (same arithmetic, float64)."""
+    h = hist.astype(np.float64)
+    total = h.sum(axis=1)
+    target = q * total
+    cum = np.cumsum(h, axis=1)
+    ok = (h > 0.0) & (cum >= target[:, None])
+    b = np.argmax(ok, axis=1)
+    any_ok = ok.any(axis=1)
+    rows = np.arange(len(h))
+    before = cum[rows, b] - h[rows, b]
+    c = np.where(h[rows, b] > 0.0, h[rows, b], 1.0)
+    f = np.maximum((target - before) / c, 0.0)
+    val = _LO[b] + f * (_HI[b] - _LO[b])
+    val = np.where(any_ok, val, _HI[63])
+    return np.where(total > 0.0, val, 0.0)
+
+
 def run(edges):
     """edges: alz_edge_out array (any order). Returns (node_keys, h2, scores) with scores in the input order."""
     n_e = len(edges)
@@ -93,7 +115,7 @@ def run(edges):
     h[:, 2] = ratio(st[:, 2], st[:, 0]); h[:, 3] = ratio(st[:, 3], st[:, 1])
     h[:, 4] = np.log1p(ratio(st[:, 4], st[:, 0])); h[:, 5] = np.log1p(ratio(st[:, 5], st[:, 1]))
     h[:, 6] = np.log1p(st[:, 6]); h[:, 7] = np.log1p(st[:, 7])
-    h[:, 8] = kind == 0; h[:, 9] = kind == 1; h[:, 10] = kind == 2; h[:, 11] = 1.0
+    h[:, 8] = kind == 0; h[:, 9] = kind == 1; h[:, 10] = kind >= 2; h[:, 11] = 1.0   # outbound, by address or by Host header
     h = h.astype(np.float32).astype(np.float64)   # features are stored as float32
     W, b, a, c = weights()
     indeg = st[:, 7]
@@ -106,8 +128,7 @@ def run(edges):
     e_feat = np.zeros((n_e, 4), dtype=np.float64)
     e_feat[:, 0] = np.log1p(cnt)
     e_feat[:, 1] = ratio(err, cnt)
-    for i in range(n_e):
-        e_feat[i, 2] = np.log1p(quantile(edges["hist"][i], 0.5))
-        e_feat[i, 3] = np.log1p(quantile(edges["hist"][i], 0.99))
+    e_feat[:, 2] = np.log1p(quantiles_vec(edges["hist"], 0.5))
+    e_feat[:, 3] = np.log1p(quantiles_vec(edges["hist"], 0.99))
     zz = np.concatenate([h[u], h[v], e_feat], axis=1) @ a + c
     return nodes, h, 1.0 / (1.0 + np.exp(-zz))
