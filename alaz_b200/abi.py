@@ -55,6 +55,9 @@ assert SOCK_QUERY.itemsize == 24
 SOCK_RESULT = np.dtype([("found", "<u4"), ("saddr", "<u4"), ("daddr", "<u4"),
                         ("sport", "<u2"), ("dport", "<u2")])
 assert SOCK_RESULT.itemsize == 16
+ALIVE_CONN = np.dtype([("from_ip", "<u4"), ("from_id", "<u4"), ("to_ip", "<u4"), ("to_id", "<u4"),
+                       ("from_port", "<u2"), ("to_port", "<u2"), ("to_type", "u1"), ("_pad", "u1", (3,))])
+assert ALIVE_CONN.itemsize == 24
 
 EDGE_OUT = np.dtype([
     ("from_type", "u1"), ("to_type", "u1"), ("_pad", "u1", (6,)),
@@ -88,6 +91,15 @@ class Stats(C.Structure):
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_ if not n.startswith("_")}
+
+
+class SockStats(C.Structure):
+    """alz_sock_stats_t."""
+    _fields_ = [(n, C.c_uint64) for n in ("lines", "pool_records", "pool_garbage", "syncs", "sync_ops", "sync_bytes",
+                                          "repools", "joined_events")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
 class SynthView(C.Structure):

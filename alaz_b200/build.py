@@ -39,11 +39,12 @@ def build(force=False, verbose=False, prof=False):
     nvcc = os.environ.get("NVCC", "nvcc")
     srcs = [os.path.join(CSRC, s) for s in SOURCES] + EXTRA
     cmd = [nvcc] + NVCC_FLAGS + (["-DALZ_INGEST_PROF"] if prof else []) + (["-Xptxas", "-v"] if verbose else []) + \
-        srcs + ["-o", out, "-ldl"]
+        srcs + ["-o", out + ".tmp", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("nvcc failed building libalazgpu.so")
+    os.replace(out + ".tmp", out)   # a snapshot of the tree (gpurun) never sees a half-written library
     if verbose:
         sys.stderr.write(r.stderr)
     return out

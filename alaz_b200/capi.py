@@ -24,7 +24,8 @@ EXPORTS = [
     "alz_submit_l7_packed", "alz_submit_l7_packed_device", "alz_pack_l7",
     "alz_submit_l7_raw", "alz_window_flush", "alz_window_flush_device", "alz_window_fetch", "alz_get_stats",
     "alz_window_clock", "alz_window_epoch", "alz_gnn_score",
-    "alz_gnn_score_device", "alz_edge_quantiles", "alz_submit_tcp", "alz_sock_lookup", "alz_comm_unique_id", "alz_comm_init",
+    "alz_gnn_score_device", "alz_edge_quantiles", "alz_submit_tcp", "alz_sock_lookup", "alz_sock_lookup_at",
+    "alz_submit_l7_join", "alz_sock_gc", "alz_sock_alive", "alz_sock_stats", "alz_comm_unique_id", "alz_comm_init",
     "alz_owner_rank",
 ]
 
@@ -70,6 +71,11 @@ def load(rebuild=False):
         "alz_edge_quantiles": ([vp, vp, sz, vp], i),
         "alz_submit_tcp": ([vp, vp, sz], i),
         "alz_sock_lookup": ([vp, vp, sz, vp], i),
+        "alz_sock_lookup_at": ([vp, vp, sz, vp, u64], i),
+        "alz_submit_l7_join": ([vp, vp, vp, sz, u64], i),
+        "alz_sock_gc": ([vp], i),
+        "alz_sock_alive": ([vp, vp, sz, C.POINTER(sz)], i),
+        "alz_sock_stats": ([vp, C.POINTER(abi.SockStats)], i),
         "alz_comm_unique_id": ([vp], i),
         "alz_comm_init": ([vp, i, i, vp], i),
         "alz_owner_rank": ([u32, u32], u32),
@@ -90,7 +96,8 @@ def load(rebuild=False):
     }
     if abi.ABI_VERSION < 2:    # A/B timing against a round-1 build (ALZ_LIB_PATH + ALZ_ABI_VERSION=1)
         for k in ("alz_submit_l7_packed", "alz_submit_l7_packed_device", "alz_pack_l7", "alz_window_fetch",
-                  "alz_pinned_alloc_local", "alz_table_upsert_batch", "alz_window_clock", "alz_window_epoch"):
+                  "alz_pinned_alloc_local", "alz_table_upsert_batch", "alz_window_clock", "alz_window_epoch",
+                  "alz_sock_lookup_at", "alz_submit_l7_join", "alz_sock_gc", "alz_sock_alive", "alz_sock_stats"):
             sig.pop(k)
     for name, (args, res) in sig.items():
         f = getattr(L, name)   # AttributeError = header/library mismatch: loud
@@ -234,6 +241,40 @@ class Handle:
     def stats(self):
         st = abi.Stats()
         self._ck(self.L.alz_get_stats(self.h, C.byref(st)), "alz_get_stats")
+        return st.as_dict()
+
+    # ---- tcp_state sink + socket timelines (alz_sock.cu) ----
+    def submit_tcp(self, recs):
+        recs = np.ascontiguousarray(recs, dtype=abi.TCP_REC)
+        self._ck(self.L.alz_submit_tcp(self.h, _ptr(recs), len(recs)), "alz_submit_tcp")
+
+    def sock_lookup(self, q, now_ns=None):
+        q = np.ascontiguousarray(q, dtype=abi.SOCK_QUERY)
+        out = np.zeros(len(q), dtype=abi.SOCK_RESULT)
+        if now_ns is None:
+            self._ck(self.L.alz_sock_lookup(self.h, _ptr(q), len(q), _ptr(out)), "alz_sock_lookup")
+        else:
+            self._ck(self.L.alz_sock_lookup_at(self.h, _ptr(q), len(q), _ptr(out), int(now_ns)), "alz_sock_lookup_at")
+        return out
+
+    def submit_join(self, recs, keys, now_ns=0):
+        recs = np.ascontiguousarray(recs, dtype=abi.L7_REC)
+        keys = np.ascontiguousarray(keys, dtype=abi.SOCK_QUERY)
+        assert len(recs) == len(keys)
+        self._ck(self.L.alz_submit_l7_join(self.h, _ptr(recs), _ptr(keys), len(recs), int(now_ns)), "alz_submit_l7_join")
+
+    def sock_gc(self):
+        self._ck(self.L.alz_sock_gc(self.h), "alz_sock_gc")
+
+    def sock_alive(self, cap=1 << 20):
+        out = np.zeros(cap, dtype=abi.ALIVE_CONN)
+        n = C.c_size_t(0)
+        self._ck(self.L.alz_sock_alive(self.h, _ptr(out), cap, C.byref(n)), "alz_sock_alive")
+        return out[: n.value]
+
+    def sock_stats(self):
+        st = abi.SockStats()
+        self._ck(self.L.alz_sock_stats(self.h, C.byref(st)), "alz_sock_stats")
         return st.as_dict()
 
     def window_clock(self, first_kernel_ns, first_user_ns, window_ns):

@@ -523,6 +523,8 @@ static int ingest_device(alz_handle* h, const void* d, uint64_t n, bool rec16, c
   return ALZ_OK;
 }
 
+int alz_internal_ingest(alz_handle* h, const alz_l7_rec* d_recs, size_t n) { return ingest_device(h, d_recs, n, false, nullptr); }
+
 extern "C" int alz_submit_l7_device(alz_handle* h, const alz_l7_rec* d, size_t n) {
   if (!h || (!d && n)) return ALZ_E_INVAL;
   if (((uintptr_t)d & 31u) != 0) return ALZ_E_INVAL;  // 32-B records, bulk copies

@@ -51,8 +51,7 @@ struct NcclApi {
 };
 NcclApi g_nccl;
 
-bool load_nccl() {
-  if (g_nccl.lib) return true;
+bool load_nccl_once() {
   void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
   if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
   if (!lib) return false;
@@ -68,6 +67,13 @@ bool load_nccl() {
 #undef SYM
   g_nccl.lib = lib;
   return true;
+}
+// several rank threads of one process may get here together (tests/test_gpu_multi.py)
+bool load_nccl() {
+  static std::once_flag once;
+  static bool ok = false;
+  std::call_once(once, [] { ok = load_nccl_once(); });
+  return ok;
 }
 
 constexpr int kCanWords = 3 + ALZ_NB;      // u64 words per canonical edge row of the general path: count, err5xx,

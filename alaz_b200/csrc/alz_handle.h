@@ -105,6 +105,8 @@ struct alz_handle {
 };
 
 int alz_internal_fold(alz_handle* h);
+// device records -> the ingest kernel of the current mode; caller holds h->mu and has set the device
+int alz_internal_ingest(alz_handle* h, const alz_l7_rec* d_recs, size_t n);
 // multi-GPU merge of the prepared (sorted) live edges; ALZ_E_UNSUPPORTED = single rank,
 // caller finishes the flush locally. local_rc: this rank's own status so far (every rank enters the
 // collectives even when its local preparation failed, and all ranks return the same failure)

@@ -235,6 +235,8 @@ using SlowQueue = Queue<kSlowQ>;
 using ColdQueue = Queue<kColdQ>;
 
 // the global path for one event whose pair row is known
+__constant__ int c_diag = 0;        // ALZ_INGEST_DIAG (timing experiments only, results are wrong): 1 = no reductions for
+                                    // cold home hits, 2 = do not wait for the probes
 __constant__ int c_keep_hint = 1;   // ALZ_INGEST_KEEP=0 turns the eviction-priority hint off (A/B runs)
 __device__ __forceinline__ uint64_t keep_policy() {
   uint64_t p;
@@ -306,14 +308,14 @@ __device__ __forceinline__ void cold_consume(ColdQueue& q, uint32_t count, const
                                              unsigned long long* t_wait, unsigned long long* t_slow) {
   const uint32_t lane = threadIdx.x & 31u;
   const long long w0 = PROF_NOW();
-  cp_async_wait_all();
+  if (!(c_diag & 2)) cp_async_wait_all();
   *t_wait += (unsigned long long)(PROF_NOW() - w0);
   const bool valid = lane < count;
   uint4 e = make_uint4(0u, 0u, 0u, 0u), ent = make_uint4(0u, 0u, kNoRow, 0u);
   if (valid) { e = *q.at(lane); ent = probe[lane]; }
   const bool filtered = valid && ent.z == kDropRow && ent.w == 1u;
   const bool home = valid && !filtered && ent.x == e.x && ent.y == e.y && ent.z < kDropRow && (e.x & e.y) != 0xFFFFFFFFu;
-  if (home) global_add(t, ent.z, e.w & 0x3Fu, ((uint64_t)(e.w >> 9) << 32) | e.z, (e.w & 0x100u) != 0u);
+  if (home && !(c_diag & 1)) global_add(t, ent.z, e.w & 0x3Fu, ((uint64_t)(e.w >> 9) << 32) | e.z, (e.w & 0x100u) != 0u);
   if (filtered) *unresolved += 1u;
   slow.push(valid && !home && !filtered, ((uint64_t)e.y << 32) | e.x, e.z, e.w, lane_lt);
   __syncwarp();
@@ -322,6 +324,70 @@ __device__ __forceinline__ void cold_consume(ColdQueue& q, uint32_t count, const
     const long long s0 = PROF_NOW();
     slow_batch<kRows>(slow, 32u, t, s, ep, ep_mask, lost, unresolved);
     *t_slow += (unsigned long long)(PROF_NOW() - s0);
+  }
+}
+
+// End of a launch, all warps (after a __syncthreads): drain the private rows into the global table and publish
+// the launch's counters.
+template <int kWarps, uint32_t kRows, bool kWin>
+__device__ __forceinline__ void drain_rows_and_count(const Shared& s, const AccTable& pairs, Counters* ctr,
+                                                     const EpEntry* __restrict__ ep, uint32_t ep_mask, uint32_t lost,
+                                                     uint32_t unresolved, uint32_t n_hit, uint32_t n_live,
+                                                     uint32_t n_cold, uint32_t n_late) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  // drain the private rows into the global table. Phase 1, a thread per row: find (or create) the pair's global
+  // row — the dependent dictionary probes of up to 32 rows per warp overlap; the row number replaces the key's
+  // low word. Phase 2, a half-warp per row: add the window's cells, 5xx count and latency sums.
+  const uint32_t used = min(*s.n_rows, kRows);
+  for (uint32_t r = threadIdx.x; r < used; r += kWarps * 32) {
+    const uint64_t key = s.rowkey[r];
+    const uint32_t* row = s.rows + r * kRowWords;
+    uint32_t any = 0;
+#pragma unroll
+    for (int k = 0; k < (int)kRowWords; ++k) any |= row[k];
+    uint32_t grow = kNoRow;                       // never hit in this launch: no global row needed
+    if (key != kEmptyKey && any != 0u) grow = find_or_insert_pair(pairs, key, kPairFwd, ep, ep_mask);
+    reinterpret_cast<uint32_t*>(&s.rowkey[r])[0] = grow;
+  }
+  __syncthreads();
+  const uint32_t hl = lane & 15u, half = lane >> 4;
+  const uint32_t n_pass = (used + kWarps * 2u - 1u) / (kWarps * 2u);     // same trip count for both halves of a warp
+  for (uint32_t ps = 0; ps < n_pass; ++ps) {
+    const uint32_t r = ps * kWarps * 2u + warp * 2u + half;
+    const bool valid = r < used;
+    const uint32_t grow = valid ? reinterpret_cast<const uint32_t*>(&s.rowkey[r])[0] : kNoRow;
+    const uint32_t* row = s.rows + (valid ? r : kRows) * kRowWords;
+    const uint32_t cnt = (row[hl >> 1] >> ((hl & 1u) * 16u)) & 0xFFFFu;
+    uint32_t tot = cnt;
+    for (int o = 8; o > 0; o >>= 1) tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o);
+    if (grow == kNoRow) continue;
+    if (grow >= kDropRow) {   // source is not a pod any more (dropped like the reference does) or capacity
+      if (hl == 0) { if (grow == kDropRow) unresolved += tot; else lost += tot; }
+      continue;
+    }
+    const uint32_t base = (uint32_t)s.rowbase[r] * 4u;
+    if (cnt) red_add_u32(&pairs.hist[(size_t)grow * ALZ_NB + base + hl], cnt);
+    if (hl == 0) {
+      const uint64_t lat = (((uint64_t)row[10] << 32) + row[9]) + (((uint64_t)row[12] << 32) + row[11]);
+      if (lat) red_add_u64(&pairs.lat_sum[grow], lat);
+      if (row[8]) red_add_u64(&pairs.err5xx[grow], (uint64_t)row[8]);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    n_hit += __shfl_xor_sync(0xFFFFFFFFu, n_hit, o);
+    n_cold += __shfl_xor_sync(0xFFFFFFFFu, n_cold, o);
+    lost += __shfl_xor_sync(0xFFFFFFFFu, lost, o);
+    unresolved += __shfl_xor_sync(0xFFFFFFFFu, unresolved, o);
+  }
+  // events that built no request row = events seen - hot hits - cold events (the last two are counted anyway);
+  // n_live is the same in every lane
+  const uint32_t not_request = n_live - n_cold - n_hit;
+  if (kWin) for (int o = 16; o > 0; o >>= 1) n_late += __shfl_xor_sync(0xFFFFFFFFu, n_late, o);
+  if (lane == 0) {
+    if (not_request) atomicAdd(&ctr->not_request, (unsigned long long)not_request);
+    if (lost) atomicAdd(&ctr->capacity_events, (unsigned long long)lost);
+    if (unresolved) atomicAdd(&ctr->src_unresolved, (unsigned long long)unresolved);
+    if (kWin && n_late) atomicAdd(&ctr->late_events, (unsigned long long)n_late);
   }
 }
 
@@ -586,60 +652,265 @@ ingest_pairs_v8_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
   PROF_FLUSH();
   __syncthreads();
 
-  // drain the private rows into the global table. Phase 1, a thread per row: find (or create) the pair's global
-  // row — the dependent dictionary probes of up to 32 rows per warp overlap; the row number replaces the key's
-  // low word. Phase 2, a half-warp per row: add the window's cells, 5xx count and latency sums.
-  const uint32_t used = min(*s.n_rows, kRows);
-  for (uint32_t r = threadIdx.x; r < used; r += kWarps * 32) {
-    const uint64_t key = s.rowkey[r];
-    const uint32_t* row = s.rows + r * kRowWords;
-    uint32_t any = 0;
-#pragma unroll
-    for (int k = 0; k < (int)kRowWords; ++k) any |= row[k];
-    uint32_t grow = kNoRow;                       // never hit in this launch: no global row needed
-    if (key != kEmptyKey && any != 0u) grow = find_or_insert_pair(pairs, key, kPairFwd, ep, ep_mask);
-    reinterpret_cast<uint32_t*>(&s.rowkey[r])[0] = grow;
+  drain_rows_and_count<kWarps, kRows, kWin>(s, pairs, ctr, ep, ep_mask, lost, unresolved, n_hit, n_live, n_cold, n_late);
+}
+
+// ---- v9: the same tiers with twice the warps ------------------------------------------------------------------
+// One record per lane per iteration and no cold queue: a cold lane requests its dictionary home slot at once
+// (cp.async into the warp's probe buffer, slot = iteration parity), keeps the event in registers, and finishes
+// it two iterations later, when the probe has had two iterations of every other warp's work to land. Cold work
+// runs at the lane occupancy of the cold events (no compaction), but nothing is pushed, popped or batched, and
+// per-warp shared memory falls from 7.5 KB to 4 KB, which pays for 32 warps per SM instead of 16.
+constexpr uint32_t kDepth9 = 2;            // iterations between a probe's request and its use
+
+template <int kWarps, int kRecWords>
+struct Layout9 {
+  static constexpr uint32_t kChunkBytes = 32u * kRecWords * 4u;
+  static constexpr uint32_t kRing = (uint32_t)kWarps * 2u * kChunkBytes;
+  static constexpr uint32_t kBars = kRing;
+  static constexpr uint32_t kTabOff = kBars + (uint32_t)kWarps * 16u;
+  static constexpr uint32_t kBloomOff = kTabOff + kTab * 4u;
+  static constexpr uint32_t kSlowOff = kBloomOff + ALZ_BLOOM_WORDS * 4u;
+  static constexpr uint32_t kProbeOff = kSlowOff + (uint32_t)kWarps * kSlowQ * kQBytes;
+  static constexpr uint32_t kMisc = kProbeOff + (uint32_t)kWarps * kDepth9 * 512u;
+  static constexpr uint32_t kRowKeys = kMisc + 16u;
+  static constexpr uint32_t kPerRow = 8u + kRowWords * 4u + 1u;
+  static constexpr uint32_t kRowsRaw = (kSmemMax - kRowKeys - 64u) / kPerRow - 1u;
+  static constexpr uint32_t kRows = (kRowsRaw < 4064u ? kRowsRaw : 4064u) / 32u * 32u;
+  static constexpr uint32_t kRowsOff = kRowKeys + (kRows + 1u) * 8u;
+  static constexpr uint32_t kBaseOff = kRowsOff + (kRows + 1u) * kRowWords * 4u;
+  static constexpr uint32_t kBytes = kBaseOff + ((kRows + 1u + 15u) / 16u) * 16u;
+  static constexpr uint32_t kPreload = kRows - kRows / 8u;
+  static_assert(kBytes <= kSmemMax, "shared memory layout too large");
+  static_assert(kRows < kBusy, "row field is 12 bits");
+  static_assert(kRows * 3u <= kTab * 2u, "index too small for the rows");
+};
+
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+// second half of a cold event: its probe has landed in `slot[lane]`
+template <uint32_t kRows>
+__device__ __forceinline__ void cold_finish(bool valid, uint32_t klo, uint32_t khi, uint32_t dlo, uint32_t meta,
+                                            const uint4* slot, SlowQueue& slow, const AccTable& t, const Shared& s,
+                                            const EpEntry* __restrict__ ep, uint32_t ep_mask, uint32_t lane_lt,
+                                            uint32_t* lost, uint32_t* unresolved) {
+  const uint32_t lane = threadIdx.x & 31u;
+  uint4 ent = make_uint4(0u, 0u, kNoRow, 0u);
+  if (valid) ent = slot[lane];
+  const bool filtered = valid && ent.z == kDropRow && ent.w == 1u;
+  const bool home = valid && !filtered && ent.x == klo && ent.y == khi && ent.z < kDropRow && (klo & khi) != 0xFFFFFFFFu;
+  if (home) global_add(t, ent.z, meta & 0x3Fu, ((uint64_t)(meta >> 9) << 32) | dlo, (meta & 0x100u) != 0u);
+  if (filtered) *unresolved += 1u;
+  slow.push(valid && !home && !filtered, ((uint64_t)khi << 32) | klo, dlo, meta, lane_lt);
+  __syncwarp();
+  if (slow.count >= 32u) slow_batch<kRows>(slow, 32u, t, s, ep, ep_mask, lost, unresolved);
+}
+
+template <int kWarps, int kRecWords, bool kWin>
+__global__ void __launch_bounds__(kWarps * 32, 1)
+ingest_pairs_v9_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable pairs, Counters* ctr,
+                       const HotState* __restrict__ hot, const EpEntry* __restrict__ ep, uint32_t ep_mask,
+                       const uint32_t* __restrict__ bloom_g, const uint64_t* __restrict__ dur_ovf,
+                       const WinClock* __restrict__ win, uint4* __restrict__ defer_buf, uint32_t defer_cap) {
+  using L = Layout9<kWarps, kRecWords>;
+  constexpr uint32_t kRows = L::kRows;
+  constexpr uint32_t kChunk9 = 32u;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t lane_lt = (1u << lane) - 1u;
+  Shared s;
+  s.tab = reinterpret_cast<uint32_t*>(smem_raw + L::kTabOff);
+  s.bloom = reinterpret_cast<uint32_t*>(smem_raw + L::kBloomOff);
+  s.n_rows = reinterpret_cast<uint32_t*>(smem_raw + L::kMisc);
+  s.rowkey = reinterpret_cast<uint64_t*>(smem_raw + L::kRowKeys);
+  s.rows = reinterpret_cast<uint32_t*>(smem_raw + L::kRowsOff);
+  s.rowbase = smem_raw + L::kBaseOff;
+  SlowQueue slow;
+  slow.bind(smem_raw + L::kSlowOff + (size_t)warp * kSlowQ * kQBytes);
+  uint4* probe = reinterpret_cast<uint4*>(smem_raw + L::kProbeOff + (size_t)warp * kDepth9 * 512u);
+  const uint32_t probe_a = smem_u32(probe);
+  const uint8_t* ring = smem_raw + (size_t)warp * 2u * L::kChunkBytes;
+  const uint32_t ring_a = smem_u32(ring);
+  const uint32_t bar_a = smem_u32(smem_raw + L::kBars + warp * 16u);
+
+  const uint32_t n_chunks = (uint32_t)((n + kChunk9 - 1u) / kChunk9);          // n < 2^37 per launch
+  const uint32_t c_stride = gridDim.x * kWarps;
+  const uint32_t c_first = blockIdx.x * kWarps + warp;
+  const uint32_t tail = (uint32_t)(n - (uint64_t)(n_chunks - 1u) * kChunk9);
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  uint32_t c_next = c_first;
+  const uint32_t* src_next = recs + (uint64_t)c_first * (kChunk9 * kRecWords);
+  const uint64_t src_step = (uint64_t)c_stride * (kChunk9 * kRecWords);
+  auto issue = [&](uint32_t stage, uint32_t dep) {
+    if (c_next < n_chunks) {
+      const uint32_t bytes = (c_next == n_chunks - 1u ? tail : kChunk9) * (uint32_t)kRecWords * 4u + dep;
+      mbar_expect_tx(bar_a + stage * 8u, bytes);
+      tma_load(ring_a + stage * L::kChunkBytes, src_next, bytes, bar_a + stage * 8u, policy);
+    }
+  };
+  if (lane == 0) {
+    mbar_init(bar_a, 1u);
+    mbar_init(bar_a + 8u, 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    issue(0u, 0u);
+    c_next += c_stride; src_next += src_step;
+    issue(1u, 0u);
+  }
+  c_next += 2u * c_stride - (lane == 0 ? c_stride : 0u);
+  src_next += 2u * src_step - (lane == 0 ? src_step : 0u);
+
+  for (uint32_t i = threadIdx.x; i < kTab; i += kWarps * 32) s.tab[i] = 0u;
+  for (uint32_t i = threadIdx.x; i < ALZ_BLOOM_WORDS; i += kWarps * 32) s.bloom[i] = bloom_g ? bloom_g[i] : 0xFFFFFFFFu;
+  for (uint32_t i = threadIdx.x; i <= kRows; i += kWarps * 32) { s.rowkey[i] = kEmptyKey; s.rowbase[i] = 0; }
+  for (uint32_t i = threadIdx.x; i < (kRows + 1u) * kRowWords; i += kWarps * 32) s.rows[i] = 0u;
+  if (threadIdx.x == 0) *s.n_rows = 0u;
+  __syncthreads();
+  if (hot != nullptr) {
+    const uint32_t na = min(hot->n_a, (uint32_t)kHotA);
+    const uint32_t nb = min(min(hot->n_b, (uint32_t)(kHotMax - kHotA)), L::kPreload - min(na, L::kPreload));
+    for (uint32_t i = threadIdx.x; i < na; i += kWarps * 32) {
+      const uint64_t k = hot->keys[i];
+      if (k != kEmptyKey) smem_admit(s, k, table_hash(k), min((uint32_t)hot->base[i], 12u), L::kPreload, false);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < nb; i += kWarps * 32) {
+      const uint64_t k = hot->keys[kHotA + i];
+      if (k != kEmptyKey) smem_admit(s, k, table_hash(k), min((uint32_t)hot->base[kHotA + i], 12u), L::kPreload, false);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && *s.n_rows > L::kPreload) *s.n_rows = L::kPreload;
   }
   __syncthreads();
-  const uint32_t hl = lane & 15u, half = lane >> 4;
-  const uint32_t n_pass = (used + kWarps * 2u - 1u) / (kWarps * 2u);     // same trip count for both halves of a warp
-  for (uint32_t ps = 0; ps < n_pass; ++ps) {
-    const uint32_t r = ps * kWarps * 2u + warp * 2u + half;
-    const bool valid = r < used;
-    const uint32_t grow = valid ? reinterpret_cast<const uint32_t*>(&s.rowkey[r])[0] : kNoRow;
-    const uint32_t* row = s.rows + (valid ? r : kRows) * kRowWords;
-    const uint32_t cnt = (row[hl >> 1] >> ((hl & 1u) * 16u)) & 0xFFFFu;
-    uint32_t tot = cnt;
-    for (int o = 8; o > 0; o >>= 1) tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o);
-    if (grow == kNoRow) continue;
-    if (grow >= kDropRow) {   // source is not a pod any more (dropped like the reference does) or capacity
-      if (hl == 0) { if (grow == kDropRow) unresolved += tot; else lost += tot; }
-      continue;
+
+  const uint32_t zero = (uint32_t)(n >> 63);
+  uint32_t lost = 0, unresolved = 0, n_hit = 0, n_live = 0, n_cold = 0, n_late = 0;
+  uint64_t win_lo = 0, win_len = ~0ull;
+  if (kWin) { win_lo = win->lo; win_len = win->len; }
+  // cold events in flight: [0] requested last iteration, [1] the one before (due now)
+  uint32_t q_klo[2] = {0u, 0u}, q_khi[2] = {0u, 0u}, q_dlo[2] = {0u, 0u}, q_meta[2] = {0u, 0u};
+  bool q_on[2] = {false, false};
+  uint32_t it = 0;
+  for (uint32_t c = c_first; c < n_chunks; c += c_stride, ++it) {
+    const uint32_t stage = it & 1u;
+    mbar_wait(bar_a + stage * 8u, (it >> 1) & 1u);
+    uint32_t w[8];
+    {
+      const uint4* p = reinterpret_cast<const uint4*>(ring + stage * L::kChunkBytes + (size_t)lane * (kRecWords * 4u));
+      const uint4 a = p[0];
+      w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+      w[4] = w[5] = w[6] = w[7] = 0u;
+      uint32_t seen = a.x;
+      if (kRecWords == 8) {
+        if (kWin) { const uint4 b = p[1]; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w; seen ^= b.x; }
+        else { const uint2 b = *reinterpret_cast<const uint2*>(p + 1); w[4] = b.x; w[5] = b.y; seen ^= b.x; }
+      }
+      // the stage goes back to the TMA only when these loads have returned (see the v8 kernel)
+      __syncwarp();
+      if (elect_one()) issue(stage, seen & zero);
+      c_next += c_stride; src_next += src_step;
     }
-    const uint32_t base = (uint32_t)s.rowbase[r] * 4u;
-    if (cnt) red_add_u32(&pairs.hist[(size_t)grow * ALZ_NB + base + hl], cnt);
-    if (hl == 0) {
-      const uint64_t lat = (((uint64_t)row[10] << 32) + row[9]) + (((uint64_t)row[12] << 32) + row[11]);
-      if (lat) red_add_u64(&pairs.lat_sum[grow], lat);
-      if (row[8]) red_add_u64(&pairs.err5xx[grow], (uint64_t)row[8]);
+    const uint32_t n_here = (c == n_chunks - 1u) ? tail : kChunk9;
+    bool live = lane < n_here;
+    if constexpr (kWin && kRecWords == 8) {
+      const uint64_t rel = (((uint64_t)w[7] << 32) | w[6]) - win_lo;
+      const bool late = live && (rel >> 63) != 0ull;
+      const bool future = live && !late && rel >= win_len;
+      n_late += late ? 1u : 0u;
+      const uint32_t fm = __ballot_sync(0xFFFFFFFFu, future);
+      if (fm != 0u) {
+        uint32_t at = 0;
+        if (lane == (uint32_t)__ffs((int)fm) - 1u) at = atomicAdd(&ctr->defer_count, (uint32_t)__popc(fm));
+        at = __shfl_sync(0xFFFFFFFFu, at, __ffs((int)fm) - 1) + __popc(fm & lane_lt);
+        if (future) {
+          if (at < defer_cap) {
+            defer_buf[2u * at] = make_uint4(w[0], w[1], w[2], w[3]);
+            defer_buf[2u * at + 1u] = make_uint4(w[4], w[5], w[6], w[7]);
+          } else ++lost;
+          live = false;
+        }
+        n_live -= (uint32_t)__popc(fm);
+      }
     }
+    n_live += n_here;
+
+    const uint32_t mw = (kRecWords == 8) ? w[3] : w[2];
+    uint32_t p = __byte_perm(mw, 0u, 0x4442u);
+    uint64_t dur;
+    if (kRecWords == 8) dur = ((uint64_t)w[5] << 32) | w[4];
+    else {
+      dur = w[3];
+      if (p & ALZ_REC16_DUR_OVERFLOW) dur = live ? __ldg(&dur_ovf[w[3]]) : 0ull;
+    }
+    const bool hk = (p & ALZ_PROTO_F_HOSTKEY) != 0u;
+    p &= 0x3Fu;
+    const uint32_t cls = shr_clamp(kProtoLut, 3u * p);
+    const bool act = live && (cls & 1u) && !((cls & 2u) && (mw & ((uint32_t)ALZ_MF_PAYLOAD_REJECT << 24)));
+    const bool rv = (cls & 4u) && (mw & ((uint32_t)ALZ_MF_METHOD_MASK << 24)) == (2u << 24);
+    const bool err = p == ALZ_PROTO_HTTP && ((mw & 0xFFFFu) - 500u) < 100u;
+    const uint64_t key = ((uint64_t)w[1] << 32) | w[0];
+    const uint32_t bucket = latency_bucket_rz(dur);
+    const uint32_t kind = hk ? kPairHost : rv ? kPairRev : kPairFwd;
+    const uint32_t dhi = (uint32_t)(dur >> 32), dlo = (uint32_t)dur;
+    const uint32_t meta = bucket | (kind << 6) | (err ? 0x100u : 0u) | (dhi << 9);
+
+    const uint32_t h = table_hash(key);
+    const uint32_t fp = tab_fp(h);
+    const uint32_t x1 = s.tab[tab_idx1(h)] ^ fp, x2 = s.tab[tab_idx2(h)] ^ fp;
+    const uint32_t x = x1 < 0x10000u ? x1 : x2;
+    const uint32_t r = min(x & kRowMask, kRows);
+    const uint32_t d = bucket - ((x >> 12) & 15u) * 4u;
+    const bool hit = act && kind == kPairFwd && x < 0x10000u && (x & kRowMask) < kRows && d < 16u && s.rowkey[r] == key;
+    uint32_t* row = s.rows + r * kRowWords;
+    if (hit) {
+      const uint32_t sh = (d & 1u) * 16u;
+      const uint32_t old = atomicAdd(&row[d >> 1], 1u << sh);
+      if (((old >> sh) & 0xFFFFu) == kCellSpill) {
+        const uint32_t grow = find_or_insert_pair(pairs, key, kPairFwd, ep, ep_mask);
+        if (grow < kDropRow) red_add_u32(&pairs.hist[(size_t)grow * ALZ_NB + bucket], 0x8000u);
+        else if (grow == kDropRow) unresolved += 0x8000u; else lost += 0x8000u;
+        atomicSub(&row[d >> 1], 0x8000u << sh);
+      }
+      uint32_t* lat = row + 9u + 2u * (lane & 1u);
+      const uint32_t oldl = atomicAdd(&lat[0], dlo);
+      const bool carry = oldl > ~dlo;
+      if (carry || dhi != 0u) atomicAdd(&lat[1], dhi + (carry ? 1u : 0u));
+      if (err) atomicAdd(&row[8], 1u);
+      ++n_hit;
+    }
+    bool cold = act && !hit;
+    n_cold += cold ? 1u : 0u;
+    if (cold && dhi >= (1u << 23)) {   // does not fit the packed form: on the spot, rare beyond words
+      slow_one<kRows>(key, dur, bucket, kind, err, pairs, s, ep, ep_mask, &lost, &unresolved);
+      cold = false;
+    }
+    __syncwarp();
+
+    // finish the cold events of two iterations ago (their probes: all groups but the latest have landed) ...
+    uint4* slot = probe + stage * 32u;
+    cp_async_wait_1();
+    cold_finish<kRows>(q_on[1], q_klo[1], q_khi[1], q_dlo[1], q_meta[1], slot, slow, pairs, s, ep, ep_mask, lane_lt,
+                       &lost, &unresolved);
+    // ... and request the probes of this iteration's into the slot that just became free
+    if (cold) {
+      if (!maybe_pod(s.bloom, (uint32_t)key)) slot[lane] = make_uint4(0u, 0u, kDropRow, 1u);
+      else cp_async16(probe_a + (stage * 32u + lane) * 16u, &pairs.dict_of(kind)[pair_hash(key) & pairs.mask_of(kind)],
+                      keep_policy());
+    }
+    cp_async_commit();
+    q_klo[1] = q_klo[0]; q_khi[1] = q_khi[0]; q_dlo[1] = q_dlo[0]; q_meta[1] = q_meta[0]; q_on[1] = q_on[0];
+    q_klo[0] = (uint32_t)key; q_khi[0] = (uint32_t)(key >> 32); q_dlo[0] = dlo; q_meta[0] = meta; q_on[0] = cold;
   }
-  for (int o = 16; o > 0; o >>= 1) {
-    n_hit += __shfl_xor_sync(0xFFFFFFFFu, n_hit, o);
-    n_cold += __shfl_xor_sync(0xFFFFFFFFu, n_cold, o);
-    lost += __shfl_xor_sync(0xFFFFFFFFu, lost, o);
-    unresolved += __shfl_xor_sync(0xFFFFFFFFu, unresolved, o);
-  }
-  // events that built no request row = events seen - hot hits - cold events (the last two are counted anyway);
-  // n_live is the same in every lane
-  const uint32_t not_request = n_live - n_cold - n_hit;
-  if (kWin) for (int o = 16; o > 0; o >>= 1) n_late += __shfl_xor_sync(0xFFFFFFFFu, n_late, o);
-  if (lane == 0) {
-    if (not_request) atomicAdd(&ctr->not_request, (unsigned long long)not_request);
-    if (lost) atomicAdd(&ctr->capacity_events, (unsigned long long)lost);
-    if (unresolved) atomicAdd(&ctr->src_unresolved, (unsigned long long)unresolved);
-    if (kWin && n_late) atomicAdd(&ctr->late_events, (unsigned long long)n_late);
-  }
+  // the last two iterations' cold events: [1] sits in slot (it & 1), [0] in the other one
+  cp_async_wait_all();
+  cold_finish<kRows>(q_on[1], q_klo[1], q_khi[1], q_dlo[1], q_meta[1], probe + (it & 1u) * 32u, slow, pairs, s, ep, ep_mask,
+                     lane_lt, &lost, &unresolved);
+  cold_finish<kRows>(q_on[0], q_klo[0], q_khi[0], q_dlo[0], q_meta[0], probe + ((it + 1u) & 1u) * 32u, slow, pairs, s, ep,
+                     ep_mask, lane_lt, &lost, &unresolved);
+  while (slow.count) slow_batch<kRows>(slow, min(slow.count, 32u), pairs, s, ep, ep_mask, &lost, &unresolved);
+  __syncthreads();
+  drain_rows_and_count<kWarps, kRows, kWin>(s, pairs, ctr, ep, ep_mask, lost, unresolved, n_hit, n_live, n_cold, n_late);
 }
 
 // open the first window on the first record ever submitted: epoch = (write_time + off) / len, docs/SPEC.md §8
@@ -701,6 +972,17 @@ void launch_variant(const void* recs, uint64_t n, const AccTable& pairs, Counter
       (const uint32_t*)recs, n, pairs, ctr, hot, ep, ep_mask, bloom, dur_ovf, win, (uint4*)defer_buf, defer_cap);
 }
 
+template <int kWarps, int kRecWords, bool kWin = false>
+void launch_variant9(const void* recs, uint64_t n, const AccTable& pairs, Counters* ctr, const HotState* hot,
+                     const EpEntry* ep, uint32_t ep_mask, const uint32_t* bloom, const uint64_t* dur_ovf, int sms,
+                     cudaStream_t s, const WinClock* win = nullptr, void* defer_buf = nullptr, uint32_t defer_cap = 0) {
+  using L = Layout9<kWarps, kRecWords>;
+  cudaFuncSetAttribute(ingest_pairs_v9_kernel<kWarps, kRecWords, kWin>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)L::kBytes);
+  ingest_pairs_v9_kernel<kWarps, kRecWords, kWin><<<(unsigned)sms, kWarps * 32, L::kBytes, s>>>(
+      (const uint32_t*)recs, n, pairs, ctr, hot, ep, ep_mask, bloom, dur_ovf, win, (uint4*)defer_buf, defer_cap);
+}
+
 constexpr int kDefaultWarps = 16;
 
 }  // namespace
@@ -720,10 +1002,19 @@ void launch_ingest_pairs(const alz_l7_rec* recs, uint64_t n, const AccTable& pai
     return k;
   }();
   (void)keep;
+  static const int diag = [] {
+    const char* v = getenv("ALZ_INGEST_DIAG");
+    const int k = v ? atoi(v) : 0;
+    if (k) cudaMemcpyToSymbol(c_diag, &k, sizeof(k));
+    return k;
+  }();
+  (void)diag;
   switch (shape) {
     case 1: launch_variant<12, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
     case 2: launch_variant<20, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
     case 3: launch_variant<24, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
+    case 9: launch_variant9<32, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
+    case 10: launch_variant9<24, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
     default: launch_variant<kDefaultWarps, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
   }
 }

@@ -391,7 +391,7 @@ def main():
     if rank == 0:
         peak, peak_src = peaks()
         kernel = "ingest_eager_kernel" if args.eager else ("ingest_pairs_kernel(v1)" if args.no_smem_cache
-                                                           else "ingest_pairs_v6_kernel")
+                                                           else "ingest_pairs_v8_kernel")
         alg_bytes = N * ALG_BYTES_PER_EVENT
         achieved = alg_bytes / (ingest_ms_max * 1e-3) / 1e9
         step_alg = N * ALG_BYTES_PER_EVENT + int(n_edges) * ALG_BYTES_PER_EDGE

@@ -287,6 +287,49 @@ int alz_edge_quantiles(const alz_edge_out* e, const double* qs, size_t nq, doubl
 int alz_submit_tcp(alz_handle* h, const alz_tcp_rec* host_recs, size_t n);
 int alz_sock_lookup(alz_handle* h, const alz_sock_query* host_q, size_t n,
                     alz_sock_result* host_out);
+/* the same with the caller's clock for the LastMatch stamps (the reference uses
+ * time.Now(), sock_num_line.go:96, :156); alz_sock_lookup passes CLOCK_REALTIME */
+int alz_sock_lookup_at(alz_handle* h, const alz_sock_query* host_q, size_t n,
+                       alz_sock_result* host_out, uint64_t now_ns);
+/* L7 events that may carry an empty 5-tuple (get_sock miss, ebpf/c/l7.c:313-314):
+ * host_keys[i] = (Pid, Fd, WriteTimeNs) of host_recs[i]. Records with saddr == 0
+ * and daddr == 0 take their addresses from the (pid, fd) timeline on the device
+ * (findRelatedSocket, aggregator/data.go:1407-1429), then the whole batch is
+ * ingested like alz_submit_l7. A miss leaves the zeros and the event is dropped
+ * and counted as src_unresolved (0.0.0.0 is no pod, data.go:829-832).
+ * now_ns: LastMatch stamp, 0 = CLOCK_REALTIME. */
+int alz_submit_l7_join(alz_handle* h, const alz_l7_rec* host_recs,
+                       const alz_sock_query* host_keys, size_t n, uint64_t now_ns);
+/* One tick of clearSocketLines (aggregator/data.go:1681-1716): SocketLine.
+ * DeleteUnused (sock_num_line.go:160-209) on every line. */
+int alz_sock_gc(alz_handle* h);
+/* sendOpenConnection (aggregator/data.go:1628-1679) for every line: one row per
+ * line whose last value is an open socket with a pod at its source address.
+ * Rows come in no particular order. *n_out = rows there are; ALZ_E_CAPACITY
+ * (first `cap` rows written) when cap was too small. Resolves against the
+ * tables as of the last alz_table_commit. */
+typedef struct alz_alive_conn {
+  uint32_t from_ip;
+  uint32_t from_id;   /* pod id */
+  uint32_t to_ip;
+  uint32_t to_id;     /* pod / service id; the raw address for ALZ_NODE_OUTBOUND */
+  uint16_t from_port;
+  uint16_t to_port;
+  uint8_t to_type;    /* ALZ_NODE_* */
+  uint8_t _pad[3];
+} alz_alive_conn;
+int alz_sock_alive(alz_handle* h, alz_alive_conn* host_out, size_t cap, size_t* n_out);
+typedef struct alz_sock_stats_t {
+  uint64_t lines;          /* (pid, fd) timelines */
+  uint64_t pool_records;   /* device pool: records allocated to segments */
+  uint64_t pool_garbage;   /* ... of which in segments left behind by grown lines */
+  uint64_t syncs;          /* host -> device syncs so far */
+  uint64_t sync_ops;       /* inserts they carried */
+  uint64_t sync_bytes;     /* bytes they copied */
+  uint64_t repools;        /* times the pool was re-laid (full or half garbage) */
+  uint64_t joined_events;  /* alz_submit_l7_join: empty 5-tuples filled */
+} alz_sock_stats_t;
+int alz_sock_stats(alz_handle* h, alz_sock_stats_t* st);
 
 /* ---- multi-GPU: one rank per GPU, events pre-partitioned by alz_owner_rank ---- */
 #define ALZ_COMM_ID_BYTES 128

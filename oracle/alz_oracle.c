@@ -492,6 +492,7 @@ void orc_compact_raw(const void* raw, size_t n, alz_l7_rec* out) {
 /* ===================== SocketLine (sock_num_line.go) ====================== */
 typedef struct ts_sock {
   uint64_t ts;
+  uint64_t last_match; /* TimestampedSocket.LastMatch, sock_num_line.go:26 */
   int open; /* SockInfo != nil */
   orc_sockinfo si;
 } ts_sock;
@@ -516,12 +517,15 @@ void orc_sockline_add(orc_sockline* l, uint64_t ts, const orc_sockinfo* si) {
   while (lo < hi) { size_t mid = (lo + hi) / 2; if (l->v[mid].ts >= ts) hi = mid; else lo = mid + 1; }
   if (l->len == l->cap) { l->cap = l->cap ? l->cap * 2 : 8; l->v = (ts_sock*)realloc(l->v, l->cap * sizeof(ts_sock)); }
   memmove(&l->v[lo + 1], &l->v[lo], (l->len - lo) * sizeof(ts_sock));
-  l->v[lo].ts = ts; l->v[lo].open = si != NULL;
+  l->v[lo].ts = ts; l->v[lo].open = si != NULL; l->v[lo].last_match = 0;
   if (si) l->v[lo].si = *si; else memset(&l->v[lo].si, 0, sizeof(orc_sockinfo));
   l->len++;
 }
 
-int orc_sockline_get(orc_sockline* l, uint64_t ts, orc_sockinfo* out) {
+int orc_sockline_get(orc_sockline* l, uint64_t ts, orc_sockinfo* out) { return orc_sockline_get_at(l, ts, 1, out); }
+
+/* GetValue with time.Now() = now (the LastMatch stamps of :96 and :156) */
+int orc_sockline_get_at(orc_sockline* l, uint64_t ts, uint64_t now, orc_sockinfo* out) {
   if (l->len == 0) return 0; /* :86-88 */
   /* sort.Search: first index with !(Timestamp < ts), :90-92 */
   size_t lo = 0, hi = l->len;
@@ -529,6 +533,7 @@ int orc_sockline_get(orc_sockline* l, uint64_t ts, orc_sockinfo* out) {
   size_t index = lo;
   const uint64_t one_minute = 60ull * 1000000000ull;
   if (index == l->len) { /* :94-105 */
+    l->v[index - 1].last_match = now; /* :96 */
     if (!l->v[l->len - 1].open) {
       if (index >= 2 && l->v[index - 2].open && (ts - l->v[index - 2].ts) < one_minute) {
         *out = l->v[index - 2].si; return 1;
@@ -551,8 +556,35 @@ int orc_sockline_get(orc_sockline* l, uint64_t ts, orc_sockinfo* out) {
     }
     return 0;
   }
+  l->v[index - 1].last_match = now; /* :156 */
   *out = l->v[index - 1].si; /* :155-157 */
   return 1;
+}
+
+/* SocketLine.DeleteUnused, sock_num_line.go:160-209, as written: the first loop runs while i < len-1, so the
+ * last element is carried over only when the loop steps over it (two opens in a row at the end). */
+void orc_sockline_delete_unused(orc_sockline* l) {
+  if (l->len <= 1) return; /* :165-167 */
+  ts_sock* res = (ts_sock*)malloc(l->len * sizeof(ts_sock));
+  size_t n = 0, i = 0;
+  while (i < l->len - 1) { /* :172-181 */
+    if (l->v[i].open && l->v[i + 1].open) { res[n++] = l->v[i + 1]; i += 2; }
+    else { res[n++] = l->v[i]; i++; }
+  }
+  uint64_t last_matched = 0; /* :184-190 */
+  for (size_t k = n; k-- > 0;)
+    if (res[k].last_match != 0 && res[k].last_match > last_matched) last_matched = res[k].last_match;
+  const uint64_t assumed_interval = 5ull * 60ull * 1000000000ull; /* :193 */
+  for (long k = (long)n - 1; k >= 1; k--) { /* :197-208 */
+    if (!res[k].open && res[k - 1].open && res[k - 1].last_match + assumed_interval < last_matched) {
+      memmove(&res[k - 1], &res[k + 1], (n - (size_t)k - 1) * sizeof(ts_sock));
+      n -= 2;
+      k--;
+    }
+  }
+  const size_t res_cap = l->len;
+  free(l->v);
+  l->v = res; l->len = n; l->cap = res_cap;
 }
 
 /* SocketMaps[pid].M[fd] -> *SocketLine (cluster.go:20, socket.go:30-40) */
@@ -618,13 +650,71 @@ void orc_sockmaps_process_tcp(orc_sockmaps* m, const alz_tcp_rec* recs, size_t n
 }
 
 void orc_sockmaps_lookup(orc_sockmaps* m, const alz_sock_query* q, size_t n, alz_sock_result* out) {
+  orc_sockmaps_lookup_at(m, q, n, 1, out);
+}
+void orc_sockmaps_lookup_at(orc_sockmaps* m, const alz_sock_query* q, size_t n, uint64_t now, alz_sock_result* out) {
   for (size_t i = 0; i < n; i++) {
     memset(&out[i], 0, sizeof out[i]);
     sm_ent* e = sm_find(m, q[i].pid, q[i].fd, 0); /* findRelatedSocket data.go:1407-1429 */
     orc_sockinfo si;
-    if (e && orc_sockline_get(e->line, q[i].timestamp_ns, &si)) {
+    if (e && orc_sockline_get_at(e->line, q[i].timestamp_ns, now, &si)) {
       out[i].found = 1; out[i].saddr = si.saddr; out[i].daddr = si.daddr;
       out[i].sport = si.sport; out[i].dport = si.dport;
     }
   }
+}
+
+/* one tick of clearSocketLines, data.go:1681-1716 (without the alive-connection export) */
+void orc_sockmaps_gc(orc_sockmaps* m) {
+  for (size_t i = 0; i < m->cap; i++) if (m->e[i].used) orc_sockline_delete_unused(m->e[i].line);
+}
+size_t orc_sockmaps_records(orc_sockmaps* m) {
+  size_t n = 0;
+  for (size_t i = 0; i < m->cap; i++) if (m->e[i].used) n += m->e[i].line->len;
+  return n;
+}
+
+/* L7 events with an empty 5-tuple take the socket of (pid, fd) at WriteTimeNs (findRelatedSocket,
+ * data.go:1407-1429); a miss leaves the record as it is */
+void orc_sockmaps_join(orc_sockmaps* m, alz_l7_rec* recs, const alz_sock_query* keys, size_t n, uint64_t now,
+                       uint64_t* joined) {
+  for (size_t i = 0; i < n; i++) {
+    if (recs[i].saddr != 0 || recs[i].daddr != 0) continue;
+    sm_ent* e = sm_find(m, keys[i].pid, keys[i].fd, 0);
+    orc_sockinfo si;
+    if (e && orc_sockline_get_at(e->line, keys[i].timestamp_ns, now, &si)) {
+      recs[i].saddr = si.saddr; recs[i].daddr = si.daddr; recs[i].sport = si.sport; recs[i].dport = si.dport;
+      if (joined) (*joined)++;
+    }
+  }
+}
+
+/* sendOpenConnection, data.go:1628-1679, for every line (clearSocketLines with SEND_ALIVE_TCP_CONNECTIONS) */
+size_t orc_sockmaps_alive(orc_sockmaps* m, const orc* o, alz_alive_conn* out, size_t cap) {
+  size_t n = 0;
+  for (size_t i = 0; i < m->cap; i++) {
+    if (!m->e[i].used) continue;
+    const orc_sockline* l = m->e[i].line;
+    if (l->len == 0) continue; /* :1632-1634 */
+    const ts_sock* t = &l->v[l->len - 1];
+    if (!t->open) continue; /* a close: ignored */
+    char from[16], to[16];
+    ip_string(t->si.saddr, from); ip_string(t->si.daddr, to);
+    smap_ent* pod = smap_find(&o->pod_ip_to_uid, from); /* :1643-1647 */
+    if (!pod) continue;
+    alz_alive_conn c;
+    memset(&c, 0, sizeof c);
+    c.from_ip = t->si.saddr; c.from_port = t->si.sport; c.to_ip = t->si.daddr; c.to_port = t->si.dport;
+    c.from_id = (uint32_t)strtoul((const char*)pod->val + 4, NULL, 10);
+    smap_ent* svc = smap_find(&o->svc_ip_to_uid, to); /* :1662-1665 */
+    if (svc) { c.to_type = ALZ_NODE_SVC; c.to_id = (uint32_t)strtoul((const char*)svc->val + 4, NULL, 10); }
+    else {
+      smap_ent* dpod = smap_find(&o->pod_ip_to_uid, to); /* :1667-1670 */
+      if (dpod) { c.to_type = ALZ_NODE_POD; c.to_id = (uint32_t)strtoul((const char*)dpod->val + 4, NULL, 10); }
+      else { c.to_type = ALZ_NODE_OUTBOUND; c.to_id = t->si.daddr; } /* :1671-1674 */
+    }
+    if (n < cap) out[n] = c;
+    n++;
+  }
+  return n;
 }

@@ -81,6 +81,8 @@ void orc_sockline_add(orc_sockline* l, uint64_t ts, const orc_sockinfo* si);
 /* GetValue (:82-158); returns 1 and fills *out, or 0 where the reference errors */
 int orc_sockline_get(orc_sockline* l, uint64_t ts, orc_sockinfo* out);
 size_t orc_sockline_len(orc_sockline* l);
+int orc_sockline_get_at(orc_sockline* l, uint64_t ts, uint64_t now, orc_sockinfo* out);
+void orc_sockline_delete_unused(orc_sockline* l);
 
 /* processTcpConnect (aggregator/data.go:404-506) over many (pid,fd) lines,
  * then findRelatedSocket-style lookups (data.go:1407-1429). */
@@ -91,6 +93,12 @@ void orc_sockmaps_process_tcp(orc_sockmaps* m, const alz_tcp_rec* recs, size_t n
                               uint64_t* localhost_dropped);
 void orc_sockmaps_lookup(orc_sockmaps* m, const alz_sock_query* q, size_t n,
                          alz_sock_result* out);
+void orc_sockmaps_lookup_at(orc_sockmaps* m, const alz_sock_query* q, size_t n, uint64_t now, alz_sock_result* out);
+void orc_sockmaps_gc(orc_sockmaps* m);
+size_t orc_sockmaps_records(orc_sockmaps* m);
+void orc_sockmaps_join(orc_sockmaps* m, alz_l7_rec* recs, const alz_sock_query* keys, size_t n, uint64_t now,
+                       uint64_t* joined);
+size_t orc_sockmaps_alive(orc_sockmaps* m, const orc* o, alz_alive_conn* out, size_t cap);
 
 /* ---- "fair" CPU arm (alz_fastcpu.c): same results, integer keys, flat tables, pinned threads ---- */
 typedef struct orc_fast orc_fast;

@@ -69,6 +69,16 @@ def lib():
         L.orc_sockmaps_destroy.argtypes = [vp]
         L.orc_sockmaps_process_tcp.argtypes = [vp, vp, sz, C.POINTER(u64)]
         L.orc_sockmaps_lookup.argtypes = [vp, vp, sz, vp]
+        L.orc_sockmaps_lookup_at.argtypes = [vp, vp, sz, u64, vp]
+        L.orc_sockmaps_gc.argtypes = [vp]
+        L.orc_sockmaps_records.argtypes = [vp]
+        L.orc_sockmaps_records.restype = sz
+        L.orc_sockmaps_join.argtypes = [vp, vp, vp, sz, u64, C.POINTER(u64)]
+        L.orc_sockmaps_alive.argtypes = [vp, vp, vp, sz]
+        L.orc_sockmaps_alive.restype = sz
+        L.orc_sockline_get_at.argtypes = [vp, u64, u64, vp]
+        L.orc_sockline_get_at.restype = C.c_int
+        L.orc_sockline_delete_unused.argtypes = [vp]
         L.orc_fast_create.argtypes = [u32]
         L.orc_fast_create.restype = vp
         L.orc_fast_destroy.argtypes = [vp]
@@ -274,11 +284,30 @@ class SockMaps:
         self.L.orc_sockmaps_process_tcp(self.h, _ptr(recs), len(recs), C.byref(d))
         self.localhost_dropped += d.value
 
-    def lookup(self, q):
+    def lookup(self, q, now_ns=1):
         q = np.ascontiguousarray(q, dtype=abi.SOCK_QUERY)
         out = np.zeros(len(q), dtype=abi.SOCK_RESULT)
-        self.L.orc_sockmaps_lookup(self.h, _ptr(q), len(q), _ptr(out))
+        self.L.orc_sockmaps_lookup_at(self.h, _ptr(q), len(q), int(now_ns), _ptr(out))
         return out
+
+    def gc(self):
+        self.L.orc_sockmaps_gc(self.h)
+
+    def records(self):
+        return int(self.L.orc_sockmaps_records(self.h))
+
+    def join(self, recs, keys, now_ns=1):
+        """recs with empty 5-tuples filled from the timelines (a copy) and the number filled."""
+        recs = np.ascontiguousarray(recs, dtype=abi.L7_REC).copy()
+        keys = np.ascontiguousarray(keys, dtype=abi.SOCK_QUERY)
+        j = C.c_uint64(0)
+        self.L.orc_sockmaps_join(self.h, _ptr(recs), _ptr(keys), len(recs), int(now_ns), C.byref(j))
+        return recs, j.value
+
+    def alive(self, oracle, cap=1 << 20):
+        out = np.zeros(cap, dtype=abi.ALIVE_CONN)
+        n = self.L.orc_sockmaps_alive(self.h, oracle.h, _ptr(out), cap)
+        return out[:n]
 
     def close(self):
         if self.h:

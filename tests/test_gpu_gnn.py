@@ -13,11 +13,13 @@ pytestmark = pytest.mark.gpu
 RTOL, ATOL = 1e-5, 1e-6
 
 
-def _run(S, N, mix, seed):
+def _run(S, N, mix, seed, max_pairs=1 << 17):
     t = ol.Topo(S, seed=seed, mix=mix)
-    h = capi.Handle(max_endpoints=4 * S, max_pairs=1 << 17)
+    h = capi.Handle(max_endpoints=4 * S, max_pairs=max_pairs)
     h.load_tables(t.pod_ip, t.svc_ip)
-    h.submit(t.events(0, N))
+    step = 8_000_000
+    for i in range(0, N, step):
+        h.submit(t.events(i, min(step, N - i)))
     edges = h.flush()
     scores = np.zeros(len(edges), dtype=np.float32)
     n = C.c_size_t(0)
@@ -42,6 +44,18 @@ def test_gnn_scores_match_float64_reference(S, N, mix):
     err = np.abs(scores.astype(np.float64) - ref)
     assert np.all(err <= ATOL + RTOL * np.abs(ref)), (float(err.max()), int(err.argmax()))
     assert scores.std() > 1e-4    # not a constant
+
+
+def test_gnn_at_config3_scale():
+    """BASELINE.json configs[2] names a 50k-service graph: most of a million edges, several hundred thousand nodes.
+    The tensor-core layer runs thousands of 128-row tiles with gathers that miss L2; same tolerance."""
+    edges, scores, keys, h2 = _run(50_000, 40_000_000, abi.MIX_SURVEY, seed=77, max_pairs=1 << 21)
+    assert len(edges) > 500_000, len(edges)
+    nodes, h2_ref, ref = gnn_ref.run(edges)
+    assert np.array_equal(keys, nodes)
+    assert np.allclose(h2, h2_ref, rtol=1e-4, atol=1e-4), float(np.abs(h2 - h2_ref).max())
+    err = np.abs(scores.astype(np.float64) - ref)
+    assert np.all(err <= ATOL + RTOL * np.abs(ref)), (float(err.max()), int(err.argmax()))
 
 
 def test_gnn_on_empty_window_and_quantiles():

@@ -245,6 +245,14 @@ class _Line:
         ok = self.L.orc_sockline_get(self.h, ts, C.byref(out))
         return out if ok else None
 
+    def get_at(self, ts, now):
+        out = _SI()
+        ok = self.L.orc_sockline_get_at(self.h, ts, now, C.byref(out))
+        return out if ok else None
+
+    def delete_unused(self):
+        self.L.orc_sockline_delete_unused(self.h)
+
     def __len__(self):
         return self.L.orc_sockline_len(self.h)
 
@@ -304,6 +312,35 @@ def test_kat_TestAlreadyEstablishCanBeFound():
     ln.add(0, _SI(saddr=0x7979))
     got = ln.get(0)
     assert got is not None and got.saddr == 0x7979
+
+
+def test_delete_unused_hand_derived():
+    # sock_num_line.go:160-209, by hand. M = one minute of ns.
+    M = 60 * 10**9
+    # (a) <= 1 value: untouched (:165-167)
+    ln = _Line(); ln.add(10, _SI(saddr=1)); ln.delete_unused(); assert len(ln) == 1
+    # (b) [open, close]: the first loop runs while i < len-1, appends the open and stops: the close is gone.
+    ln = _Line(); ln.add(10, _SI(saddr=1)); ln.add(20, None); ln.delete_unused()
+    assert len(ln) == 1 and ln.get(15).saddr == 1 and ln.get(10**6).saddr == 1   # last value is the open now
+    # (c) two opens in a row: the first is dropped (its close never arrived, :170-176); here they are the
+    # last two values, the loop steps over both, so nothing else is lost
+    ln = _Line(); ln.add(10, _SI(saddr=1)); ln.add(20, _SI(saddr=2)); ln.delete_unused()
+    assert len(ln) == 1 and ln.get(15).saddr == 2
+    # (d) closed pairs whose open was last matched more than five minutes before the line's latest match go
+    # (:193-208): opens at 10/30/50 closes at 20/40/60, plus an open at 70 that keeps 60 in the first loop
+    ln = _Line()
+    for ts, si in [(10, _SI(saddr=1)), (20, None), (30, _SI(saddr=3)), (40, None), (50, _SI(saddr=5)), (60, None),
+                   (70, _SI(saddr=7))]:
+        ln.add(ts, si)
+    assert ln.get_at(15, 1 * M).saddr == 1          # pair (10,20) last matched at 1 min
+    assert ln.get_at(35, 3 * M).saddr == 3          # pair (30,40) at 3 min
+    assert ln.get_at(55, 7 * M).saddr == 5          # pair (50,60) at 7 min = the latest match
+    ln.delete_unused()
+    # first loop: 7 values, no two opens adjacent -> values 0..5 kept, the open at 70 dropped.
+    # second loop from the back: (50,60): 7M+5M < 7M no. (30,40): 3M+5M < 7M no. (10,20): 1M+5M < 7M yes -> gone
+    assert len(ln) == 4
+    assert ln.get(15).saddr == 3                    # before the first value, which is the open at 30 (:107-115)
+    assert ln.get(65).saddr == 5                    # after the close at 60, within a minute of the open at 50 (:97-101)
 
 
 def test_sockline_closed_last_entry_rules():
