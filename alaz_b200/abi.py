@@ -50,6 +50,10 @@ TCP_REC = np.dtype([
 ])
 assert TCP_REC.itemsize == 40
 
+# struct tcp_event as the perf ring carries it (ebpf/c/struct.h:2-12), 64 B with tail padding
+BPF_TCP_EVENT = np.dtype({"names": ["fd", "timestamp", "type", "pid", "sport", "dport", "saddr", "daddr"],
+                          "formats": ["<u8", "<u8", "<u4", "<u4", "<u2", "<u2", ("u1", (16,)), ("u1", (16,))],
+                          "offsets": [0, 8, 16, 20, 24, 26, 28, 44], "itemsize": 64})
 SOCK_QUERY = np.dtype([("fd", "<u8"), ("timestamp_ns", "<u8"), ("pid", "<u4"), ("_pad", "<u4")])
 assert SOCK_QUERY.itemsize == 24
 SOCK_RESULT = np.dtype([("found", "<u4"), ("saddr", "<u4"), ("daddr", "<u4"),

@@ -24,7 +24,7 @@ EXPORTS = [
     "alz_submit_l7_packed", "alz_submit_l7_packed_device", "alz_pack_l7",
     "alz_submit_l7_raw", "alz_window_flush", "alz_window_flush_device", "alz_window_fetch", "alz_get_stats",
     "alz_window_clock", "alz_window_epoch", "alz_gnn_score",
-    "alz_gnn_score_device", "alz_edge_quantiles", "alz_submit_tcp", "alz_sock_lookup", "alz_sock_lookup_at",
+    "alz_gnn_score_device", "alz_edge_quantiles", "alz_submit_tcp", "alz_submit_tcp_raw", "alz_sock_lookup", "alz_sock_lookup_at",
     "alz_submit_l7_join", "alz_sock_gc", "alz_sock_alive", "alz_sock_stats", "alz_comm_unique_id", "alz_comm_init",
     "alz_owner_rank",
 ]
@@ -72,6 +72,7 @@ def load(rebuild=False):
         "alz_submit_tcp": ([vp, vp, sz], i),
         "alz_sock_lookup": ([vp, vp, sz, vp], i),
         "alz_sock_lookup_at": ([vp, vp, sz, vp, u64], i),
+        "alz_submit_tcp_raw": ([vp, vp, sz], i),
         "alz_submit_l7_join": ([vp, vp, vp, sz, u64], i),
         "alz_sock_gc": ([vp], i),
         "alz_sock_alive": ([vp, vp, sz, C.POINTER(sz)], i),
@@ -97,7 +98,8 @@ def load(rebuild=False):
     if abi.ABI_VERSION < 2:    # A/B timing against a round-1 build (ALZ_LIB_PATH + ALZ_ABI_VERSION=1)
         for k in ("alz_submit_l7_packed", "alz_submit_l7_packed_device", "alz_pack_l7", "alz_window_fetch",
                   "alz_pinned_alloc_local", "alz_table_upsert_batch", "alz_window_clock", "alz_window_epoch",
-                  "alz_sock_lookup_at", "alz_submit_l7_join", "alz_sock_gc", "alz_sock_alive", "alz_sock_stats"):
+                  "alz_sock_lookup_at", "alz_submit_l7_join", "alz_sock_gc", "alz_sock_alive", "alz_sock_stats",
+                  "alz_submit_tcp_raw"):
             sig.pop(k)
     for name, (args, res) in sig.items():
         f = getattr(L, name)   # AttributeError = header/library mismatch: loud

@@ -327,6 +327,29 @@ extern "C" int alz_submit_tcp(alz_handle* h, const alz_tcp_rec* recs, size_t n) 
   return ALZ_OK;
 }
 
+// struct tcp_event (ebpf/c/struct.h:2-12): fd u64 @0, timestamp u64 @8, type u32 @16, pid u32 @20, sport u16 @24,
+// dport u16 @26, saddr[16] @28, daddr[16] @44, padded to 64
+extern "C" int alz_submit_tcp_raw(alz_handle* h, const void* raw, size_t n) {
+  if (!h || (!raw && n)) return ALZ_E_INVAL;
+  const uint8_t* p = static_cast<const uint8_t*>(raw);
+  alz_tcp_rec buf[256];
+  for (size_t done = 0; done < n;) {
+    const size_t m = std::min<size_t>(256, n - done);
+    for (size_t i = 0; i < m; ++i, p += ALZ_BPF_TCP_EVENT_SIZE) {
+      alz_tcp_rec& r = buf[i];
+      memset(&r, 0, sizeof r);
+      memcpy(&r.fd, p, 8); memcpy(&r.timestamp_ns, p + 8, 8); memcpy(&r.type, p + 16, 4); memcpy(&r.pid, p + 20, 4);
+      memcpy(&r.sport, p + 24, 2); memcpy(&r.dport, p + 26, 2);
+      r.saddr = ((uint32_t)p[28] << 24) | ((uint32_t)p[29] << 16) | ((uint32_t)p[30] << 8) | p[31];   // tcp.go:241
+      r.daddr = ((uint32_t)p[44] << 24) | ((uint32_t)p[45] << 16) | ((uint32_t)p[46] << 8) | p[47];   // tcp.go:242
+    }
+    const int rc = alz_submit_tcp(h, buf, m);
+    if (rc != ALZ_OK) return rc;
+    done += m;
+  }
+  return ALZ_OK;
+}
+
 static uint32_t pow2_at_least(size_t x) { uint32_t p = 16; while (p < x) p <<= 1; return p; }
 
 static uint32_t seg_cap_for(size_t len) { return std::max<uint32_t>(8u, pow2_at_least(len + len / 2)); }

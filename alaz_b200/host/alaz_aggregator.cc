@@ -269,4 +269,38 @@ int Aggregator::Flush(bool with_scores) {
 
 int Aggregator::Stats(alz_stats* out) { return h_ ? alz_get_stats(h_, out) : ALZ_E_STATE; }
 
+int Aggregator::ClearSocketLines(bool send_alive, int64_t check_time_ms) {
+  if (!h_) return ALZ_E_STATE;
+  std::lock_guard<std::mutex> g(mu_);
+  if (send_alive) {
+    if (tables_dirty_) {   // the export resolves against the committed tables
+      int rc = alz_table_commit(h_);
+      if (rc != ALZ_OK) return rc;
+      tables_dirty_ = false;
+    }
+    size_t n = 0;
+    if (alive_.empty()) alive_.resize(1u << 12);
+    int rc = alz_sock_alive(h_, alive_.data(), alive_.size(), &n);
+    if (rc == ALZ_E_CAPACITY) {   // n = the rows there are
+      alive_.resize(n + n / 4);
+      rc = alz_sock_alive(h_, alive_.data(), alive_.size(), &n);
+    }
+    if (rc != ALZ_OK) return rc;
+    for (size_t i = 0; i < n && ds_; ++i) {
+      const alz_alive_conn& c = alive_[i];
+      AliveConnection ac;
+      ac.CheckTime = check_time_ms;
+      ac.FromIP = FormatIPv4(c.from_ip); ac.FromType = "pod"; ac.FromPort = c.from_port;
+      ac.FromUID = c.from_id < pods_.names.size() ? pods_.names[c.from_id] : std::string("?");
+      ac.ToIP = FormatIPv4(c.to_ip); ac.ToPort = c.to_port;
+      ac.ToType = NodeTypeName(c.to_type);
+      if (c.to_type == ALZ_NODE_POD) ac.ToUID = c.to_id < pods_.names.size() ? pods_.names[c.to_id] : std::string("?");
+      else if (c.to_type == ALZ_NODE_SVC) ac.ToUID = c.to_id < svcs_.names.size() ? svcs_.names[c.to_id] : std::string("?");
+      else ac.ToUID = ac.ToIP;                                             // data.go:1672-1673
+      ds_->PersistAliveConnection(ac);
+    }
+  }
+  return alz_sock_gc(h_);
+}
+
 }  // namespace alaz

@@ -59,11 +59,21 @@ struct EdgeWindow {
   float Score = 0.f;                              // GNN anomaly score when requested
 };
 
+// datastore/dto.go AliveConnection, as sendOpenConnection fills it (aggregator/data.go:1649-1675)
+struct AliveConnection {
+  int64_t CheckTime = 0;   // unix ms
+  std::string FromIP, FromType, FromUID;
+  uint16_t FromPort = 0;
+  std::string ToIP, ToType, ToUID;
+  uint16_t ToPort = 0;
+};
+
 // the sink, next to DataStore.PersistRequest (datastore/datastore.go:13)
 class DataStore {
  public:
   virtual ~DataStore() = default;
   virtual int PersistEdgeWindow(const std::vector<EdgeWindow>& edges) = 0;
+  virtual int PersistAliveConnection(const AliveConnection&) { return 0; }   // datastore/datastore.go:19
 };
 
 struct AggregatorConfig {
@@ -96,6 +106,10 @@ class Aggregator {
   // close the window: rows grouped by edge go to ds->PersistEdgeWindow. Returns 0 or an alz_status.
   int Flush(bool with_scores = false);
   int Stats(alz_stats* out);
+  // one tick of clearSocketLines (aggregator/data.go:1681-1716, every 120 s there): with send_alive (the
+  // reference's SEND_ALIVE_TCP_CONNECTIONS) every open connection with a pod at its source goes to
+  // ds->PersistAliveConnection, then every socket line is garbage-collected (SocketLine.DeleteUnused)
+  int ClearSocketLines(bool send_alive, int64_t check_time_ms = 0);
 
   static uint32_t ParseIPv4(const std::string& s, bool* ok);   // "a.b.c.d" -> the integer IntToIPv4 takes
   static std::string FormatIPv4(uint32_t ip);
@@ -130,6 +144,7 @@ class Aggregator {
   std::vector<std::string> host_names_;
   std::vector<alz_edge_out> out_;
   std::vector<float> scores_;
+  std::vector<alz_alive_conn> alive_;
 };
 
 }  // namespace alaz

@@ -285,6 +285,12 @@ int alz_edge_quantiles(const alz_edge_out* e, const double* qs, size_t nq, doubl
  * SocketLine.AddValue (sock_num_line.go:62-80); alz_sock_lookup replaces
  * SocketLine.GetValue (sock_num_line.go:82-158). */
 int alz_submit_tcp(alz_handle* h, const alz_tcp_rec* host_recs, size_t n);
+/* n raw perf samples of the tcp_connect_events ring exactly as perf.Reader yields
+ * them: struct tcp_event (ebpf/c/struct.h:2-12; BpfTcpEvent, ebpf/tcp_state/
+ * tcp.go:63-72), 64 bytes with its tail padding. The IPv4 sits in the first four
+ * address bytes, first octet first (tcp.go:241-242). */
+#define ALZ_BPF_TCP_EVENT_SIZE 64
+int alz_submit_tcp_raw(alz_handle* h, const void* host_bpf_tcp_events, size_t n);
 int alz_sock_lookup(alz_handle* h, const alz_sock_query* host_q, size_t n,
                     alz_sock_result* host_out);
 /* the same with the caller's clock for the LastMatch stamps (the reference uses

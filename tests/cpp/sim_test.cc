@@ -34,6 +34,8 @@ struct MockDataStore : alaz::DataStore {   // main_benchmark_test.go:639-678
     }
     return 0;
   }
+  std::vector<alaz::AliveConnection> alive;
+  int PersistAliveConnection(const alaz::AliveConnection& c) override { alive.push_back(c); return 0; }
 };
 
 static uint64_t rng_state = 0x5EED5EEDull;
@@ -126,6 +128,19 @@ int main(int argc, char** argv) {
   CHECK(a.Stats(&st) == 0, "stats");
   CHECK(st.src_unresolved == 1000, "src_unresolved %" PRIu64, (uint64_t)st.src_unresolved);
   CHECK(st.tcp_events_in == (uint64_t)conf.edgeCount, "tcp events");
+  // clearSocketLines tick with SEND_ALIVE_TCP_CONNECTIONS (data.go:1681-1716): every tcpEstablish above is still
+  // open; the one whose pod was deleted and re-added under a new UID reports the new UID
+  CHECK(a.ClearSocketLines(true, 1234) == 0, "ClearSocketLines: %s", a.LastError().c_str());
+  CHECK(ds.alive.size() == (size_t)conf.edgeCount, "alive connections %zu", ds.alive.size());
+  size_t reborn = 0;
+  for (const auto& c : ds.alive) {
+    CHECK(c.FromType == "pod" && c.ToType == "service" && c.CheckTime == 1234, "alive row types");
+    CHECK(c.ToUID.rfind("svc-uid-", 0) == 0 && c.ToIP.rfind("172.20.0.", 0) == 0, "alive row destination");
+    reborn += c.FromUID == "reborn-uid";
+  }
+  size_t on_t0 = 0;
+  for (const Traffic& t : edges) on_t0 += t.pod == t0.pod;
+  CHECK(reborn == on_t0, "alive rows of the re-added pod: %zu vs %zu", reborn, on_t0);
   printf("sim ok: %" PRIu64 " rows over %d windows, %zu edges\n", expectedTotalReqProcessed, conf.testDuration,
          expected.size());
   return 0;

@@ -298,3 +298,28 @@ def test_alive_connections_export():
     rc = h.L.alz_sock_alive(h.h, small.ctypes.data_as(C.c_void_p), 10, C.byref(k))
     assert rc == abi.E_CAPACITY and k.value == len(exp)
     h.close()
+
+
+def test_raw_tcp_samples_equal_decoded_ones():
+    """alz_submit_tcp_raw takes struct tcp_event as the ring carries it (64 B, address bytes first octet first)."""
+    rng = np.random.default_rng(13)
+    pids, fds, ev = _random_tcp(rng, 500, 20000)
+    raw = np.zeros(len(ev), dtype=abi.BPF_TCP_EVENT)
+    raw["fd"], raw["timestamp"], raw["type"], raw["pid"] = ev["fd"], ev["timestamp_ns"], ev["type"], ev["pid"]
+    raw["sport"], raw["dport"] = ev["sport"], ev["dport"]
+    for f in ("saddr", "daddr"):
+        for k in range(4):
+            raw[f][:, k] = (ev[f] >> (24 - 8 * k)) & 0xFF
+        raw[f][:, 4:] = 0xEE                                    # the other twelve bytes are not read
+    q = np.zeros(50000, dtype=abi.SOCK_QUERY)
+    ql = rng.integers(0, 500, len(q))
+    q["pid"], q["fd"] = pids[ql], fds[ql]
+    q["timestamp_ns"] = rng.integers(0, 10**12, len(q)).astype(np.uint64)
+    a = capi.Handle(max_endpoints=64, max_pairs=256)
+    b = capi.Handle(max_endpoints=64, max_pairs=256)
+    a.submit_tcp(ev)
+    b._ck(b.L.alz_submit_tcp_raw(b.h, raw.ctypes.data_as(C.c_void_p), len(raw)), "alz_submit_tcp_raw")
+    ra, rb = a.sock_lookup(q, now_ns=1), b.sock_lookup(q, now_ns=1)
+    assert ra.tobytes() == rb.tobytes() and ra["found"].sum() > 1000
+    assert a.stats()["tcp_events_in"] == b.stats()["tcp_events_in"] == len(ev)
+    a.close(); b.close()
