@@ -289,7 +289,7 @@ struct alz_comm_state {
   size_t tmp_bytes = 0;
   size_t gather_cap = 0;          // keys
   // default path
-  alz_edge_out* d_send = nullptr; // [1 + max_edges]: header row + local sorted rows
+  alz_edge_out* d_send = nullptr; // [1 + block_rows_for(max_edges)]: header row + local sorted rows (+ head room)
   alz_edge_out* d_recv = nullptr; // [R * (1 + cap_r)]
   size_t recv_rows = 0;           // allocated rows of d_recv
   uint32_t cap_r = 0;             // rows per rank block of the next collective (0 = not known yet)
@@ -326,6 +326,11 @@ extern "C" int alz_comm_unique_id(void* out_id) {
   return ALZ_OK;
 }
 
+static uint32_t block_rows_for(uint64_t max_count) {   // +25 % head room, in steps of 1024 rows
+  const uint64_t want = max_count + max_count / 4 + 1024;
+  return (uint32_t)((want + 1023) / 1024 * 1024);
+}
+
 extern "C" int alz_comm_init(alz_handle* h, int nranks, int rank, const void* id_bytes) {
   if (!h || !id_bytes || nranks < 1 || rank < 0 || rank >= nranks) return ALZ_E_INVAL;
   std::lock_guard<std::mutex> g(h->mu);
@@ -354,7 +359,11 @@ extern "C" int alz_comm_init(alz_handle* h, int nranks, int rank, const void* id
   CK(cudaMalloc(&c->d_vals, me * 4));
   c->tmp_bytes = std::max(sort_pairs_temp_bytes((uint32_t)me), scan_temp_bytes((uint32_t)me));
   CK(cudaMalloc(&c->d_tmp, c->tmp_bytes));
-  CK(cudaMalloc(&c->d_send, (me + 1) * sizeof(alz_edge_out)));
+  // a block is sized from the largest rank's count plus head room: up to block_rows_for(max_edges) rows are SENT
+  // from here even when this rank has fewer (max_edges must be the same on every rank)
+  const size_t send_rows = (size_t)block_rows_for(me) + 1;
+  CK(cudaMalloc(&c->d_send, send_rows * sizeof(alz_edge_out)));
+  CK(cudaMemset(c->d_send, 0, send_rows * sizeof(alz_edge_out)));
   CK(cudaMallocHost(&c->h_hdr, sizeof(alz_edge_out)));
   CK(cudaMalloc(&c->d_info, sizeof(MergeInfo)));
   CK(cudaMallocHost(&c->h_info, sizeof(MergeInfo)));
@@ -444,11 +453,6 @@ static int merge_allreduce(alz_handle* h) {
   h->last_n_edges = n_can;
   h->windows++;
   return ALZ_OK;
-}
-
-static uint32_t block_rows_for(uint64_t max_count) {   // +25 % head room, in steps of 1024 rows
-  const uint64_t want = max_count + max_count / 4 + 1024;
-  return (uint32_t)((want + 1023) / 1024 * 1024);
 }
 
 // Called by the flush after prepare_flush(): local live edges are sorted in d_keys[1] (keys) / d_rows[1]
