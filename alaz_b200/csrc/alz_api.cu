@@ -62,12 +62,18 @@ static int alloc_table(alz_handle* h, AccTable* t, uint32_t max_rows, uint32_t* 
   const size_t rows = (size_t)max_rows + kPairKinds;
   CK(cudaMalloc(&t->dict, (size_t)dict_cap * sizeof(DictEnt)));
   CK(cudaMalloc(&t->row_key, rows * 8));
-  CK(cudaMalloc(&t->lat_sum, rows * 8));
-  CK(cudaMalloc(&t->err5xx, rows * 8));
   if (!pair_table) {
+    CK(cudaMalloc(&t->lat_sum, rows * 8));
+    CK(cudaMalloc(&t->err5xx, rows * 8));
     CK(cudaMalloc(&t->count, rows * 8));
+    CK(cudaMalloc(&t->hist, rows * ALZ_NB * 4));
     CK(cudaMemsetAsync(t->count, 0, rows * 8, h->stream));
+    CK(cudaMemsetAsync(t->lat_sum, 0, rows * 8, h->stream));
+    CK(cudaMemsetAsync(t->err5xx, 0, rows * 8, h->stream));
+    CK(cudaMemsetAsync(t->hist, 0, rows * ALZ_NB * 4, h->stream));
   } else {
+    CK(cudaMalloc(&t->sect, rows * kSectPerRow * 32));
+    CK(cudaMemsetAsync(t->sect, 0, rows * kSectPerRow * 32, h->stream));
     // reversed rows are a few per cent of the traffic: a quarter-size dictionary is ample, and both
     // dictionaries draw rows from the one pool
     const uint32_t rev_cap = std::max<uint32_t>(1024u, dict_cap >> 2);
@@ -86,16 +92,12 @@ static int alloc_table(alz_handle* h, AccTable* t, uint32_t max_rows, uint32_t* 
     CK(cudaMalloc(&t->row_base, rows)); CK(cudaMemsetAsync(t->row_base, 0, rows, h->stream));
     CK(cudaMalloc(&t->row_aux, rows * 4));
   }
-  CK(cudaMalloc(&t->hist, rows * ALZ_NB * 4));
   CK(cudaMemsetAsync(t->dict, 0xFF, (size_t)dict_cap * sizeof(DictEnt), h->stream));
-  CK(cudaMemsetAsync(t->lat_sum, 0, rows * 8, h->stream));
-  CK(cudaMemsetAsync(t->err5xx, 0, rows * 8, h->stream));
-  CK(cudaMemsetAsync(t->hist, 0, rows * ALZ_NB * 4, h->stream));
   return ALZ_OK;
 }
 static void free_table(AccTable* t) {
   cudaFree(t->dict); cudaFree(t->dict_rev); cudaFree(t->dict_host); cudaFree(t->row_key); cudaFree(t->row_kind); cudaFree(t->lat_sum);
-  cudaFree(t->err5xx); cudaFree(t->count); cudaFree(t->row_cnt); cudaFree(t->row_base); cudaFree(t->row_aux); cudaFree(t->hist);
+  cudaFree(t->err5xx); cudaFree(t->count); cudaFree(t->row_cnt); cudaFree(t->row_base); cudaFree(t->row_aux); cudaFree(t->hist); cudaFree(t->sect);
   memset(t, 0, sizeof(*t));
 }
 // all keys out of the dictionaries, row allocator back to zero (rows were zeroed by fold / gather)

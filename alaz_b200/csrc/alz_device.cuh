@@ -160,8 +160,24 @@ struct AccTable {
   uint8_t* row_base;  // [max_rows + 3] (pair table only) first bucket / 4 of the 16-bucket window that held most of
                       // the row's events at the last fold (the per-CTA table keeps only such a window per pair)
   uint32_t* row_aux;  // [max_rows + 3] (pair table only) edge row found by fold_resolve_kernel
-  uint32_t* hist;     // [(max_rows + 3) * ALZ_NB]
+  uint32_t* hist;     // [(max_rows + 3) * ALZ_NB] (edge table only)
+  // Pair table rows are kept in 32-byte SECTORS, 16 per row (512 B): sector g = { cells 4g, 4g+1 | cells 4g+2, 4g+3 |
+  // latency partial u64 | 5xx partial u64 }. A global reduction costs the SM one LSU pass per distinct sector an
+  // instruction touches, not per lane (scripts/micro/red_merge.cu on B200: a histogram increment and a latency add as
+  // two instructions = 93 G events/s chip-wide whether or not they share a sector; as ONE red.u64 instruction with two
+  // lanes on the same sector = 172 G/s, the price of a single reduction, 188 G/s). So an event's cell and latency live
+  // in one sector and are added by a lane pair of one instruction; a row's latency / 5xx totals are the sums of its 16
+  // partials (fold_pairs_kernel). A cell pair is added to as a u64: cells are u32 and a fold runs before any cell
+  // could reach 2^31 (alz_api.cu), so nothing carries from the low cell into the high one.
+  uint64_t* sect;     // [(max_rows + 3) * kSectPerRow * 4] (pair table only; hist / lat_sum / err5xx are null there)
 };
+constexpr uint32_t kSectPerRow = 16;
+__device__ __forceinline__ uint64_t* pair_sect(const AccTable& t, uint32_t row, uint32_t bucket) {
+  return t.sect + ((size_t)row * kSectPerRow + (bucket >> 2)) * 4u;
+}
+__device__ __forceinline__ uint32_t* pair_cell(const AccTable& t, uint32_t row, uint32_t bucket) {
+  return reinterpret_cast<uint32_t*>(pair_sect(t, row, bucket)) + (bucket & 3u);
+}
 
 // row of `key`, inserting it if absent; >= kLostRow when capacity is exhausted
 __device__ __forceinline__ uint32_t find_or_insert(const AccTable& t, uint64_t key) {

@@ -246,9 +246,37 @@ __device__ __forceinline__ uint64_t keep_policy() {
 }
 __device__ __forceinline__ void global_add(const AccTable& t, uint32_t row, uint32_t bucket, uint64_t dur, bool err) {
   const uint64_t pol = keep_policy();
-  red_add_u32_keep(&t.hist[(size_t)row * ALZ_NB + bucket], 1u, pol);
-  red_add_u64_keep(&t.lat_sum[row], dur, pol);
-  if (err) red_add_u64_keep(&t.err5xx[row], 1ull, pol);
+  uint64_t* sc = pair_sect(t, row, bucket);
+  red_add_u32_keep(reinterpret_cast<uint32_t*>(sc) + (bucket & 3u), 1u, pol);
+  red_add_u64_keep(sc + 2, dur, pol);
+  if (err) red_add_u64_keep(sc + 3, 1ull, pol);
+}
+// The same for up to 32 events held one per lane (`on`, row, meta = bucket | ... | err << 8 | dur_hi << 9, dur_lo), as
+// ONE red.u64 instruction per 16 events: lane pair (2j, 2j+1) takes one event, the even lane adds to the cell pair,
+// the odd lane the duration, both in the event's sector, which the LSU serves in one pass (alz_device.cuh, AccTable).
+// kSparse: the events sit in arbitrary lanes and pair j takes lane 2j's in round 0, lane 2j+1's in round 1; otherwise
+// round r takes lanes 16r..16r+15 in order. All lanes must call this.
+template <bool kSparse>
+__device__ __forceinline__ void global_add_paired(const AccTable& t, bool on, uint32_t row, uint32_t meta, uint32_t dlo) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t have = __ballot_sync(0xFFFFFFFFu, on);
+  if (have == 0u) return;
+  const uint64_t pol = keep_policy();
+  const uint32_t odd = lane & 1u;
+#pragma unroll
+  for (uint32_t r = 0; r < 2u; ++r) {
+    if ((have & (kSparse ? (r ? 0xAAAAAAAAu : 0x55555555u) : (r ? 0xFFFF0000u : 0x0000FFFFu))) == 0u) continue;   // warp-uniform
+    const uint32_t src = kSparse ? ((lane & ~1u) | r) : (r * 16u + (lane >> 1));
+    const uint32_t row_s = __shfl_sync(0xFFFFFFFFu, row, src);
+    const uint32_t meta_s = __shfl_sync(0xFFFFFFFFu, meta, src);
+    const uint32_t dlo_s = __shfl_sync(0xFFFFFFFFu, dlo, src);
+    if ((have >> src) & 1u) {
+      uint64_t* sc = pair_sect(t, row_s, meta_s & 0x3Fu);
+      const uint64_t dur = ((uint64_t)(meta_s >> 9) << 32) | dlo_s;
+      red_add_u64_keep(odd ? sc + 2 : sc + ((meta_s & 3u) >> 1), odd ? dur : 1ull << (32u * (meta_s & 1u)), pol);
+      if (odd && (meta_s & 0x100u)) red_add_u64_keep(sc + 3, 1ull, pol);   // 5xx: rare
+    }
+  }
 }
 
 // slow tier for one event (walks the dictionary): the pair is new to it, or its home slot is taken by another
@@ -315,7 +343,7 @@ __device__ __forceinline__ void cold_consume(ColdQueue& q, uint32_t count, const
   if (valid) { e = *q.at(lane); ent = probe[lane]; }
   const bool filtered = valid && ent.z == kDropRow && ent.w == 1u;
   const bool home = valid && !filtered && ent.x == e.x && ent.y == e.y && ent.z < kDropRow && (e.x & e.y) != 0xFFFFFFFFu;
-  if (home && !(c_diag & 1)) global_add(t, ent.z, e.w & 0x3Fu, ((uint64_t)(e.w >> 9) << 32) | e.z, (e.w & 0x100u) != 0u);
+  global_add_paired<false>(t, home && !(c_diag & 1), ent.z, e.w, e.z);
   if (filtered) *unresolved += 1u;
   slow.push(valid && !home && !filtered, ((uint64_t)e.y << 32) | e.x, e.z, e.w, lane_lt);
   __syncwarp();
@@ -365,12 +393,15 @@ __device__ __forceinline__ void drain_rows_and_count(const Shared& s, const AccT
       if (hl == 0) { if (grow == kDropRow) unresolved += tot; else lost += tot; }
       continue;
     }
+    // the window's 16 cells = 4 sectors of the global row, 4 lanes each; the row's latency and 5xx totals go to the
+    // partials of the window's first sector (any sector of the row would do: the fold sums them)
     const uint32_t base = (uint32_t)s.rowbase[r] * 4u;
-    if (cnt) red_add_u32(&pairs.hist[(size_t)grow * ALZ_NB + base + hl], cnt);
+    if (cnt) red_add_u32(pair_cell(pairs, grow, base + hl), cnt);
     if (hl == 0) {
       const uint64_t lat = (((uint64_t)row[10] << 32) + row[9]) + (((uint64_t)row[12] << 32) + row[11]);
-      if (lat) red_add_u64(&pairs.lat_sum[grow], lat);
-      if (row[8]) red_add_u64(&pairs.err5xx[grow], (uint64_t)row[8]);
+      uint64_t* sc = pair_sect(pairs, grow, base);
+      if (lat) red_add_u64(sc + 2, lat);
+      if (row[8]) red_add_u64(sc + 3, (uint64_t)row[8]);
     }
   }
   for (int o = 16; o > 0; o >>= 1) {
@@ -600,7 +631,7 @@ ingest_pairs_v8_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
           // this lane took the cell to 0x8000: move 0x8000 counts into the global table (rare: a pair with more
           // than 32767 events in one bucket within one launch of one CTA)
           const uint32_t grow = find_or_insert_pair(pairs, key[u], kPairFwd, ep, ep_mask);
-          if (grow < kDropRow) red_add_u32(&pairs.hist[(size_t)grow * ALZ_NB + bucket], 0x8000u);
+          if (grow < kDropRow) red_add_u32(pair_cell(pairs, grow, bucket), 0x8000u);
           else if (grow == kDropRow) unresolved += 0x8000u; else lost += 0x8000u;
           atomicSub(&row[d >> 1], 0x8000u << sh);
         }
@@ -699,7 +730,7 @@ __device__ __forceinline__ void cold_finish(bool valid, uint32_t klo, uint32_t k
   if (valid) ent = slot[lane];
   const bool filtered = valid && ent.z == kDropRow && ent.w == 1u;
   const bool home = valid && !filtered && ent.x == klo && ent.y == khi && ent.z < kDropRow && (klo & khi) != 0xFFFFFFFFu;
-  if (home) global_add(t, ent.z, meta & 0x3Fu, ((uint64_t)(meta >> 9) << 32) | dlo, (meta & 0x100u) != 0u);
+  global_add_paired<true>(t, home, ent.z, meta, dlo);
   if (filtered) *unresolved += 1u;
   slow.push(valid && !home && !filtered, ((uint64_t)khi << 32) | klo, dlo, meta, lane_lt);
   __syncwarp();
@@ -868,7 +899,7 @@ ingest_pairs_v9_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
       const uint32_t old = atomicAdd(&row[d >> 1], 1u << sh);
       if (((old >> sh) & 0xFFFFu) == kCellSpill) {
         const uint32_t grow = find_or_insert_pair(pairs, key, kPairFwd, ep, ep_mask);
-        if (grow < kDropRow) red_add_u32(&pairs.hist[(size_t)grow * ALZ_NB + bucket], 0x8000u);
+        if (grow < kDropRow) red_add_u32(pair_cell(pairs, grow, bucket), 0x8000u);
         else if (grow == kDropRow) unresolved += 0x8000u; else lost += 0x8000u;
         atomicSub(&row[d >> 1], 0x8000u << sh);
       }

@@ -50,6 +50,14 @@ __device__ __forceinline__ void global_accumulate(const AccTable& t, uint32_t ro
   if (err) atomicAdd((unsigned long long*)&t.err5xx[row], 1ull);
 }
 
+// the same into a pair row (sectored layout, alz_device.cuh); v1 plan: one lane per event, three instructions
+__device__ __forceinline__ void pair_accumulate(const AccTable& t, uint32_t row, uint32_t bucket, uint64_t dur, bool err) {
+  uint64_t* sc = pair_sect(t, row, bucket);
+  atomicAdd(reinterpret_cast<uint32_t*>(sc) + (bucket & 3u), 1u);
+  atomicAdd((unsigned long long*)(sc + 2), (unsigned long long)dur);
+  if (err) atomicAdd((unsigned long long*)(sc + 3), 1ull);
+}
+
 __device__ __forceinline__ void flush_thread_counters(Counters* ctr, uint32_t not_request, uint32_t unresolved,
                                                       uint32_t lost) {
   for (int o = 16; o > 0; o >>= 1) {
@@ -93,7 +101,7 @@ __global__ void __launch_bounds__(256) ingest_pairs_kernel(const alz_l7_rec* __r
       if (e.act) {
         if (row == kDropRow) ++unresolved;
         else if (row >= kLostRow) ++lost;
-        else global_accumulate(pairs, row, e.bucket, e.dur, e.err);
+        else pair_accumulate(pairs, row, e.bucket, e.dur, e.err);
       }
     }
   }
@@ -161,9 +169,9 @@ __global__ void __launch_bounds__(256) fold_resolve_kernel(AccTable pairs, const
     const uint64_t key = sentinel ? kEmptyKey : pairs.row_key[row];
     const uint32_t kind = sentinel ? (i - n_rows) : pairs.row_kind[row];
     if (sentinel) {                                            // the sentinel rows exist even when unused
-      uint32_t any = 0;
-      for (int b = 0; b < ALZ_NB; ++b) any |= pairs.hist[(size_t)row * ALZ_NB + b];
-      if (any == 0u) { pairs.row_aux[row] = kDropRow; continue; }
+      uint64_t any = 0;
+      for (uint32_t g = 0; g < kSectPerRow; ++g) { const uint64_t* sc = pairs.sect + ((size_t)row * kSectPerRow + g) * 4u; any |= sc[0] | sc[1]; }
+      if (any == 0ull) { pairs.row_aux[row] = kDropRow; continue; }
     }
     uint64_t ekey = 0;
     uint32_t erow = kDropRow;                                  // source is not a pod: data.go:829-832
@@ -188,10 +196,17 @@ __global__ void __launch_bounds__(256) fold_pairs_kernel(AccTable pairs, AccTabl
   for (uint32_t it = 0; it < n_iter; ++it, i += groups_per_grid) {
     const bool valid = i < n_rows + kPairKinds;
     const uint32_t row = !valid ? 0u : (i >= n_rows) ? pairs.max_rows + (i - n_rows) : i;
-    uint4* cells = reinterpret_cast<uint4*>(pairs.hist + (size_t)row * ALZ_NB + sl * 8u);
-    uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
-    if (valid) { a = cells[0]; b = cells[1]; }
+    // the lane's two sectors = 64 contiguous bytes: cells 8sl..8sl+3 | lat, 5xx partials | cells 8sl+4..8sl+7 | partials
+    uint4* cells = reinterpret_cast<uint4*>(pairs.sect + ((size_t)row * kSectPerRow + sl * 2u) * 4u);
+    uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a, pa = a, pb = a;
+    if (valid) { a = cells[0]; pa = cells[1]; b = cells[2]; pb = cells[3]; }
+    uint64_t lat = ((((uint64_t)pa.y << 32) | pa.x) + (((uint64_t)pb.y << 32) | pb.x));
+    uint64_t e5 = ((((uint64_t)pa.w << 32) | pa.z) + (((uint64_t)pb.w << 32) | pb.z));
     uint64_t cnt = (uint64_t)a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+    for (int o = 1; o < 8; o <<= 1) {
+      lat += __shfl_xor_sync(0xFFFFFFFFu, lat, o);
+      e5 += __shfl_xor_sync(0xFFFFFFFFu, e5, o);
+    }
     cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 1);
     cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 2);
     cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 4);
@@ -228,9 +243,8 @@ __global__ void __launch_bounds__(256) fold_pairs_kernel(AccTable pairs, AccTabl
       if (b.w) atomicAdd(dst + 7, b.w);
       if (sl == 0) {
         atomicAdd((unsigned long long*)&edges.count[erow], (unsigned long long)cnt);
-        atomicAdd((unsigned long long*)&edges.lat_sum[erow], (unsigned long long)pairs.lat_sum[row]);
-        const uint64_t e = pairs.err5xx[row];
-        if (e) atomicAdd((unsigned long long*)&edges.err5xx[erow], (unsigned long long)e);
+        atomicAdd((unsigned long long*)&edges.lat_sum[erow], (unsigned long long)lat);
+        if (e5) atomicAdd((unsigned long long*)&edges.err5xx[erow], (unsigned long long)e5);
       }
     } else if (sl == 0) {
       if (erow == kDropRow) atomicAdd(&ctr->src_unresolved, (unsigned long long)cnt);
@@ -238,7 +252,8 @@ __global__ void __launch_bounds__(256) fold_pairs_kernel(AccTable pairs, AccTabl
     }
     cells[0] = make_uint4(0u, 0u, 0u, 0u);
     cells[1] = make_uint4(0u, 0u, 0u, 0u);
-    if (sl == 0) { pairs.lat_sum[row] = 0ull; pairs.err5xx[row] = 0ull; }
+    cells[2] = make_uint4(0u, 0u, 0u, 0u);
+    cells[3] = make_uint4(0u, 0u, 0u, 0u);
   }
 }
 
