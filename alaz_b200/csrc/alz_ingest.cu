@@ -14,8 +14,8 @@
 //   hot   the event's socket pair is in the CTA's shared-memory table. A row holds a 16-bucket
 //         WINDOW of the latency histogram in 16-bit cells (52 bytes instead of 292: the window is
 //         where the pair's latencies fall, chosen from its own histogram at the previous fold), so
-//         ~1250 pairs fit and ~77 % of the events of a Zipf(1.1) stream end here: two probes of a
-//         2-choice direct-mapped index (fingerprint | window | row), one key load, two shared
+//         ~1250 pairs fit and ~77 % of the events of a Zipf(1.1) stream end here: one 8-byte load of a
+//         2-way bucket of the index (fingerprint | window | row per entry), one key load, two shared
 //         reductions. 16-bit cells stay exact: the lane that sees a cell at 0x7FFF spills 0x8000
 //         counts into the global table (bit 15 is head room for the increments racing with it).
 //   cold  everything else (a pair without a row, a latency outside its row's window, a reversed
@@ -55,7 +55,7 @@ namespace {
 
 constexpr uint32_t kRowWords = 13;         // 8 words = 16 x u16 histogram cells, err5xx u32, 2 x (lat_lo, lat_hi); odd stride
 constexpr uint32_t kCellSpill = 0x7FFFu;   // a 16-bit cell seen at this value is spilled (bit 15 = head room)
-constexpr uint32_t kTab = 4096;            // index entries: fingerprint 16 | window base 4 | row 12, two choices per key
+constexpr uint32_t kTab = 4096;            // index entries: fingerprint 16 | window base 4 | row 12, in buckets of two
 constexpr uint32_t kTabShift = 20;
 constexpr uint32_t kRowMask = 0xFFFu;
 constexpr uint32_t kBusy = kRowMask;       // entry whose row field is no row: claimed, not (or never) published
@@ -171,8 +171,10 @@ constexpr uint32_t kProtoLut = proto_class(0) | proto_class(1) << 3 | proto_clas
 __device__ __forceinline__ uint32_t table_hash(uint64_t key) {
   return (uint32_t)key * 0x9E3779B1u + (uint32_t)(key >> 32) * 0x85EBCA6Bu;
 }
-__device__ __forceinline__ uint32_t tab_idx1(uint32_t h) { return h >> kTabShift; }
-__device__ __forceinline__ uint32_t tab_idx2(uint32_t h) { return (h * 0xC2B2AE35u) >> kTabShift; }
+// the key's two index slots are the two halves of one 8-byte bucket: one LDS.64 fetches both (two independent
+// 4-byte probes cost two instructions and, with 32 random addresses each, about twice the shared-memory passes)
+__device__ __forceinline__ uint32_t tab_idx1(uint32_t h) { return (h >> kTabShift) & ~1u; }
+__device__ __forceinline__ uint32_t tab_idx2(uint32_t h) { return (h >> kTabShift) | 1u; }
 // the filter of pod addresses (alz_api.cu keeps it in step with the table): false = certainly not a pod
 __device__ __forceinline__ bool maybe_pod(const uint32_t* bloom, uint32_t ip) {
   const uint32_t h = hash32(ip);
@@ -615,10 +617,11 @@ ingest_pairs_v8_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
       dlo[u] = (uint32_t)dur;
       meta[u] = bucket | (kind << 6) | (err ? 0x100u : 0u) | (dhi << 9);
 
-      // per-CTA table: two index probes, the matching entry names the row and its histogram window
+      // per-CTA table: the key's bucket of two index entries, the matching one names the row and its histogram window
       const uint32_t h = table_hash(key[u]);
       const uint32_t fp = tab_fp(h);
-      const uint32_t x1 = s.tab[tab_idx1(h)] ^ fp, x2 = s.tab[tab_idx2(h)] ^ fp;
+      const uint2 t2 = *reinterpret_cast<const uint2*>(&s.tab[tab_idx1(h)]);
+      const uint32_t x1 = t2.x ^ fp, x2 = t2.y ^ fp;
       const uint32_t x = x1 < 0x10000u ? x1 : x2;                    // upper 16 bits 0: the fingerprint matched
       const uint32_t r = min(x & kRowMask, kRows);
       const uint32_t d = bucket - ((x >> 12) & 15u) * 4u;            // cell of this latency in the row's window
@@ -888,7 +891,8 @@ ingest_pairs_v9_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
 
     const uint32_t h = table_hash(key);
     const uint32_t fp = tab_fp(h);
-    const uint32_t x1 = s.tab[tab_idx1(h)] ^ fp, x2 = s.tab[tab_idx2(h)] ^ fp;
+    const uint2 t2 = *reinterpret_cast<const uint2*>(&s.tab[tab_idx1(h)]);
+    const uint32_t x1 = t2.x ^ fp, x2 = t2.y ^ fp;
     const uint32_t x = x1 < 0x10000u ? x1 : x2;
     const uint32_t r = min(x & kRowMask, kRows);
     const uint32_t d = bucket - ((x >> 12) & 15u) * 4u;
