@@ -66,10 +66,10 @@ constexpr uint32_t kSmemMax = 232448;      // 227 KB per CTA on sm_100
 constexpr int kU = 2;                      // events per lane per iteration
 constexpr uint32_t kChunk = 32u * kU;      // events per warp per iteration = one TMA copy
 
-template <int kWarps, int kRecWords>
+template <int kWarps, int kRecWords, int kStages = 2>
 struct Layout {
   static constexpr uint32_t kChunkBytes = kChunk * kRecWords * 4u;
-  static constexpr uint32_t kRing = (uint32_t)kWarps * 2u * kChunkBytes;
+  static constexpr uint32_t kRing = (uint32_t)kWarps * (uint32_t)kStages * kChunkBytes;
   static constexpr uint32_t kBars = kRing;                              // kWarps * 2 mbarriers
   static constexpr uint32_t kTabOff = kBars + (uint32_t)kWarps * 16u;
   static constexpr uint32_t kBloomOff = kTabOff + kTab * 4u;            // pod-address filter, ALZ_BLOOM_WORDS words
@@ -435,13 +435,16 @@ struct WinClock {
 // kWin (32-B records only): an event whose write_time lies beyond the open window is not reduced but appended
 // to `defer_buf` (it is submitted again when its window opens); one that lies before it is late: reduced into
 // the open window and counted.
-template <int kWarps, int kRecWords, bool kWin>
+// kStages = 2: the chunk after the one being worked on has landed or is in flight, the one after that is requested
+// when this one's records are in registers. kStages = 1: a single 2-KB stage per warp — the next chunk is requested
+// as soon as this one's records are in registers and has one iteration to arrive; the 2 KB per warp saved go to rows.
+template <int kWarps, int kRecWords, bool kWin, int kStages>
 __global__ void __launch_bounds__(kWarps * 32, 1)
 ingest_pairs_v8_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable pairs, Counters* ctr,
                        const HotState* __restrict__ hot, const EpEntry* __restrict__ ep, uint32_t ep_mask,
                        const uint32_t* __restrict__ bloom_g, const uint64_t* __restrict__ dur_ovf,
                        const WinClock* __restrict__ win, uint4* __restrict__ defer_buf, uint32_t defer_cap) {
-  using L = Layout<kWarps, kRecWords>;
+  using L = Layout<kWarps, kRecWords, kStages>;
   constexpr uint32_t kRows = L::kRows;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -459,7 +462,7 @@ ingest_pairs_v8_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
   slow.bind(smem_raw + L::kSlowOff + (size_t)warp * kSlowQ * kQBytes);
   uint4* probe = reinterpret_cast<uint4*>(smem_raw + L::kProbeOff + (size_t)warp * 512u);
   const uint32_t probe_a = smem_u32(probe);
-  const uint8_t* ring = smem_raw + (size_t)warp * 2u * L::kChunkBytes;
+  const uint8_t* ring = smem_raw + (size_t)warp * (uint32_t)kStages * L::kChunkBytes;
   const uint32_t ring_a = smem_u32(ring);
   const uint32_t bar_a = smem_u32(smem_raw + L::kBars + warp * 16u);
 
@@ -491,11 +494,14 @@ ingest_pairs_v8_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     issue(0u, 0u);
-    c_next += c_stride; src_next += src_step;
-    issue(1u, 0u);
+    if (kStages == 2) {
+      c_next += c_stride; src_next += src_step;
+      issue(1u, 0u);
+    }
   }
-  c_next += 2u * c_stride - (lane == 0 ? c_stride : 0u);   // every lane tracks the producer state, so any lane can be elected
-  src_next += 2u * src_step - (lane == 0 ? src_step : 0u);
+  // every lane tracks the producer state, so any lane can be elected
+  c_next += (uint32_t)kStages * c_stride - ((kStages == 2 && lane == 0) ? c_stride : 0u);
+  src_next += (uint64_t)kStages * src_step - ((kStages == 2 && lane == 0) ? src_step : 0u);
 
   for (uint32_t i = threadIdx.x; i < kTab; i += kWarps * 32) s.tab[i] = 0u;
   for (uint32_t i = threadIdx.x; i < ALZ_BLOOM_WORDS; i += kWarps * 32) s.bloom[i] = bloom_g ? bloom_g[i] : 0xFFFFFFFFu;
@@ -530,9 +536,9 @@ ingest_pairs_v8_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
   const long long p_begin = PROF_NOW();
   uint32_t it = 0;
   for (uint32_t c = c_first; c < n_chunks; c += c_stride, ++it) {
-    const uint32_t stage = it & 1u;
+    const uint32_t stage = kStages == 2 ? (it & 1u) : 0u;
     pc0 = PROF_NOW();
-    mbar_wait(bar_a + stage * 8u, (it >> 1) & 1u);
+    mbar_wait(bar_a + stage * 8u, kStages == 2 ? ((it >> 1) & 1u) : (it & 1u));
     pc1 = PROF_NOW();
     PROF_ADD(1, pc1 - pc0);
     PROF_ADD(6, 1);
@@ -589,33 +595,33 @@ ingest_pairs_v8_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
     }
     n_live += n_here;
 
-    // hot tier for both events of the lane, then one pass over the cold queue
-    uint64_t key[kU];
-    uint32_t dlo[kU], meta[kU];
-    bool coldf[kU];
+    // hot tier for both events of the lane, then one pass over the cold queue. The two events go through the tier
+    // phase by phase (decode + index bucket, row key, reductions) rather than one after the other: a phase's loads
+    // of both events are in flight together, and the divergent regions (the reductions) come last
+    uint64_t key[kU], dur[kU];
+    uint32_t dlo[kU], meta[kU], cell[kU], rowi[kU];
+    bool coldf[kU], act[kU], cand[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const uint32_t mw = (kRecWords == 8) ? w[u][3] : w[u][2];   // status | protocol << 16 | method_flags << 24
       uint32_t p = __byte_perm(mw, 0u, 0x4442u);                  // protocol byte, flag bits still on
-      uint64_t dur;
-      if (kRecWords == 8) dur = ((uint64_t)w[u][5] << 32) | w[u][4];
+      if (kRecWords == 8) dur[u] = ((uint64_t)w[u][5] << 32) | w[u][4];
       else {
-        dur = w[u][3];
-        if (p & ALZ_REC16_DUR_OVERFLOW) dur = live[u] ? __ldg(&dur_ovf[w[u][3]]) : 0ull;
+        dur[u] = w[u][3];
+        if (p & ALZ_REC16_DUR_OVERFLOW) dur[u] = live[u] ? __ldg(&dur_ovf[w[u][3]]) : 0ull;
       }
       const bool hk = (p & ALZ_PROTO_F_HOSTKEY) != 0u;             // daddr is a Host-header id: own key space, cold tier
       p &= 0x3Fu;
       const uint32_t cls = shr_clamp(kProtoLut, 3u * p);
       // a row is built unless the class says "payload parser decides" and the parser said no (bit 30 of mw)
-      const bool act = live[u] && (cls & 1u) && !((cls & 2u) && (mw & ((uint32_t)ALZ_MF_PAYLOAD_REJECT << 24)));
+      act[u] = live[u] && (cls & 1u) && !((cls & 2u) && (mw & ((uint32_t)ALZ_MF_PAYLOAD_REJECT << 24)));
       const bool rv = (cls & 4u) && (mw & ((uint32_t)ALZ_MF_METHOD_MASK << 24)) == (2u << 24);   // DELIVER / PUSHED_EVENT
       const bool err = p == ALZ_PROTO_HTTP && ((mw & 0xFFFFu) - 500u) < 100u;
       key[u] = ((uint64_t)w[u][1] << 32) | w[u][0];               // make_pair_key: the record's first two words as they lie
-      const uint32_t bucket = latency_bucket_rz(dur);
+      const uint32_t bucket = latency_bucket_rz(dur[u]);
       const uint32_t kind = hk ? kPairHost : rv ? kPairRev : kPairFwd;
-      const uint32_t dhi = (uint32_t)(dur >> 32);
-      dlo[u] = (uint32_t)dur;
-      meta[u] = bucket | (kind << 6) | (err ? 0x100u : 0u) | (dhi << 9);
+      dlo[u] = (uint32_t)dur[u];
+      meta[u] = bucket | (kind << 6) | (err ? 0x100u : 0u) | ((uint32_t)(dur[u] >> 32) << 9);
 
       // per-CTA table: the key's bucket of two index entries, the matching one names the row and its histogram window
       const uint32_t h = table_hash(key[u]);
@@ -623,18 +629,26 @@ ingest_pairs_v8_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
       const uint2 t2 = *reinterpret_cast<const uint2*>(&s.tab[tab_idx1(h)]);
       const uint32_t x1 = t2.x ^ fp, x2 = t2.y ^ fp;
       const uint32_t x = x1 < 0x10000u ? x1 : x2;                    // upper 16 bits 0: the fingerprint matched
-      const uint32_t r = min(x & kRowMask, kRows);
-      const uint32_t d = bucket - ((x >> 12) & 15u) * 4u;            // cell of this latency in the row's window
-      const bool hit = act && kind == kPairFwd && x < 0x10000u && (x & kRowMask) < kRows && d < 16u && s.rowkey[r] == key[u];
-      uint32_t* row = s.rows + r * kRowWords;
-      if (hit) {
+      rowi[u] = min(x & kRowMask, kRows);
+      cell[u] = bucket - ((x >> 12) & 15u) * 4u;                     // cell of this latency in the row's window
+      cand[u] = act[u] && kind == kPairFwd && x < 0x10000u && (x & kRowMask) < kRows && cell[u] < 16u;
+    }
+    bool hit[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) hit[u] = cand[u] && s.rowkey[rowi[u]] == key[u];   // row kRows holds no key
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      uint32_t* row = s.rows + rowi[u] * kRowWords;
+      const uint32_t d = cell[u];
+      const uint32_t dhi = (uint32_t)(dur[u] >> 32);
+      if (hit[u]) {
         const uint32_t sh = (d & 1u) * 16u;
         const uint32_t old = atomicAdd(&row[d >> 1], 1u << sh);
         if (((old >> sh) & 0xFFFFu) == kCellSpill) {
           // this lane took the cell to 0x8000: move 0x8000 counts into the global table (rare: a pair with more
           // than 32767 events in one bucket within one launch of one CTA)
           const uint32_t grow = find_or_insert_pair(pairs, key[u], kPairFwd, ep, ep_mask);
-          if (grow < kDropRow) red_add_u32(pair_cell(pairs, grow, bucket), 0x8000u);
+          if (grow < kDropRow) red_add_u32(pair_cell(pairs, grow, meta[u] & 0x3Fu), 0x8000u);
           else if (grow == kDropRow) unresolved += 0x8000u; else lost += 0x8000u;
           atomicSub(&row[d >> 1], 0x8000u << sh);
         }
@@ -642,14 +656,15 @@ ingest_pairs_v8_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
         const uint32_t oldl = atomicAdd(&lat[0], dlo[u]);
         const bool carry = oldl > ~dlo[u];                               // out of the low word
         if (carry || dhi != 0u) atomicAdd(&lat[1], dhi + (carry ? 1u : 0u));
-        if (err) atomicAdd(&row[8], 1u);
+        if (meta[u] & 0x100u) atomicAdd(&row[8], 1u);
         ++n_hit;
       }
-      coldf[u] = act && !hit;
+      coldf[u] = act[u] && !hit[u];
       // a duration that does not fit the queue entry (>= 2^55 ns) is handled on the spot: rare beyond words
       if (coldf[u] && dhi >= (1u << 23)) {
         ++n_cold;                    // per-lane here, folded into the warp total below
-        slow_one<kRows>(key[u], dur, bucket, kind, err, pairs, s, ep, ep_mask, &lost, &unresolved);
+        slow_one<kRows>(key[u], dur[u], meta[u] & 0x3Fu, (meta[u] >> 6) & 3u, (meta[u] & 0x100u) != 0u, pairs, s, ep, ep_mask,
+                        &lost, &unresolved);
         coldf[u] = false;
       }
     }
@@ -995,15 +1010,15 @@ __global__ void __launch_bounds__(256) hot_emit_kernel(AccTable pairs, HotState*
   }
 }
 
-template <int kWarps, int kRecWords, bool kWin = false>
+template <int kWarps, int kRecWords, bool kWin = false, int kStages = 2>
 void launch_variant(const void* recs, uint64_t n, const AccTable& pairs, Counters* ctr, const HotState* hot,
                     const EpEntry* ep, uint32_t ep_mask, const uint32_t* bloom, const uint64_t* dur_ovf, int sms,
                     cudaStream_t s, const WinClock* win = nullptr, void* defer_buf = nullptr, uint32_t defer_cap = 0) {
-  using L = Layout<kWarps, kRecWords>;
+  using L = Layout<kWarps, kRecWords, kStages>;
   // per device (a process may drive several GPUs), so not cached in a static
-  cudaFuncSetAttribute(ingest_pairs_v8_kernel<kWarps, kRecWords, kWin>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaFuncSetAttribute(ingest_pairs_v8_kernel<kWarps, kRecWords, kWin, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)L::kBytes);
-  ingest_pairs_v8_kernel<kWarps, kRecWords, kWin><<<(unsigned)sms, kWarps * 32, L::kBytes, s>>>(
+  ingest_pairs_v8_kernel<kWarps, kRecWords, kWin, kStages><<<(unsigned)sms, kWarps * 32, L::kBytes, s>>>(
       (const uint32_t*)recs, n, pairs, ctr, hot, ep, ep_mask, bloom, dur_ovf, win, (uint4*)defer_buf, defer_cap);
 }
 
@@ -1048,6 +1063,9 @@ void launch_ingest_pairs(const alz_l7_rec* recs, uint64_t n, const AccTable& pai
     case 1: launch_variant<12, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
     case 2: launch_variant<20, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
     case 3: launch_variant<24, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
+    case 4: launch_variant<16, 8, false, 1>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
+    case 5: launch_variant<20, 8, false, 1>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
+    case 6: launch_variant<24, 8, false, 1>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
     case 9: launch_variant9<32, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
     case 10: launch_variant9<24, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
     default: launch_variant<kDefaultWarps, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
