@@ -189,10 +189,12 @@ __global__ void __launch_bounds__(256) unpack_canonical_kernel(const uint64_t* _
 
 // packed edge key of an output row (inverse of unpack_edge_key)
 __device__ __forceinline__ uint64_t row_key_of(const alz_edge_out* r) {
-  const uint4 hd = *reinterpret_cast<const uint4*>(r);   // from_type, to_type, pad | pad | from | to
-  const uint32_t ft = hd.x & 0xFFu, tt = (hd.x >> 8) & 0xFFu;
-  if (ft == ALZ_NODE_POD) return ((uint64_t)tt << 61) | ((uint64_t)(hd.z & 0x1FFFFFFFu) << 32) | hd.w;
-  return (1ull << 63) | ((uint64_t)ft << 61) | ((uint64_t)(hd.w & 0x1FFFFFFFu) << 32) | hd.z;
+  // rows are 296 bytes apart: 8-byte aligned only
+  const uint2 ty = reinterpret_cast<const uint2*>(r)[0];   // from_type, to_type, pad | pad
+  const uint2 ft_ = reinterpret_cast<const uint2*>(r)[1];  // from | to
+  const uint32_t ft = ty.x & 0xFFu, tt = (ty.x >> 8) & 0xFFu;
+  if (ft == ALZ_NODE_POD) return ((uint64_t)tt << 61) | ((uint64_t)(ft_.x & 0x1FFFFFFFu) << 32) | ft_.y;
+  return (1ull << 63) | ((uint64_t)ft << 61) | ((uint64_t)(ft_.y & 0x1FFFFFFFu) << 32) | ft_.x;
 }
 __device__ __forceinline__ uint32_t lower_bound_rows(const alz_edge_out* rows, uint32_t n, uint64_t k, bool* equal) {
   uint32_t lo = 0, hi = n;

@@ -494,6 +494,10 @@ def verify_window(h, capi, abi, topo, d_ev, N, S, world, rank, dist, torch):
     edges = h.d2h(p_edges, n, abi.EDGE_OUT)
     pod_ids = np.arange(len(topo.pod_ip))
     sample_ids = pod_ids[pod_ids % 64 == 5]
+    if world > 1:
+        # this rank's events are those of the sources it owns: only their edges can be checked against them
+        own = np.array([h.L.alz_owner_rank(int(ip), world) for ip in topo.pod_ip[sample_ids]])
+        sample_ids = sample_ids[own == rank]
     sample_ips = np.sort(topo.pod_ip[sample_ids])
     rec = dev_view(torch, d_ev, N * 8)
     sad = rec.view(N, 8)[:, 0]
