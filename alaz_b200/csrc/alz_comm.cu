@@ -260,10 +260,19 @@ __global__ void __launch_bounds__(256) merge_blocks_kernel(const alz_edge_out* _
   }
 }
 
-// a successful merge consumes the window: zero the local edge rows that were sent
-__global__ void __launch_bounds__(256) zero_edge_rows_kernel(AccTable edges, const uint32_t* __restrict__ rows, uint32_t n) {
+// a successful merge consumes the window: zero the local edge rows that were sent, empty the edge dictionary, reset
+// the row allocator. Decided on the device from the merge kernel's verdict, so the host reads that verdict once, at
+// the end, instead of synchronising in the middle of the flush to decide whether to launch this.
+__global__ void __launch_bounds__(256) consume_window_kernel(const MergeInfo* __restrict__ info, AccTable edges,
+                                                             const uint32_t* __restrict__ rows, uint32_t n) {
+  if (info->peer_status != ALZ_OK || info->overflow != 0u || info->dup != 0u) return;
   const uint32_t sl = threadIdx.x & 7u;
   const uint32_t groups = (gridDim.x * blockDim.x) >> 3;
+  const size_t dict_words = ((size_t)edges.dict_mask + 1u) * (sizeof(DictEnt) / 16u);
+  uint4* dict = reinterpret_cast<uint4*>(edges.dict);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < dict_words; i += (size_t)gridDim.x * blockDim.x)
+    dict[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *edges.n_rows = 0u;
   for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; i < n; i += groups) {
     const uint32_t row = rows[i];
     uint4* cells = reinterpret_cast<uint4*>(edges.hist + (size_t)row * ALZ_NB + sl * 8u);
@@ -501,7 +510,8 @@ int alz_internal_merge_ranks(alz_handle* h, int local_rc) {
     NK(g_nccl.AllGather(c->d_send, c->d_recv, block_rows * kRowWords64, ncclUint64, c->comm, s));
     h->collective_bytes_last += (uint64_t)block_rows * R * kRowBytes;
     merge_blocks_kernel<<<grid, 256, 0, s>>>(c->d_recv, c->cap_r, (uint32_t)R, h->d_out, h->cfg.max_edges, c->d_info);
-    h->launches += 1;
+    consume_window_kernel<<<grid, 256, 0, s>>>(c->d_info, h->edges, h->d_rows[1], n_local);
+    h->launches += 2;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(c->h_info, c->d_info, sizeof(MergeInfo), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));   // the flush's one synchronisation: the caller needs the edge count
@@ -511,10 +521,7 @@ int alz_internal_merge_ranks(alz_handle* h, int local_rc) {
     if (inf.overflow == 2u) return ALZ_E_CAPACITY;                                    // merged graph larger than max_edges
     c->cap_r = block_rows_for(inf.max_count);                                         // next window's block size
     if (inf.dup) return merge_allreduce(h);                                           // not partitioned by owner: general path
-    // success: the window is consumed
-    if (n_local) { zero_edge_rows_kernel<<<grid, 256, 0, s>>>(h->edges, h->d_rows[1], n_local); h->launches += 1; }
-    CK(cudaMemsetAsync(h->edges.dict, 0xFF, ((size_t)h->edges.dict_mask + 1) * sizeof(DictEnt), s));
-    CK(cudaMemsetAsync(h->edges.n_rows, 0, 4, s));
+    // success: consume_window_kernel has consumed the window
     h->last_n_edges = inf.total;
     h->windows++;
     return ALZ_OK;

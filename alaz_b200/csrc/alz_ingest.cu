@@ -40,6 +40,8 @@ namespace alz {
 // goes in a REAL run — ncu's kernel replay flushes the caches between passes unless told otherwise.
 #ifdef ALZ_INGEST_PROF
 __device__ unsigned long long g_ingest_prof[8];
+__device__ unsigned long long g_ingest_phase[4];   // per CTA, summed: prologue, main loop until the slowest warp, drain; CTAs
+#define PROF_PHASE(i, v) do { if (threadIdx.x == 0) atomicAdd(&g_ingest_phase[i], (unsigned long long)(v)); } while (0)
 #define PROF_DECL unsigned long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pc0 = 0, pc1 = 0; (void)pc0; (void)pc1
 #define PROF_NOW() clock64()
 #define PROF_ADD(i, v) pt[i] += (unsigned long long)(v)
@@ -49,6 +51,7 @@ __device__ unsigned long long g_ingest_prof[8];
 #define PROF_NOW() 0ll
 #define PROF_ADD(i, v)
 #define PROF_FLUSH()
+#define PROF_PHASE(i, v)
 #endif
 
 namespace {
@@ -77,7 +80,8 @@ struct Layout {
   static constexpr uint32_t kSlowOff = kColdOff + (uint32_t)kWarps * kColdQ * kQBytes;
   static constexpr uint32_t kProbeOff = kSlowOff + (uint32_t)kWarps * kSlowQ * kQBytes;   // per warp: 32 x 16-B DictEnt
   static constexpr uint32_t kMisc = kProbeOff + (uint32_t)kWarps * 512u;                  // row allocator
-  static constexpr uint32_t kRowKeys = kMisc + 16u;
+  static constexpr uint32_t kScratchOff = kMisc + 16u;                                    // per warp: one word per lane
+  static constexpr uint32_t kRowKeys = kScratchOff + (uint32_t)kWarps * 128u;
   static constexpr uint32_t kPerRow = 8u + kRowWords * 4u + 1u;         // key, cells, window base
   static constexpr uint32_t kRowsRaw = (kSmemMax - kRowKeys - 64u) / kPerRow - 1u;
   static constexpr uint32_t kRows = (kRowsRaw < 4064u ? kRowsRaw : 4064u) / 32u * 32u;
@@ -237,8 +241,6 @@ using SlowQueue = Queue<kSlowQ>;
 using ColdQueue = Queue<kColdQ>;
 
 // the global path for one event whose pair row is known
-__constant__ int c_diag = 0;        // ALZ_INGEST_DIAG (timing experiments only, results are wrong): 1 = no reductions for
-                                    // cold home hits, 2 = do not wait for the probes
 __constant__ int c_keep_hint = 1;   // ALZ_INGEST_KEEP=0 turns the eviction-priority hint off (A/B runs)
 __device__ __forceinline__ uint64_t keep_policy() {
   uint64_t p;
@@ -338,14 +340,14 @@ __device__ __forceinline__ void cold_consume(ColdQueue& q, uint32_t count, const
                                              unsigned long long* t_wait, unsigned long long* t_slow) {
   const uint32_t lane = threadIdx.x & 31u;
   const long long w0 = PROF_NOW();
-  if (!(c_diag & 2)) cp_async_wait_all();
+  cp_async_wait_all();
   *t_wait += (unsigned long long)(PROF_NOW() - w0);
   const bool valid = lane < count;
   uint4 e = make_uint4(0u, 0u, 0u, 0u), ent = make_uint4(0u, 0u, kNoRow, 0u);
   if (valid) { e = *q.at(lane); ent = probe[lane]; }
   const bool filtered = valid && ent.z == kDropRow && ent.w == 1u;
   const bool home = valid && !filtered && ent.x == e.x && ent.y == e.y && ent.z < kDropRow && (e.x & e.y) != 0xFFFFFFFFu;
-  global_add_paired<false>(t, home && !(c_diag & 1), ent.z, e.w, e.z);
+  global_add_paired<false>(t, home, ent.z, e.w, e.z);
   if (filtered) *unresolved += 1u;
   slow.push(valid && !home && !filtered, ((uint64_t)e.y << 32) | e.x, e.z, e.w, lane_lt);
   __syncwarp();
@@ -447,6 +449,8 @@ ingest_pairs_v8_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
   using L = Layout<kWarps, kRecWords, kStages>;
   constexpr uint32_t kRows = L::kRows;
   extern __shared__ __align__(128) uint8_t smem_raw[];
+  const long long k_entry = PROF_NOW();
+  (void)k_entry;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t lane_lt = (1u << lane) - 1u;
   Shared s;
@@ -462,6 +466,9 @@ ingest_pairs_v8_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
   slow.bind(smem_raw + L::kSlowOff + (size_t)warp * kSlowQ * kQBytes);
   uint4* probe = reinterpret_cast<uint4*>(smem_raw + L::kProbeOff + (size_t)warp * 512u);
   const uint32_t probe_a = smem_u32(probe);
+  // where the reductions of a lane whose event is not a hit go (they add 0): the hot tier's reductions are issued
+  // by all lanes with selected operands instead of sitting in divergent regions
+  uint32_t* const idle = reinterpret_cast<uint32_t*>(smem_raw + L::kScratchOff + (size_t)warp * 128u) + lane;
   const uint8_t* ring = smem_raw + (size_t)warp * (uint32_t)kStages * L::kChunkBytes;
   const uint32_t ring_a = smem_u32(ring);
   const uint32_t bar_a = smem_u32(smem_raw + L::kBars + warp * 16u);
@@ -638,27 +645,34 @@ ingest_pairs_v8_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
     for (int u = 0; u < kU; ++u) hit[u] = cand[u] && s.rowkey[rowi[u]] == key[u];   // row kRows holds no key
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
+      const bool ht = hit[u];
       uint32_t* row = s.rows + rowi[u] * kRowWords;
       const uint32_t d = cell[u];
       const uint32_t dhi = (uint32_t)(dur[u] >> 32);
-      if (hit[u]) {
-        const uint32_t sh = (d & 1u) * 16u;
-        const uint32_t old = atomicAdd(&row[d >> 1], 1u << sh);
-        if (((old >> sh) & 0xFFFFu) == kCellSpill) {
+      const uint32_t sh = (d & 1u) * 16u;
+      uint32_t* cellp = ht ? row + (d >> 1) : idle;
+      const uint32_t old = atomicAdd(cellp, ht ? (1u << sh) : 0u);
+      const bool spill = ht && ((old >> sh) & 0xFFFFu) == kCellSpill;
+      if (__any_sync(0xFFFFFFFFu, spill)) {
+        if (spill) {
           // this lane took the cell to 0x8000: move 0x8000 counts into the global table (rare: a pair with more
           // than 32767 events in one bucket within one launch of one CTA)
           const uint32_t grow = find_or_insert_pair(pairs, key[u], kPairFwd, ep, ep_mask);
           if (grow < kDropRow) red_add_u32(pair_cell(pairs, grow, meta[u] & 0x3Fu), 0x8000u);
           else if (grow == kDropRow) unresolved += 0x8000u; else lost += 0x8000u;
-          atomicSub(&row[d >> 1], 0x8000u << sh);
+          atomicSub(cellp, 0x8000u << sh);
         }
-        uint32_t* lat = row + 9u + 2u * (lane & 1u);
-        const uint32_t oldl = atomicAdd(&lat[0], dlo[u]);
-        const bool carry = oldl > ~dlo[u];                               // out of the low word
-        if (carry || dhi != 0u) atomicAdd(&lat[1], dhi + (carry ? 1u : 0u));
-        if (meta[u] & 0x100u) atomicAdd(&row[8], 1u);
-        ++n_hit;
+        __syncwarp();
       }
+      uint32_t* latp = ht ? row + 9u + 2u * (lane & 1u) : idle;
+      const uint32_t oldl = atomicAdd(latp, ht ? dlo[u] : 0u);
+      const bool carry = ht && oldl > ~dlo[u];                           // out of the low word
+      const bool more = ht && (carry || dhi != 0u);
+      if (__any_sync(0xFFFFFFFFu, more)) {
+        if (more) atomicAdd(latp + 1, dhi + (carry ? 1u : 0u));
+      }
+      if (ht && (meta[u] & 0x100u)) atomicAdd(&row[8], 1u);
+      n_hit += ht ? 1u : 0u;
       coldf[u] = act[u] && !hit[u];
       // a duration that does not fit the queue entry (>= 2^55 ns) is handled on the spot: rare beyond words
       if (coldf[u] && dhi >= (1u << 23)) {
@@ -700,8 +714,14 @@ ingest_pairs_v8_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
   PROF_ADD(4, t_slow);
   PROF_FLUSH();
   __syncthreads();
+  const long long k_loop_end = PROF_NOW();
+  (void)k_loop_end;
 
   drain_rows_and_count<kWarps, kRows, kWin>(s, pairs, ctr, ep, ep_mask, lost, unresolved, n_hit, n_live, n_cold, n_late);
+  PROF_PHASE(0, p_begin - k_entry);
+  PROF_PHASE(1, k_loop_end - p_begin);
+  PROF_PHASE(2, PROF_NOW() - k_loop_end);
+  PROF_PHASE(3, 1);
 }
 
 // ---- v9: the same tiers with twice the warps ------------------------------------------------------------------
@@ -1052,13 +1072,6 @@ void launch_ingest_pairs(const alz_l7_rec* recs, uint64_t n, const AccTable& pai
     return k;
   }();
   (void)keep;
-  static const int diag = [] {
-    const char* v = getenv("ALZ_INGEST_DIAG");
-    const int k = v ? atoi(v) : 0;
-    if (k) cudaMemcpyToSymbol(c_diag, &k, sizeof(k));
-    return k;
-  }();
-  (void)diag;
   switch (shape) {
     case 1: launch_variant<12, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
     case 2: launch_variant<20, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
@@ -1099,15 +1112,17 @@ void launch_hot_select(const AccTable& pairs, HotState* hot, int sms, cudaStream
 }  // namespace alz
 
 // profiling build only: cycles per section of the ingest main loop since the last call (see g_ingest_prof)
-extern "C" int alz_debug_ingest_prof(unsigned long long* out8) {
+extern "C" int alz_debug_ingest_prof(unsigned long long* out12) {   // 8 section counters + 4 phase counters
 #ifdef ALZ_INGEST_PROF
   unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (cudaDeviceSynchronize() != cudaSuccess) return ALZ_E_CUDA;
-  if (cudaMemcpyFromSymbol(out8, alz::g_ingest_prof, sizeof(z)) != cudaSuccess) return ALZ_E_CUDA;
+  if (cudaMemcpyFromSymbol(out12, alz::g_ingest_prof, sizeof(z)) != cudaSuccess) return ALZ_E_CUDA;
   if (cudaMemcpyToSymbol(alz::g_ingest_prof, z, sizeof(z)) != cudaSuccess) return ALZ_E_CUDA;
+  if (cudaMemcpyFromSymbol(out12 + 8, alz::g_ingest_phase, 4 * sizeof(unsigned long long)) != cudaSuccess) return ALZ_E_CUDA;
+  if (cudaMemcpyToSymbol(alz::g_ingest_phase, z, 4 * sizeof(unsigned long long)) != cudaSuccess) return ALZ_E_CUDA;
   return ALZ_OK;
 #else
-  (void)out8;
+  (void)out12;
   return ALZ_E_UNSUPPORTED;
 #endif
 }

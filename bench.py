@@ -428,7 +428,11 @@ def main():
         }
         if world > 1:
             cs = h.stats()
-            line["multi_gpu"] = {"collective_bytes_per_step": cs.get("collective_bytes_last", None)}
+            line["multi_gpu"] = {"collective_bytes_per_step": cs.get("collective_bytes_last", None),
+                                 "flush_local_ms_last": cs.get("flush_local_us_last", 0) / 1000.0,
+                                 "merge_ms_last": cs.get("merge_us_last", 0) / 1000.0,
+                                 "what": "rank 0, last window: local part of the flush (fold, sort) and cross-rank part "
+                                         "(gather rows, one ncclAllGather, merge kernel), device time between events"}
         if gnn_ms is not None:
             line["gnn_update"] = gnn_ms
         if not args.no_cpu:

@@ -34,7 +34,7 @@ for k in range(a.windows):
     topo.fill_device(h, k * a.events, a.events, d)
     wins.append(d)
 h.sync()
-buf = (C.c_ulonglong * 8)()
+buf = (C.c_ulonglong * 12)()
 for k in range(3):
     h.submit_device(wins[k % a.windows], a.events); h.flush_device()
 h.sync()
@@ -60,4 +60,11 @@ out = {"ingest_ms_with_instrumentation": ms / a.steps, "max_pairs": a.max_pairs,
        "cycles_per_iteration": v[0] / max(1, v[6]),
        "shares": {names[i]: round(v[i] / tot, 4) for i in (1, 2, 3, 4, 5)},
        "cold_batches_per_iteration": v[7] / max(1, v[6])}
+ctas = max(1, v[11])
+warps_per_cta = 16
+out["phases_cycles_per_cta"] = {"prologue (smem init, hot list preload)": v[8] / ctas,
+                                "main loop until the slowest warp is done": v[9] / ctas,
+                                "mean warp's main loop (16 warps assumed)": v[0] / ctas / warps_per_cta,
+                                "drain of the private rows": v[10] / ctas}
+out["phases_ms_at_1965MHz"] = {k: round(c / 1.965e6, 4) for k, c in out["phases_cycles_per_cta"].items()}
 print(json.dumps(out))
