@@ -6,7 +6,7 @@
 // elected lane, L2 evict-first). Lanes copy their records from the ring into registers, the stage
 // goes back to the TMA as soon as those loads have returned, and the next two chunks are in flight
 // while the warp works: no per-lane address arithmetic, no scoreboard stall on the first use of a
-// streamed record (profiles/r2_ingest_sections.txt: 4 % of a warp's time waits on the ring; with
+// streamed record (profiles/r2_ingest_phases.json: 3 % of a warp's time waits on the ring; with
 // plain loads, even prefetched into L2 by the TMA engine, it was 28 %), no cross-warp barrier
 // anywhere in the main loop.
 //
@@ -22,9 +22,12 @@
 //         or host-keyed row) is NOT handled inline: the lane pushes the event onto its warp's
 //         queue (ballot-compacted, no atomics) and the warp runs the cold path for 32 queued
 //         events at a time with all lanes busy — global dictionary probe of the home slot, then
-//         reductions (REDG) into the pair's row in L2. The probes are cp.async copies into shared
-//         memory and are consumed when the next batch is requested, one to three iterations
-//         later, so their L2/DRAM round trip is off the warp's critical path. A source address
+//         the reduction into the pair's row in L2: ONE red.u64 per event, a lane pair adding the
+//         histogram cell and the duration into the 32-byte sector of the row that holds both
+//         (global_add_paired; the SM pays per sector an instruction touches, not per lane). The
+//         probes are cp.async copies into shared memory and are consumed when the next batch is
+//         requested, one to three iterations later, so their L2/DRAM round trip is off the warp's
+//         critical path. A source address
 //         that cannot be a pod (a 128-Kbit filter of the pod addresses, built by the host at table
 //         commit) is dropped right there, as setFromToV2 would (aggregator/data.go:829-832).
 //   slow  a cold event whose home slot does not hold its pair (new pair, collision) is queued once
