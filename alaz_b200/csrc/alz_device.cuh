@@ -320,8 +320,16 @@ struct HotState {
   uint32_t n_a, n_b;           // tier A occupies keys[0, n_a), tier B keys[kHotA, kHotA + n_b)
   uint64_t keys[kHotMax];
   uint8_t base[kHotMax];       // the pair's histogram window (first bucket / 4), see AccTable::row_base
+  // tier S: the (at most) kHotS hottest pairs of all. The per-CTA table gives each of them kHotRep rows and a lane
+  // uses row (lane % kHotRep) of the group: when one pair is most of a GPU's traffic — the rank that owns the
+  // hottest pair of a sharded stream sees it in every second event — its reductions would otherwise pile up on
+  // one shared-memory word and serialise (8 GPUs, config 2: that rank's ingest 2.2 ms against 1.13 ms elsewhere)
+  uint32_t thr_s, n_s;
+  uint64_t skeys[8];
+  uint8_t sbase[8];
 };
 constexpr int kHotA = 64;
+constexpr int kHotS = 8, kHotRep = 8;
 // monotone bin of a count >= 1: 4 bins per octave
 __device__ __forceinline__ uint32_t count_bin(uint32_t c) {
   const uint32_t o = 31u - (uint32_t)__clz((int)c);

@@ -429,6 +429,47 @@ __device__ __forceinline__ void drain_rows_and_count(const Shared& s, const AccT
   }
 }
 
+// Start of a launch, all threads: build the per-CTA table from the hot list of the previous fold. Tier S pairs get
+// kHotRep rows each in rows [0, kHotS * kHotRep) (the index entry names the first, a lane adds lane % kHotRep), then
+// tier A, then tier B while rows are left below `limit`. Returns the number of replicated rows (0 or kHotS * kHotRep).
+template <int kThreads>
+__device__ __forceinline__ uint32_t preload_hot(const Shared& s, const HotState* __restrict__ hot, uint32_t limit) {
+  if (hot == nullptr) return 0u;
+  const uint32_t ns = min(hot->n_s, (uint32_t)kHotS);
+  const uint32_t rep_rows = ns ? (uint32_t)(kHotS * kHotRep) : 0u;
+  if (threadIdx.x < ns * kHotRep) {
+    const uint32_t i = threadIdx.x / kHotRep;
+    s.rowkey[threadIdx.x] = hot->skeys[i];
+    s.rowbase[threadIdx.x] = (uint8_t)min((uint32_t)hot->sbase[i], 12u);
+  }
+  if (threadIdx.x < ns) {
+    const uint64_t k = hot->skeys[threadIdx.x];
+    const uint32_t h = table_hash(k);
+    uint32_t idx = tab_idx1(h);
+    bool got = atomicCAS(&s.tab[idx], 0u, kBusy) == 0u;
+    if (!got) { idx = tab_idx2(h); got = atomicCAS(&s.tab[idx], 0u, kBusy) == 0u; }
+    if (got && k != kEmptyKey) s.tab[idx] = tab_entry(h, min((uint32_t)hot->sbase[threadIdx.x], 12u), threadIdx.x * kHotRep);
+  }
+  if (threadIdx.x == 0) *s.n_rows = rep_rows;
+  __syncthreads();
+  const uint32_t na = min(hot->n_a, (uint32_t)kHotA);
+  const uint32_t room = limit - min(limit, rep_rows + na);
+  const uint32_t nb = min(min(hot->n_b, (uint32_t)(kHotMax - kHotA)), room);
+  for (uint32_t i = threadIdx.x; i < na; i += kThreads) {   // tier A before B: the hotter pairs cannot lose their slots
+    const uint64_t k = hot->keys[i];
+    if (k != kEmptyKey) smem_admit(s, k, table_hash(k), min((uint32_t)hot->base[i], 12u), limit, false);
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < nb; i += kThreads) {
+    const uint64_t k = hot->keys[kHotA + i];
+    if (k != kEmptyKey) smem_admit(s, k, table_hash(k), min((uint32_t)hot->base[kHotA + i], 12u), limit, false);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && *s.n_rows > limit) *s.n_rows = limit;   // failed claims past the limit
+  __syncthreads();
+  return rep_rows;
+}
+
 // time-cut windows (docs/SPEC.md §8): the open window in the records' own (kernel) clock
 struct WinClock {
   uint64_t lo;        // first kernel-time ns of the open window
@@ -519,21 +560,7 @@ ingest_pairs_v8_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
   for (uint32_t i = threadIdx.x; i < (kRows + 1u) * kRowWords; i += kWarps * 32) s.rows[i] = 0u;
   if (threadIdx.x == 0) *s.n_rows = 0u;
   __syncthreads();
-  if (hot != nullptr) {   // tier A first so that the hottest pairs cannot lose their slots to cooler ones
-    const uint32_t na = min(hot->n_a, (uint32_t)kHotA);
-    const uint32_t nb = min(min(hot->n_b, (uint32_t)(kHotMax - kHotA)), L::kPreload - min(na, L::kPreload));
-    for (uint32_t i = threadIdx.x; i < na; i += kWarps * 32) {
-      const uint64_t k = hot->keys[i];
-      if (k != kEmptyKey) smem_admit(s, k, table_hash(k), min((uint32_t)hot->base[i], 12u), L::kPreload, false);
-    }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < nb; i += kWarps * 32) {
-      const uint64_t k = hot->keys[kHotA + i];
-      if (k != kEmptyKey) smem_admit(s, k, table_hash(k), min((uint32_t)hot->base[kHotA + i], 12u), L::kPreload, false);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && *s.n_rows > L::kPreload) *s.n_rows = L::kPreload;   // failed claims past the limit
-  }
+  const uint32_t rep_rows = preload_hot<kWarps * 32>(s, hot, L::kPreload);
   __syncthreads();
 
   const uint32_t zero = (uint32_t)(n >> 63);   // n < 2^37
@@ -640,6 +667,7 @@ ingest_pairs_v8_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
       const uint32_t x1 = t2.x ^ fp, x2 = t2.y ^ fp;
       const uint32_t x = x1 < 0x10000u ? x1 : x2;                    // upper 16 bits 0: the fingerprint matched
       rowi[u] = min(x & kRowMask, kRows);
+      rowi[u] += rowi[u] < rep_rows ? (lane & (uint32_t)(kHotRep - 1)) : 0u;   // tier S: this lane's row of the group
       cell[u] = bucket - ((x >> 12) & 15u) * 4u;                     // cell of this latency in the row's window
       cand[u] = act[u] && kind == kPairFwd && x < 0x10000u && (x & kRowMask) < kRows && cell[u] < 16u;
     }
@@ -839,21 +867,7 @@ ingest_pairs_v9_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
   for (uint32_t i = threadIdx.x; i < (kRows + 1u) * kRowWords; i += kWarps * 32) s.rows[i] = 0u;
   if (threadIdx.x == 0) *s.n_rows = 0u;
   __syncthreads();
-  if (hot != nullptr) {
-    const uint32_t na = min(hot->n_a, (uint32_t)kHotA);
-    const uint32_t nb = min(min(hot->n_b, (uint32_t)(kHotMax - kHotA)), L::kPreload - min(na, L::kPreload));
-    for (uint32_t i = threadIdx.x; i < na; i += kWarps * 32) {
-      const uint64_t k = hot->keys[i];
-      if (k != kEmptyKey) smem_admit(s, k, table_hash(k), min((uint32_t)hot->base[i], 12u), L::kPreload, false);
-    }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < nb; i += kWarps * 32) {
-      const uint64_t k = hot->keys[kHotA + i];
-      if (k != kEmptyKey) smem_admit(s, k, table_hash(k), min((uint32_t)hot->base[kHotA + i], 12u), L::kPreload, false);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && *s.n_rows > L::kPreload) *s.n_rows = L::kPreload;
-  }
+  const uint32_t rep_rows = preload_hot<kWarps * 32>(s, hot, L::kPreload);
   __syncthreads();
 
   const uint32_t zero = (uint32_t)(n >> 63);
@@ -932,7 +946,8 @@ ingest_pairs_v9_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
     const uint2 t2 = *reinterpret_cast<const uint2*>(&s.tab[tab_idx1(h)]);
     const uint32_t x1 = t2.x ^ fp, x2 = t2.y ^ fp;
     const uint32_t x = x1 < 0x10000u ? x1 : x2;
-    const uint32_t r = min(x & kRowMask, kRows);
+    uint32_t r = min(x & kRowMask, kRows);
+    r += r < rep_rows ? (lane & (uint32_t)(kHotRep - 1)) : 0u;   // tier S: this lane's row of the group
     const uint32_t d = bucket - ((x >> 12) & 15u) * 4u;
     const bool hit = act && kind == kPairFwd && x < 0x10000u && (x & kRowMask) < kRows && d < 16u && s.rowkey[r] == key;
     uint32_t* row = s.rows + r * kRowWords;
@@ -1004,26 +1019,30 @@ __global__ void win_advance_kernel(WinClock* win) {
 // the forward rows; thresholds = the lowest bins that keep tier A <= kHotA and A+B <= target. Every block derives
 // the same two thresholds from the bins itself (128 adds) instead of a separate launch.
 __global__ void __launch_bounds__(256) hot_emit_kernel(AccTable pairs, HotState* hot, uint32_t target_total) {
-  __shared__ uint32_t s_thr[2];
+  __shared__ uint32_t s_thr[3];
   if (threadIdx.x == 0) {
-    uint32_t cum = 0, thr_a = 128, thr_b = 128;
+    uint32_t cum = 0, thr_s = 128, thr_a = 128, thr_b = 128;
     for (int b = 127; b >= 0; --b) {
       cum += hot->bins[b];
+      if (cum <= (uint32_t)kHotS) thr_s = (uint32_t)b;
       if (cum <= (uint32_t)kHotA) thr_a = (uint32_t)b;
       if (cum <= target_total) thr_b = (uint32_t)b;
     }
-    s_thr[0] = thr_a; s_thr[1] = thr_b;
-    if (blockIdx.x == 0) { hot->thr_a = thr_a; hot->thr_b = thr_b; }
+    s_thr[0] = thr_a; s_thr[1] = thr_b; s_thr[2] = thr_s;
+    if (blockIdx.x == 0) { hot->thr_a = thr_a; hot->thr_b = thr_b; hot->thr_s = thr_s; }
   }
   __syncthreads();
-  const uint32_t thr_a = s_thr[0], thr_b = s_thr[1];
+  const uint32_t thr_a = s_thr[0], thr_b = s_thr[1], thr_s = s_thr[2];
   const uint32_t n_rows = min(*pairs.n_rows, pairs.max_rows);
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t row = blockIdx.x * blockDim.x + threadIdx.x; row < n_rows; row += stride) {
     const uint32_t c = pairs.row_cnt[row];
     if (c == 0u || pairs.row_kind[row] != kPairFwd) continue;   // only forward pairs enter the per-CTA table
     const uint32_t b = count_bin(c);
-    if (b >= thr_a) {
+    if (b >= thr_s) {
+      const uint32_t p = atomicAdd(&hot->n_s, 1u);
+      if (p < (uint32_t)kHotS) { hot->skeys[p] = pairs.row_key[row]; hot->sbase[p] = pairs.row_base[row]; }
+    } else if (b >= thr_a) {
       const uint32_t p = atomicAdd(&hot->n_a, 1u);
       if (p < (uint32_t)kHotA) { hot->keys[p] = pairs.row_key[row]; hot->base[p] = pairs.row_base[row]; }
     } else if (b >= thr_b) {

@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256) fold_resolve_kernel(AccTable pairs, const
   // the list; both run after this kernel, the ingest launches that read the list ran before it)
   if (blockIdx.x == 0 && hot != nullptr) {
     if (threadIdx.x < 128) hot->bins[threadIdx.x] = 0u;
-    if (threadIdx.x == 0) { hot->n_a = 0u; hot->n_b = 0u; }
+    if (threadIdx.x == 0) { hot->n_a = 0u; hot->n_b = 0u; hot->n_s = 0u; }
   }
   const uint32_t n_rows = min(*pairs.n_rows, pairs.max_rows);
   const uint32_t stride = gridDim.x * blockDim.x;

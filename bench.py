@@ -277,7 +277,9 @@ def main():
     flags = (abi.CFG_EAGER_JOIN if args.eager else 0) | (abi.CFG_NO_SMEM_CACHE if args.no_smem_cache else 0)
     # capacities: distinct pairs per rank per window (topology pairs it owns + unresolved sources), merged edges
     max_pairs = max(1 << 20, int(1.6 * topo.n_edges / (1 if world == 1 else world * 0.7)) + (1 << 19))
-    max_edges = max(1 << 20, int(1.25 * topo.n_edges))
+    # live edges: a topology pair shows up as a forward edge and, for the protocols that reverse (AMQP DELIVER, REDIS
+    # PUSHED_EVENT), as a reversed one too: 1.9 edges per pair at config 2 (188,749 edges over 100k pairs)
+    max_edges = max(1 << 20, int(2.3 * topo.n_edges))
 
     def new_handle():
         hh = capi.Handle(device=local_rank, max_endpoints=4 * S, max_pairs=max_pairs, max_edges=max_edges,
