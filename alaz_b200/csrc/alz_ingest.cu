@@ -72,10 +72,10 @@ constexpr uint32_t kSmemMax = 232448;      // 227 KB per CTA on sm_100
 constexpr int kU = 2;                      // events per lane per iteration
 constexpr uint32_t kChunk = 32u * kU;      // events per warp per iteration = one TMA copy
 
-template <int kWarps, int kRecWords, int kStages = 2>
+template <int kWarps, int kRecWords>
 struct Layout {
   static constexpr uint32_t kChunkBytes = kChunk * kRecWords * 4u;
-  static constexpr uint32_t kRing = (uint32_t)kWarps * (uint32_t)kStages * kChunkBytes;
+  static constexpr uint32_t kRing = (uint32_t)kWarps * 2u * kChunkBytes;
   static constexpr uint32_t kBars = kRing;                              // kWarps * 2 mbarriers
   static constexpr uint32_t kTabOff = kBars + (uint32_t)kWarps * 16u;
   static constexpr uint32_t kBloomOff = kTabOff + kTab * 4u;            // pod-address filter, ALZ_BLOOM_WORDS words
@@ -244,11 +244,9 @@ using SlowQueue = Queue<kSlowQ>;
 using ColdQueue = Queue<kColdQ>;
 
 // the global path for one event whose pair row is known
-__constant__ int c_keep_hint = 1;   // ALZ_INGEST_KEEP=0 turns the eviction-priority hint off (A/B runs)
 __device__ __forceinline__ uint64_t keep_policy() {
   uint64_t p;
-  if (c_keep_hint) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
 __device__ __forceinline__ void global_add(const AccTable& t, uint32_t row, uint32_t bucket, uint64_t dur, bool err) {
@@ -261,9 +259,7 @@ __device__ __forceinline__ void global_add(const AccTable& t, uint32_t row, uint
 // The same for up to 32 events held one per lane (`on`, row, meta = bucket | ... | err << 8 | dur_hi << 9, dur_lo), as
 // ONE red.u64 instruction per 16 events: lane pair (2j, 2j+1) takes one event, the even lane adds to the cell pair,
 // the odd lane the duration, both in the event's sector, which the LSU serves in one pass (alz_device.cuh, AccTable).
-// kSparse: the events sit in arbitrary lanes and pair j takes lane 2j's in round 0, lane 2j+1's in round 1; otherwise
-// round r takes lanes 16r..16r+15 in order. All lanes must call this.
-template <bool kSparse>
+// Round r takes the events of lanes 16r..16r+15. All lanes must call this.
 __device__ __forceinline__ void global_add_paired(const AccTable& t, bool on, uint32_t row, uint32_t meta, uint32_t dlo) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t have = __ballot_sync(0xFFFFFFFFu, on);
@@ -272,8 +268,8 @@ __device__ __forceinline__ void global_add_paired(const AccTable& t, bool on, ui
   const uint32_t odd = lane & 1u;
 #pragma unroll
   for (uint32_t r = 0; r < 2u; ++r) {
-    if ((have & (kSparse ? (r ? 0xAAAAAAAAu : 0x55555555u) : (r ? 0xFFFF0000u : 0x0000FFFFu))) == 0u) continue;   // warp-uniform
-    const uint32_t src = kSparse ? ((lane & ~1u) | r) : (r * 16u + (lane >> 1));
+    if ((have & (r ? 0xFFFF0000u : 0x0000FFFFu)) == 0u) continue;   // warp-uniform
+    const uint32_t src = r * 16u + (lane >> 1);
     const uint32_t row_s = __shfl_sync(0xFFFFFFFFu, row, src);
     const uint32_t meta_s = __shfl_sync(0xFFFFFFFFu, meta, src);
     const uint32_t dlo_s = __shfl_sync(0xFFFFFFFFu, dlo, src);
@@ -350,7 +346,7 @@ __device__ __forceinline__ void cold_consume(ColdQueue& q, uint32_t count, const
   if (valid) { e = *q.at(lane); ent = probe[lane]; }
   const bool filtered = valid && ent.z == kDropRow && ent.w == 1u;
   const bool home = valid && !filtered && ent.x == e.x && ent.y == e.y && ent.z < kDropRow && (e.x & e.y) != 0xFFFFFFFFu;
-  global_add_paired<false>(t, home, ent.z, e.w, e.z);
+  global_add_paired(t, home, ent.z, e.w, e.z);
   if (filtered) *unresolved += 1u;
   slow.push(valid && !home && !filtered, ((uint64_t)e.y << 32) | e.x, e.z, e.w, lane_lt);
   __syncwarp();
@@ -481,16 +477,13 @@ struct WinClock {
 // kWin (32-B records only): an event whose write_time lies beyond the open window is not reduced but appended
 // to `defer_buf` (it is submitted again when its window opens); one that lies before it is late: reduced into
 // the open window and counted.
-// kStages = 2: the chunk after the one being worked on has landed or is in flight, the one after that is requested
-// when this one's records are in registers. kStages = 1: a single 2-KB stage per warp — the next chunk is requested
-// as soon as this one's records are in registers and has one iteration to arrive; the 2 KB per warp saved go to rows.
-template <int kWarps, int kRecWords, bool kWin, int kStages>
+template <int kWarps, int kRecWords, bool kWin>
 __global__ void __launch_bounds__(kWarps * 32, 1)
 ingest_pairs_v8_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable pairs, Counters* ctr,
                        const HotState* __restrict__ hot, const EpEntry* __restrict__ ep, uint32_t ep_mask,
                        const uint32_t* __restrict__ bloom_g, const uint64_t* __restrict__ dur_ovf,
                        const WinClock* __restrict__ win, uint4* __restrict__ defer_buf, uint32_t defer_cap) {
-  using L = Layout<kWarps, kRecWords, kStages>;
+  using L = Layout<kWarps, kRecWords>;
   constexpr uint32_t kRows = L::kRows;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const long long k_entry = PROF_NOW();
@@ -513,7 +506,7 @@ ingest_pairs_v8_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
   // where the reductions of a lane whose event is not a hit go (they add 0): the hot tier's reductions are issued
   // by all lanes with selected operands instead of sitting in divergent regions
   uint32_t* const idle = reinterpret_cast<uint32_t*>(smem_raw + L::kScratchOff + (size_t)warp * 128u) + lane;
-  const uint8_t* ring = smem_raw + (size_t)warp * (uint32_t)kStages * L::kChunkBytes;
+  const uint8_t* ring = smem_raw + (size_t)warp * 2u * L::kChunkBytes;
   const uint32_t ring_a = smem_u32(ring);
   const uint32_t bar_a = smem_u32(smem_raw + L::kBars + warp * 16u);
 
@@ -545,14 +538,11 @@ ingest_pairs_v8_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     issue(0u, 0u);
-    if (kStages == 2) {
-      c_next += c_stride; src_next += src_step;
-      issue(1u, 0u);
-    }
+    c_next += c_stride; src_next += src_step;
+    issue(1u, 0u);
   }
-  // every lane tracks the producer state, so any lane can be elected
-  c_next += (uint32_t)kStages * c_stride - ((kStages == 2 && lane == 0) ? c_stride : 0u);
-  src_next += (uint64_t)kStages * src_step - ((kStages == 2 && lane == 0) ? src_step : 0u);
+  c_next += 2u * c_stride - (lane == 0 ? c_stride : 0u);   // every lane tracks the producer state, so any lane can be elected
+  src_next += 2u * src_step - (lane == 0 ? src_step : 0u);
 
   for (uint32_t i = threadIdx.x; i < kTab; i += kWarps * 32) s.tab[i] = 0u;
   for (uint32_t i = threadIdx.x; i < ALZ_BLOOM_WORDS; i += kWarps * 32) s.bloom[i] = bloom_g ? bloom_g[i] : 0xFFFFFFFFu;
@@ -573,9 +563,9 @@ ingest_pairs_v8_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
   const long long p_begin = PROF_NOW();
   uint32_t it = 0;
   for (uint32_t c = c_first; c < n_chunks; c += c_stride, ++it) {
-    const uint32_t stage = kStages == 2 ? (it & 1u) : 0u;
+    const uint32_t stage = it & 1u;
     pc0 = PROF_NOW();
-    mbar_wait(bar_a + stage * 8u, kStages == 2 ? ((it >> 1) & 1u) : (it & 1u));
+    mbar_wait(bar_a + stage * 8u, (it >> 1) & 1u);
     pc1 = PROF_NOW();
     PROF_ADD(1, pc1 - pc0);
     PROF_ADD(6, 1);
@@ -755,252 +745,6 @@ ingest_pairs_v8_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
   PROF_PHASE(3, 1);
 }
 
-// ---- v9: the same tiers with twice the warps ------------------------------------------------------------------
-// One record per lane per iteration and no cold queue: a cold lane requests its dictionary home slot at once
-// (cp.async into the warp's probe buffer, slot = iteration parity), keeps the event in registers, and finishes
-// it two iterations later, when the probe has had two iterations of every other warp's work to land. Cold work
-// runs at the lane occupancy of the cold events (no compaction), but nothing is pushed, popped or batched, and
-// per-warp shared memory falls from 7.5 KB to 4 KB, which pays for 32 warps per SM instead of 16.
-constexpr uint32_t kDepth9 = 2;            // iterations between a probe's request and its use
-
-template <int kWarps, int kRecWords>
-struct Layout9 {
-  static constexpr uint32_t kChunkBytes = 32u * kRecWords * 4u;
-  static constexpr uint32_t kRing = (uint32_t)kWarps * 2u * kChunkBytes;
-  static constexpr uint32_t kBars = kRing;
-  static constexpr uint32_t kTabOff = kBars + (uint32_t)kWarps * 16u;
-  static constexpr uint32_t kBloomOff = kTabOff + kTab * 4u;
-  static constexpr uint32_t kSlowOff = kBloomOff + ALZ_BLOOM_WORDS * 4u;
-  static constexpr uint32_t kProbeOff = kSlowOff + (uint32_t)kWarps * kSlowQ * kQBytes;
-  static constexpr uint32_t kMisc = kProbeOff + (uint32_t)kWarps * kDepth9 * 512u;
-  static constexpr uint32_t kRowKeys = kMisc + 16u;
-  static constexpr uint32_t kPerRow = 8u + kRowWords * 4u + 1u;
-  static constexpr uint32_t kRowsRaw = (kSmemMax - kRowKeys - 64u) / kPerRow - 1u;
-  static constexpr uint32_t kRows = (kRowsRaw < 4064u ? kRowsRaw : 4064u) / 32u * 32u;
-  static constexpr uint32_t kRowsOff = kRowKeys + (kRows + 1u) * 8u;
-  static constexpr uint32_t kBaseOff = kRowsOff + (kRows + 1u) * kRowWords * 4u;
-  static constexpr uint32_t kBytes = kBaseOff + ((kRows + 1u + 15u) / 16u) * 16u;
-  static constexpr uint32_t kPreload = kRows - kRows / 8u;
-  static_assert(kBytes <= kSmemMax, "shared memory layout too large");
-  static_assert(kRows < kBusy, "row field is 12 bits");
-  static_assert(kRows * 3u <= kTab * 2u, "index too small for the rows");
-};
-
-__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-
-// second half of a cold event: its probe has landed in `slot[lane]`
-template <uint32_t kRows>
-__device__ __forceinline__ void cold_finish(bool valid, uint32_t klo, uint32_t khi, uint32_t dlo, uint32_t meta,
-                                            const uint4* slot, SlowQueue& slow, const AccTable& t, const Shared& s,
-                                            const EpEntry* __restrict__ ep, uint32_t ep_mask, uint32_t lane_lt,
-                                            uint32_t* lost, uint32_t* unresolved) {
-  const uint32_t lane = threadIdx.x & 31u;
-  uint4 ent = make_uint4(0u, 0u, kNoRow, 0u);
-  if (valid) ent = slot[lane];
-  const bool filtered = valid && ent.z == kDropRow && ent.w == 1u;
-  const bool home = valid && !filtered && ent.x == klo && ent.y == khi && ent.z < kDropRow && (klo & khi) != 0xFFFFFFFFu;
-  global_add_paired<true>(t, home, ent.z, meta, dlo);
-  if (filtered) *unresolved += 1u;
-  slow.push(valid && !home && !filtered, ((uint64_t)khi << 32) | klo, dlo, meta, lane_lt);
-  __syncwarp();
-  if (slow.count >= 32u) slow_batch<kRows>(slow, 32u, t, s, ep, ep_mask, lost, unresolved);
-}
-
-template <int kWarps, int kRecWords, bool kWin>
-__global__ void __launch_bounds__(kWarps * 32, 1)
-ingest_pairs_v9_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable pairs, Counters* ctr,
-                       const HotState* __restrict__ hot, const EpEntry* __restrict__ ep, uint32_t ep_mask,
-                       const uint32_t* __restrict__ bloom_g, const uint64_t* __restrict__ dur_ovf,
-                       const WinClock* __restrict__ win, uint4* __restrict__ defer_buf, uint32_t defer_cap) {
-  using L = Layout9<kWarps, kRecWords>;
-  constexpr uint32_t kRows = L::kRows;
-  constexpr uint32_t kChunk9 = 32u;
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t lane_lt = (1u << lane) - 1u;
-  Shared s;
-  s.tab = reinterpret_cast<uint32_t*>(smem_raw + L::kTabOff);
-  s.bloom = reinterpret_cast<uint32_t*>(smem_raw + L::kBloomOff);
-  s.n_rows = reinterpret_cast<uint32_t*>(smem_raw + L::kMisc);
-  s.rowkey = reinterpret_cast<uint64_t*>(smem_raw + L::kRowKeys);
-  s.rows = reinterpret_cast<uint32_t*>(smem_raw + L::kRowsOff);
-  s.rowbase = smem_raw + L::kBaseOff;
-  SlowQueue slow;
-  slow.bind(smem_raw + L::kSlowOff + (size_t)warp * kSlowQ * kQBytes);
-  uint4* probe = reinterpret_cast<uint4*>(smem_raw + L::kProbeOff + (size_t)warp * kDepth9 * 512u);
-  const uint32_t probe_a = smem_u32(probe);
-  const uint8_t* ring = smem_raw + (size_t)warp * 2u * L::kChunkBytes;
-  const uint32_t ring_a = smem_u32(ring);
-  const uint32_t bar_a = smem_u32(smem_raw + L::kBars + warp * 16u);
-
-  const uint32_t n_chunks = (uint32_t)((n + kChunk9 - 1u) / kChunk9);          // n < 2^37 per launch
-  const uint32_t c_stride = gridDim.x * kWarps;
-  const uint32_t c_first = blockIdx.x * kWarps + warp;
-  const uint32_t tail = (uint32_t)(n - (uint64_t)(n_chunks - 1u) * kChunk9);
-  uint64_t policy;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-  uint32_t c_next = c_first;
-  const uint32_t* src_next = recs + (uint64_t)c_first * (kChunk9 * kRecWords);
-  const uint64_t src_step = (uint64_t)c_stride * (kChunk9 * kRecWords);
-  auto issue = [&](uint32_t stage, uint32_t dep) {
-    if (c_next < n_chunks) {
-      const uint32_t bytes = (c_next == n_chunks - 1u ? tail : kChunk9) * (uint32_t)kRecWords * 4u + dep;
-      mbar_expect_tx(bar_a + stage * 8u, bytes);
-      tma_load(ring_a + stage * L::kChunkBytes, src_next, bytes, bar_a + stage * 8u, policy);
-    }
-  };
-  if (lane == 0) {
-    mbar_init(bar_a, 1u);
-    mbar_init(bar_a + 8u, 1u);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    issue(0u, 0u);
-    c_next += c_stride; src_next += src_step;
-    issue(1u, 0u);
-  }
-  c_next += 2u * c_stride - (lane == 0 ? c_stride : 0u);
-  src_next += 2u * src_step - (lane == 0 ? src_step : 0u);
-
-  for (uint32_t i = threadIdx.x; i < kTab; i += kWarps * 32) s.tab[i] = 0u;
-  for (uint32_t i = threadIdx.x; i < ALZ_BLOOM_WORDS; i += kWarps * 32) s.bloom[i] = bloom_g ? bloom_g[i] : 0xFFFFFFFFu;
-  for (uint32_t i = threadIdx.x; i <= kRows; i += kWarps * 32) { s.rowkey[i] = kEmptyKey; s.rowbase[i] = 0; }
-  for (uint32_t i = threadIdx.x; i < (kRows + 1u) * kRowWords; i += kWarps * 32) s.rows[i] = 0u;
-  if (threadIdx.x == 0) *s.n_rows = 0u;
-  __syncthreads();
-  const uint32_t rep_rows = preload_hot<kWarps * 32>(s, hot, L::kPreload);
-  __syncthreads();
-
-  const uint32_t zero = (uint32_t)(n >> 63);
-  uint32_t lost = 0, unresolved = 0, n_hit = 0, n_live = 0, n_cold = 0, n_late = 0;
-  uint64_t win_lo = 0, win_len = ~0ull;
-  if (kWin) { win_lo = win->lo; win_len = win->len; }
-  // cold events in flight: [0] requested last iteration, [1] the one before (due now)
-  uint32_t q_klo[2] = {0u, 0u}, q_khi[2] = {0u, 0u}, q_dlo[2] = {0u, 0u}, q_meta[2] = {0u, 0u};
-  bool q_on[2] = {false, false};
-  uint32_t it = 0;
-  for (uint32_t c = c_first; c < n_chunks; c += c_stride, ++it) {
-    const uint32_t stage = it & 1u;
-    mbar_wait(bar_a + stage * 8u, (it >> 1) & 1u);
-    uint32_t w[8];
-    {
-      const uint4* p = reinterpret_cast<const uint4*>(ring + stage * L::kChunkBytes + (size_t)lane * (kRecWords * 4u));
-      const uint4 a = p[0];
-      w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
-      w[4] = w[5] = w[6] = w[7] = 0u;
-      uint32_t seen = a.x;
-      if (kRecWords == 8) {
-        if (kWin) { const uint4 b = p[1]; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w; seen ^= b.x; }
-        else { const uint2 b = *reinterpret_cast<const uint2*>(p + 1); w[4] = b.x; w[5] = b.y; seen ^= b.x; }
-      }
-      // the stage goes back to the TMA only when these loads have returned (see the v8 kernel)
-      __syncwarp();
-      if (elect_one()) issue(stage, seen & zero);
-      c_next += c_stride; src_next += src_step;
-    }
-    const uint32_t n_here = (c == n_chunks - 1u) ? tail : kChunk9;
-    bool live = lane < n_here;
-    if constexpr (kWin && kRecWords == 8) {
-      const uint64_t rel = (((uint64_t)w[7] << 32) | w[6]) - win_lo;
-      const bool late = live && (rel >> 63) != 0ull;
-      const bool future = live && !late && rel >= win_len;
-      n_late += late ? 1u : 0u;
-      const uint32_t fm = __ballot_sync(0xFFFFFFFFu, future);
-      if (fm != 0u) {
-        uint32_t at = 0;
-        if (lane == (uint32_t)__ffs((int)fm) - 1u) at = atomicAdd(&ctr->defer_count, (uint32_t)__popc(fm));
-        at = __shfl_sync(0xFFFFFFFFu, at, __ffs((int)fm) - 1) + __popc(fm & lane_lt);
-        if (future) {
-          if (at < defer_cap) {
-            defer_buf[2u * at] = make_uint4(w[0], w[1], w[2], w[3]);
-            defer_buf[2u * at + 1u] = make_uint4(w[4], w[5], w[6], w[7]);
-          } else ++lost;
-          live = false;
-        }
-        n_live -= (uint32_t)__popc(fm);
-      }
-    }
-    n_live += n_here;
-
-    const uint32_t mw = (kRecWords == 8) ? w[3] : w[2];
-    uint32_t p = __byte_perm(mw, 0u, 0x4442u);
-    uint64_t dur;
-    if (kRecWords == 8) dur = ((uint64_t)w[5] << 32) | w[4];
-    else {
-      dur = w[3];
-      if (p & ALZ_REC16_DUR_OVERFLOW) dur = live ? __ldg(&dur_ovf[w[3]]) : 0ull;
-    }
-    const bool hk = (p & ALZ_PROTO_F_HOSTKEY) != 0u;
-    p &= 0x3Fu;
-    const uint32_t cls = shr_clamp(kProtoLut, 3u * p);
-    const bool act = live && (cls & 1u) && !((cls & 2u) && (mw & ((uint32_t)ALZ_MF_PAYLOAD_REJECT << 24)));
-    const bool rv = (cls & 4u) && (mw & ((uint32_t)ALZ_MF_METHOD_MASK << 24)) == (2u << 24);
-    const bool err = p == ALZ_PROTO_HTTP && ((mw & 0xFFFFu) - 500u) < 100u;
-    const uint64_t key = ((uint64_t)w[1] << 32) | w[0];
-    const uint32_t bucket = latency_bucket_rz(dur);
-    const uint32_t kind = hk ? kPairHost : rv ? kPairRev : kPairFwd;
-    const uint32_t dhi = (uint32_t)(dur >> 32), dlo = (uint32_t)dur;
-    const uint32_t meta = bucket | (kind << 6) | (err ? 0x100u : 0u) | (dhi << 9);
-
-    const uint32_t h = table_hash(key);
-    const uint32_t fp = tab_fp(h);
-    const uint2 t2 = *reinterpret_cast<const uint2*>(&s.tab[tab_idx1(h)]);
-    const uint32_t x1 = t2.x ^ fp, x2 = t2.y ^ fp;
-    const uint32_t x = x1 < 0x10000u ? x1 : x2;
-    uint32_t r = min(x & kRowMask, kRows);
-    r += r < rep_rows ? (lane & (uint32_t)(kHotRep - 1)) : 0u;   // tier S: this lane's row of the group
-    const uint32_t d = bucket - ((x >> 12) & 15u) * 4u;
-    const bool hit = act && kind == kPairFwd && x < 0x10000u && (x & kRowMask) < kRows && d < 16u && s.rowkey[r] == key;
-    uint32_t* row = s.rows + r * kRowWords;
-    if (hit) {
-      const uint32_t sh = (d & 1u) * 16u;
-      const uint32_t old = atomicAdd(&row[d >> 1], 1u << sh);
-      if (((old >> sh) & 0xFFFFu) == kCellSpill) {
-        const uint32_t grow = find_or_insert_pair(pairs, key, kPairFwd, ep, ep_mask);
-        if (grow < kDropRow) red_add_u32(pair_cell(pairs, grow, bucket), 0x8000u);
-        else if (grow == kDropRow) unresolved += 0x8000u; else lost += 0x8000u;
-        atomicSub(&row[d >> 1], 0x8000u << sh);
-      }
-      uint32_t* lat = row + 9u + 2u * (lane & 1u);
-      const uint32_t oldl = atomicAdd(&lat[0], dlo);
-      const bool carry = oldl > ~dlo;
-      if (carry || dhi != 0u) atomicAdd(&lat[1], dhi + (carry ? 1u : 0u));
-      if (err) atomicAdd(&row[8], 1u);
-      ++n_hit;
-    }
-    bool cold = act && !hit;
-    n_cold += cold ? 1u : 0u;
-    if (cold && dhi >= (1u << 23)) {   // does not fit the packed form: on the spot, rare beyond words
-      slow_one<kRows>(key, dur, bucket, kind, err, pairs, s, ep, ep_mask, &lost, &unresolved);
-      cold = false;
-    }
-    __syncwarp();
-
-    // finish the cold events of two iterations ago (their probes: all groups but the latest have landed) ...
-    uint4* slot = probe + stage * 32u;
-    cp_async_wait_1();
-    cold_finish<kRows>(q_on[1], q_klo[1], q_khi[1], q_dlo[1], q_meta[1], slot, slow, pairs, s, ep, ep_mask, lane_lt,
-                       &lost, &unresolved);
-    // ... and request the probes of this iteration's into the slot that just became free
-    if (cold) {
-      if (!maybe_pod(s.bloom, (uint32_t)key)) slot[lane] = make_uint4(0u, 0u, kDropRow, 1u);
-      else cp_async16(probe_a + (stage * 32u + lane) * 16u, &pairs.dict_of(kind)[pair_hash(key) & pairs.mask_of(kind)],
-                      keep_policy());
-    }
-    cp_async_commit();
-    q_klo[1] = q_klo[0]; q_khi[1] = q_khi[0]; q_dlo[1] = q_dlo[0]; q_meta[1] = q_meta[0]; q_on[1] = q_on[0];
-    q_klo[0] = (uint32_t)key; q_khi[0] = (uint32_t)(key >> 32); q_dlo[0] = dlo; q_meta[0] = meta; q_on[0] = cold;
-  }
-  // the last two iterations' cold events: [1] sits in slot (it & 1), [0] in the other one
-  cp_async_wait_all();
-  cold_finish<kRows>(q_on[1], q_klo[1], q_khi[1], q_dlo[1], q_meta[1], probe + (it & 1u) * 32u, slow, pairs, s, ep, ep_mask,
-                     lane_lt, &lost, &unresolved);
-  cold_finish<kRows>(q_on[0], q_klo[0], q_khi[0], q_dlo[0], q_meta[0], probe + ((it + 1u) & 1u) * 32u, slow, pairs, s, ep,
-                     ep_mask, lane_lt, &lost, &unresolved);
-  while (slow.count) slow_batch<kRows>(slow, min(slow.count, 32u), pairs, s, ep, ep_mask, &lost, &unresolved);
-  __syncthreads();
-  drain_rows_and_count<kWarps, kRows, kWin>(s, pairs, ctr, ep, ep_mask, lost, unresolved, n_hit, n_live, n_cold, n_late);
-}
-
 // open the first window on the first record ever submitted: epoch = (write_time + off) / len, docs/SPEC.md §8
 // (off = FirstUserspaceTime - FirstKernelTime, aggregator/data.go:1740-1743)
 __global__ void win_init_kernel(const uint32_t* __restrict__ recs, uint64_t n, WinClock* win, uint64_t off) {
@@ -1052,26 +796,15 @@ __global__ void __launch_bounds__(256) hot_emit_kernel(AccTable pairs, HotState*
   }
 }
 
-template <int kWarps, int kRecWords, bool kWin = false, int kStages = 2>
+template <int kWarps, int kRecWords, bool kWin = false>
 void launch_variant(const void* recs, uint64_t n, const AccTable& pairs, Counters* ctr, const HotState* hot,
                     const EpEntry* ep, uint32_t ep_mask, const uint32_t* bloom, const uint64_t* dur_ovf, int sms,
                     cudaStream_t s, const WinClock* win = nullptr, void* defer_buf = nullptr, uint32_t defer_cap = 0) {
-  using L = Layout<kWarps, kRecWords, kStages>;
+  using L = Layout<kWarps, kRecWords>;
   // per device (a process may drive several GPUs), so not cached in a static
-  cudaFuncSetAttribute(ingest_pairs_v8_kernel<kWarps, kRecWords, kWin, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaFuncSetAttribute(ingest_pairs_v8_kernel<kWarps, kRecWords, kWin>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)L::kBytes);
-  ingest_pairs_v8_kernel<kWarps, kRecWords, kWin, kStages><<<(unsigned)sms, kWarps * 32, L::kBytes, s>>>(
-      (const uint32_t*)recs, n, pairs, ctr, hot, ep, ep_mask, bloom, dur_ovf, win, (uint4*)defer_buf, defer_cap);
-}
-
-template <int kWarps, int kRecWords, bool kWin = false>
-void launch_variant9(const void* recs, uint64_t n, const AccTable& pairs, Counters* ctr, const HotState* hot,
-                     const EpEntry* ep, uint32_t ep_mask, const uint32_t* bloom, const uint64_t* dur_ovf, int sms,
-                     cudaStream_t s, const WinClock* win = nullptr, void* defer_buf = nullptr, uint32_t defer_cap = 0) {
-  using L = Layout9<kWarps, kRecWords>;
-  cudaFuncSetAttribute(ingest_pairs_v9_kernel<kWarps, kRecWords, kWin>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (int)L::kBytes);
-  ingest_pairs_v9_kernel<kWarps, kRecWords, kWin><<<(unsigned)sms, kWarps * 32, L::kBytes, s>>>(
+  ingest_pairs_v8_kernel<kWarps, kRecWords, kWin><<<(unsigned)sms, kWarps * 32, L::kBytes, s>>>(
       (const uint32_t*)recs, n, pairs, ctr, hot, ep, ep_mask, bloom, dur_ovf, win, (uint4*)defer_buf, defer_cap);
 }
 
@@ -1085,26 +818,7 @@ void launch_ingest_pairs(const alz_l7_rec* recs, uint64_t n, const AccTable& pai
                          const HotState* hot, const EpEntry* ep, uint32_t ep_mask, const uint32_t* bloom, int sms,
                          cudaStream_t s) {
   if (n == 0) return;
-  // ALZ_INGEST_SHAPE: CTA shape for profiling runs (default = the measured best)
-  static const int shape = [] { const char* v = getenv("ALZ_INGEST_SHAPE"); return v ? atoi(v) : 0; }();
-  static const int keep = [] {
-    const char* v = getenv("ALZ_INGEST_KEEP");
-    const int k = v ? atoi(v) : 1;
-    if (!k) cudaMemcpyToSymbol(c_keep_hint, &k, sizeof(k));
-    return k;
-  }();
-  (void)keep;
-  switch (shape) {
-    case 1: launch_variant<12, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
-    case 2: launch_variant<20, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
-    case 3: launch_variant<24, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
-    case 4: launch_variant<16, 8, false, 1>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
-    case 5: launch_variant<20, 8, false, 1>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
-    case 6: launch_variant<24, 8, false, 1>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
-    case 9: launch_variant9<32, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
-    case 10: launch_variant9<24, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
-    default: launch_variant<kDefaultWarps, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s); break;
-  }
+  launch_variant<kDefaultWarps, 8>(recs, n, pairs, ctr, hot, ep, ep_mask, bloom, nullptr, sms, s);
 }
 
 void launch_ingest_pairs_rec16(const alz_l7_rec16* recs, uint64_t n, const uint64_t* dur_ovf, const AccTable& pairs,
