@@ -1,5 +1,6 @@
 #!/bin/bash
-# round 2: 8 GPUs of one box: merge parity at 2/4/8 ranks, bench configs 2 (weak), 4 and 5 (strong)
+# 8 GPUs of one box: merge parity at 2/4/8 ranks, bench configs 2 (weak), 4 and 5 (strong).
+# Budget note: an 8-GPU call is charged 8x its wall time; give gpurun a --timeout that the remaining budget covers.
 set -u
 N=8
 mkdir -p gpurun_out
