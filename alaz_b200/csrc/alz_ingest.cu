@@ -32,7 +32,6 @@
 //         commit) is dropped right there, as setFromToV2 would (aggregator/data.go:829-832).
 //   slow  a cold event whose home slot does not hold its pair (new pair, collision) is queued once
 //         more and 32 of them at a time walk find_or_insert_pair.
-#include <cstdlib>
 
 #include "alz_kernels.cuh"
 
