@@ -95,3 +95,133 @@ class Aggregator:
         g["lat_sum"] += row["Latency"]
         g["hist"][bucket(row["Latency"])] += 1
         self.stats["rows_emitted"] += 1
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SocketLine (aggregator/sock_num_line.go), restated from the Go source independently of oracle/alz_oracle.c:
+# Python lists and bisect instead of the C arrays and hand-written binary searches.
+# ---------------------------------------------------------------------------------------------------------------
+import bisect  # noqa: E402
+
+ONE_MINUTE_NS = 60 * 10**9
+FIVE_MINUTES_NS = 5 * ONE_MINUTE_NS
+
+
+class SocketLine:
+    """Values: list of [timestamp, sockinfo-or-None, last_match]; sockinfo = (saddr, daddr, sport, dport)."""
+
+    def __init__(self):
+        self.values = []
+
+    def add_value(self, ts, si):  # :62-80, insertIntoSortedSlice :311-322
+        if self.values:
+            last = self.values[-1]
+            if last[1] is not None and si is not None and last[1] == si:
+                return
+        # sort.Search for the first index with Timestamp >= ts
+        idx = bisect.bisect_left([v[0] for v in self.values], ts)
+        self.values.insert(idx, [ts, si, 0])
+
+    def get_value(self, ts, now):  # :82-158
+        v = self.values
+        if not v:
+            return None
+        index = bisect.bisect_left([x[0] for x in v], ts)      # first i with !(Timestamp < ts)
+        if index == len(v):
+            v[index - 1][2] = now                                # :96
+            if v[-1][1] is None:
+                if index - 2 >= 0 and v[index - 2][1] is not None and (ts - v[index - 2][0]) < ONE_MINUTE_NS:
+                    return v[index - 2][1]
+                return None
+            return v[-1][1]
+        if index == 0:
+            return v[0][1]                                       # an open socket or None (:112-118)
+        si = v[index - 1][1]
+        if si is None:
+            prev = v[index - 2] if index - 2 >= 0 else None
+            after = v[index]
+            if prev is not None and prev[1] is not None and after[1] is not None:
+                if prev[1][1] == after[1][1] and prev[1][3] == after[1][3]:     # Daddr, Dport
+                    return prev[1] if ts - prev[0] < after[0] - ts else after[1]
+            return None
+        v[index - 1][2] = now                                    # :156
+        return si
+
+    def delete_unused(self):  # :160-209, as written
+        v = self.values
+        if len(v) <= 1:
+            return
+        result = []
+        i = 0
+        while i < len(v) - 1:
+            if v[i][1] is not None and v[i + 1][1] is not None:
+                result.append(v[i + 1])
+                i += 2
+            else:
+                result.append(v[i])
+                i += 1
+        v = result
+        last_matched = 0
+        for x in reversed(v):
+            if x[2] != 0 and x[2] > last_matched:
+                last_matched = x[2]
+        i = len(v) - 1
+        while i >= 1:
+            if v[i][1] is None and v[i - 1][1] is not None and v[i - 1][2] + FIVE_MINUTES_NS < last_matched:
+                v = v[:i - 1] + v[i + 1:]
+                i -= 1
+            i -= 1
+        self.values = v
+
+
+class SocketMaps:
+    """processTcpConnect (aggregator/data.go:404-506) over SocketMaps[pid].M[fd], plus findRelatedSocket
+    (:1407-1429) and sendOpenConnection (:1628-1679)."""
+
+    def __init__(self):
+        self.lines = {}
+        self.localhost_dropped = 0
+
+    def process_tcp(self, typ, pid, fd, ts, saddr, daddr, sport, dport):
+        if typ not in (1, 5):
+            return
+        if ip_string(saddr) == "127.0.0.1" or ip_string(daddr) == "127.0.0.1":
+            self.localhost_dropped += 1
+            return
+        if typ == 1:
+            self.lines.setdefault((pid, fd), SocketLine()).add_value(ts, (saddr, daddr, sport, dport))
+        else:
+            ln = self.lines.get((pid, fd))
+            if ln is not None:
+                ln.add_value(ts, None)
+
+    def lookup(self, pid, fd, ts, now):
+        ln = self.lines.get((pid, fd))
+        return None if ln is None else ln.get_value(ts, now)
+
+    def gc(self):
+        for ln in self.lines.values():
+            ln.delete_unused()
+
+    def alive(self, pod_ip_to_uid, svc_ip_to_uid):
+        """Rows (from_ip, from_uid, from_port, to_ip, to_type, to_uid, to_port) of sendOpenConnection."""
+        out = []
+        for ln in self.lines.values():
+            if not ln.values:
+                continue
+            t = ln.values[-1]
+            if t[1] is None:
+                continue
+            saddr, daddr, sport, dport = t[1]
+            from_uid = pod_ip_to_uid.get(ip_string(saddr))
+            if from_uid is None:
+                continue
+            to_ip = ip_string(daddr)
+            if to_ip in svc_ip_to_uid:
+                to_type, to_uid = "service", svc_ip_to_uid[to_ip]
+            elif to_ip in pod_ip_to_uid:
+                to_type, to_uid = "pod", pod_ip_to_uid[to_ip]
+            else:
+                to_type, to_uid = "outbound", to_ip
+            out.append((saddr, from_uid, sport, daddr, to_type, to_uid, dport))
+        return out

@@ -41,3 +41,60 @@ def test_c_oracle_equals_python_restatement(pods, svcs, events):
     stc = o.stats()
     for key, v in a.stats.items():
         assert stc[key] == v
+
+
+# ---- SocketLine: C restatement vs the independent Python one, arbitrary interleavings -------------------------
+_ts_s = st.integers(0, 40) .map(lambda k: k * 20 * 10**9)          # 20 s steps: the one-minute rule is exercised
+_op_s = st.one_of(
+    st.tuples(st.just("tcp"), st.sampled_from([1, 5, 1, 5, 2]), st.integers(1, 3), st.integers(3, 5), _ts_s,
+              st.sampled_from([abi.ip("10.0.0.1"), abi.ip("10.0.0.2"), abi.ip("127.0.0.1")]),
+              st.sampled_from([abi.ip("10.0.0.5"), abi.ip("10.0.0.6"), abi.ip("8.8.8.8")]),
+              st.sampled_from([1000, 1001]), st.sampled_from([80, 443])),
+    st.tuples(st.just("get"), st.integers(1, 3), st.integers(3, 5), st.integers(0, 45).map(lambda k: k * 17 * 10**9 + 3),
+              st.integers(1, 20).map(lambda m: m * 60 * 10**9)),
+    st.tuples(st.just("gc")),
+)
+
+
+@settings(max_examples=300, deadline=None)
+@given(ops=st.lists(_op_s, max_size=60))
+def test_sockline_c_equals_python_restatement(ops):
+    c = ol.SockMaps()
+    p = ref_py.SocketMaps()
+    for op in ops:
+        if op[0] == "tcp":
+            _, typ, pid, fd, ts, sa, da, sp, dp = op
+            r = np.zeros(1, dtype=abi.TCP_REC)
+            r[0] = (fd, ts, pid, sa, da, sp, dp, typ, 0)
+            c.process(r)
+            p.process_tcp(typ, pid, fd, ts, sa, da, sp, dp)
+        elif op[0] == "get":
+            _, pid, fd, ts, now = op
+            q = np.zeros(1, dtype=abi.SOCK_QUERY)
+            q[0] = (fd, ts, pid, 0)
+            got = c.lookup(q, now_ns=now)[0]
+            exp = p.lookup(pid, fd, ts, now)
+            if exp is None:
+                assert got["found"] == 0, (op, got)
+            else:
+                assert got["found"] == 1 and (int(got["saddr"]), int(got["daddr"]), int(got["sport"]), int(got["dport"])) == exp, (op, got, exp)
+        else:
+            c.gc()
+            p.gc()
+        assert c.records() == sum(len(l.values) for l in p.lines.values())
+    assert c.localhost_dropped == p.localhost_dropped
+    # sendOpenConnection over what is left
+    o = ol.Oracle()
+    pods = {abi.ip("10.0.0.1"): 7, abi.ip("10.0.0.5"): 9}
+    svcs = {abi.ip("10.0.0.6"): 3}
+    for ip, i in pods.items():
+        o.upsert(abi.TABLE_POD, ip, i)
+    for ip, i in svcs.items():
+        o.upsert(abi.TABLE_SVC, ip, i)
+    got = c.alive(o, cap=256)
+    exp = p.alive({ref_py.ip_string(ip): i for ip, i in pods.items()}, {ref_py.ip_string(ip): i for ip, i in svcs.items()})
+    tname = {abi.NODE_POD: "pod", abi.NODE_SVC: "service", abi.NODE_OUTBOUND: "outbound"}
+    got_rows = sorted((int(g["from_ip"]), int(g["from_id"]), int(g["from_port"]), int(g["to_ip"]), tname[int(g["to_type"])],
+                       int(g["to_id"]) if int(g["to_type"]) != abi.NODE_OUTBOUND else ref_py.ip_string(int(g["to_id"])),
+                       int(g["to_port"])) for g in got)
+    assert got_rows == sorted(exp)
