@@ -36,6 +36,22 @@ def bucket(d):  # docs/SPEC.md §4
     return 2 * (o - 8) + ((d >> (o - 1)) & 1)
 
 
+def parse_http_payload_host(request):  # parseHttpPayload's hostHeader, aggregator/data.go:508-531
+    if isinstance(request, bytes):
+        request = request.decode("latin-1")
+    lines = request.split("\n")
+    host = ""
+    for line in lines[1:]:
+        if line.startswith("Host:"):
+            parts = line.split(" ")
+            if len(parts) >= 2:
+                host = parts[1]
+                if host.endswith("\r"):
+                    host = host[:-1]
+                break
+    return host
+
+
 class Aggregator:
     def __init__(self):
         self.pod_ip_to_uid = {}   # cluster.go:15
@@ -43,7 +59,7 @@ class Aggregator:
         self.groups = {}
         self.stats = dict(events_in=0, rows_emitted=0, not_request=0, src_unresolved=0)
 
-    def set_from_to_v2(self, row):  # aggregator/data.go:827-870
+    def set_from_to_v2(self, row, host_header=""):  # aggregator/data.go:827-870
         uid = self.pod_ip_to_uid.get(row["FromIP"])
         if uid is None:
             return False
@@ -56,10 +72,13 @@ class Aggregator:
         if p is not None:
             row["ToUID"], row["ToType"] = p, "pod"
             return True
+        if host_header != "":
+            row["ToUID"], row["ToType"] = host_header, "outbound"  # :851-854
+            return True
         row["ToUID"], row["ToType"] = row["ToIP"], "outbound"  # :862, DNS treated as failing
         return True
 
-    def process_l7(self, rec):  # aggregator/data.go:1364-1383
+    def process_l7(self, rec, payload=None):  # aggregator/data.go:1364-1383; payload: the HTTP request bytes, if any
         self.stats["events_in"] += 1
         proto = _PROTO.get(int(rec["protocol"]), "Unknown")
         mf = int(rec["method_flags"])
@@ -74,7 +93,8 @@ class Aggregator:
         row = dict(Latency=int(rec["duration_ns"]), FromIP=ip_string(int(rec["saddr"])),
                    ToIP=ip_string(int(rec["daddr"])), Protocol=proto, Tls=tls,
                    StatusCode=int(rec["status"]), Method=method)
-        if not self.set_from_to_v2(row):
+        host = parse_http_payload_host(payload) if (proto == "HTTP" and payload is not None) else ""   # :1213
+        if not self.set_from_to_v2(row, host):
             self.stats["src_unresolved"] += 1
             return
         if (proto == "AMQP" and method == "DELIVER") or (proto == "REDIS" and method == "PUSHED_EVENT"):

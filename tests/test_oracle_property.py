@@ -98,3 +98,64 @@ def test_sockline_c_equals_python_restatement(ops):
                        int(g["to_id"]) if int(g["to_type"]) != abi.NODE_OUTBOUND else ref_py.ip_string(int(g["to_id"])),
                        int(g["to_port"])) for g in got)
     assert got_rows == sorted(exp)
+
+
+# ---- Host header: the C parser vs the Python one on arbitrary payloads; host-keyed rows through both aggregators --
+_frag = st.sampled_from(["GET / HTTP/1.1", "Host:", "Host: ", "Host:  ", "host: x", "Host: a.com", "Host: b.org:80", " ", "\r",
+                         "X-Host: no", "Host:nospace", "8.8.8.8", "Host: 8.8.8.8", "Host: a.com extra", "", "Accept: */*"])
+_payload_s = st.lists(_frag, max_size=8).flatmap(
+    lambda fr: st.lists(st.sampled_from(["\n", "\r\n", " ", ""]), min_size=len(fr), max_size=len(fr)).map(
+        lambda seps: "".join(f + s_ for f, s_ in zip(fr, seps))))
+
+
+@settings(max_examples=400, deadline=None)
+@given(payload=_payload_s)
+def test_host_header_parsers_agree(payload):
+    assert ol.parse_http_host(payload.encode("latin-1")) == ref_py.parse_http_payload_host(payload)
+
+
+@settings(max_examples=100, deadline=None)
+@given(pods=table_s, svcs=table_s,
+       events=st.lists(st.tuples(ip_s, ip_s, st.sampled_from([1, 1, 1, 2, 5, 3]), st.integers(0, 3), st.integers(0, 2)), max_size=40))
+def test_host_keyed_rows_c_equals_python(pods, svcs, events):
+    """orc_process_l7_hosts against the Python aggregator fed the payloads themselves: only HTTP events carry a payload
+    (processHttpEvent is the only handler that parses one), the header keys outbound destinations only."""
+    names = ["api.example.com", "b.org:80", "8.8.8.8"]
+    o = ol.Oracle()
+    a = ref_py.Aggregator()
+    for ip, i in pods.items():
+        o.upsert(abi.TABLE_POD, ip, i)
+        a.pod_ip_to_uid[ref_py.ip_string(ip)] = "pod-%d" % i
+    for ip, i in svcs.items():
+        o.upsert(abi.TABLE_SVC, ip, i)
+        a.svc_ip_to_uid[ref_py.ip_string(ip)] = "svc-%d" % i
+    recs = np.zeros(len(events), dtype=abi.L7_REC)
+    host_idx = np.zeros(len(events), dtype=np.uint32)
+    for k, (s_, d, proto, meth, hn) in enumerate(events):
+        recs[k] = (s_, d, 1000 + k, 80, 200, proto, meth, 1000 + k, k)
+        has = proto == 1 and hn > 0
+        host_idx[k] = hn if has else 0
+        payload = ("GET / HTTP/1.1\r\nHost: %s\r\n\r\n" % names[hn - 1]) if has else ("GET / HTTP/1.1\r\n\r\n" if proto == 1 else None)
+        a.process_l7(recs[k], payload)
+    o.process_hosts(recs, host_idx, names)
+    got = o.edges()
+    # the C side reports a host-keyed node as (ALZ_NODE_OUTBOUND_HOST, index into names), or as a raw address when the
+    # text is a dotted quad; translate the Python groups the same way
+    exp = {}
+    for (ft, fu, tt, tu), g in a.groups.items():
+        exp[(ft, fu, tt, tu)] = g["count"]
+    got_map = {}
+    tname = {abi.NODE_POD: "pod", abi.NODE_SVC: "service", abi.NODE_OUTBOUND: "outbound", abi.NODE_OUTBOUND_HOST: "outbound"}
+
+    def uid(t, v):
+        if t == abi.NODE_POD:
+            return "pod-%d" % v
+        if t == abi.NODE_SVC:
+            return "svc-%d" % v
+        if t == abi.NODE_OUTBOUND_HOST:
+            return names[v]
+        return ref_py.ip_string(v)
+    for e in got:
+        k = (tname[int(e["from_type"])], uid(int(e["from_type"]), int(e["from"])), tname[int(e["to_type"])], uid(int(e["to_type"]), int(e["to"])))
+        got_map[k] = got_map.get(k, 0) + int(e["count"])
+    assert got_map == exp
