@@ -106,3 +106,44 @@ def test_cpp_host_adapter_conversions_and_loud_failure():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "host unit ok" in r.stdout
+
+
+def test_pack_l7_is_lossless_for_what_the_reduce_reads():
+    """alz_pack_l7 is host code (no GPU needed): 32-B records -> 16-B records + overflow durations (docs/SPEC.md §10)."""
+    import ctypes as C
+    rng = np.random.default_rng(3)
+    n = 5000
+    ev = np.zeros(n, dtype=abi.L7_REC)
+    ev["saddr"] = rng.integers(0, 2**32, n)
+    ev["daddr"] = rng.integers(0, 2**32, n)
+    ev["sport"] = rng.integers(0, 65536, n)
+    ev["dport"] = rng.integers(0, 65536, n)
+    ev["status"] = rng.integers(0, 65536, n)
+    ev["protocol"] = rng.integers(0, 256, n)
+    ev["method_flags"] = rng.integers(0, 256, n)
+    dur = rng.integers(0, 2**32, n).astype(np.uint64)
+    big = rng.random(n) < 0.1
+    dur[big] = rng.integers(2**32, 2**63, int(big.sum())).astype(np.uint64)      # >= 4.29 s: side array
+    dur[0], dur[1] = 2**32 - 1, 2**32                                            # the boundary
+    big[0], big[1] = False, True
+    ev["duration_ns"] = dur
+    ev["write_time_ns"] = rng.integers(0, 2**63, n)
+    r16, ovf = capi.pack_l7(ev)
+    assert len(ovf) == int(big.sum())
+    assert np.array_equal(r16["saddr"], ev["saddr"]) and np.array_equal(r16["daddr"], ev["daddr"])
+    assert np.array_equal(r16["status"], ev["status"]) and np.array_equal(r16["method_flags"], ev["method_flags"])
+    flag = (r16["protocol"] & abi.REC16_DUR_OVERFLOW) != 0
+    assert np.array_equal(flag, big)
+    back = r16["duration_ns"].astype(np.uint64)
+    back[flag] = ovf[r16["duration_ns"][flag]]                                   # the index into the side array
+    assert np.array_equal(back, dur)
+    # protocol: bits 0..5 the value, bit 6 ALZ_PROTO_F_HOSTKEY travels; a value with bit 7 set is no protocol at all
+    p16 = r16["protocol"] & 0x7F
+    hi = (ev["protocol"] & 0x80) != 0
+    assert np.array_equal(p16[~hi], ev["protocol"][~hi] & 0x7F)
+    assert np.all((p16[hi] & 0x3F) == 0x3F)
+    # a side array that is too small is an error, not a truncation
+    L = capi.load()
+    out = np.zeros(n, dtype=abi.L7_REC16)
+    small = np.zeros(1, dtype=np.uint64)
+    assert L.alz_pack_l7(ev.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p), small.ctypes.data_as(C.c_void_p), 1) == -1
