@@ -98,7 +98,11 @@ typedef struct fworker {
   const orc_fast* f; const alz_l7_rec* recs; size_t n;
   fmap local; alz_stats st;
   struct fworker* all; int nworkers, id; fmap* shard_out;
+  uint32_t* order;   /* slots of the live entries of `local`, grouped by the merge thread that owns the key */
+  size_t* group;     /* [nworkers + 1] offsets into order */
 } fworker;
+
+static int owner_of(uint64_t key, int nworkers) { return (int)((h64(key) >> 40) % (uint64_t)nworkers); }
 
 static void pin_to(int cpu) {
   cpu_set_t s; CPU_ZERO(&s); CPU_SET(cpu % CPU_SETSIZE, &s);
@@ -133,19 +137,30 @@ static void* fwork_main(void* p) {
   fworker* w = (fworker*)p;
   pin_to(w->id);
   process_range(w->f, w->recs, w->n, &w->local, &w->st);
+  /* hand-over for the merge: a counting sort of the live slots by owner, so that every merge thread reads only
+   * the entries it owns (scanning all maps in every merge thread is quadratic in the thread count) */
+  const int T = w->nworkers;
+  w->group = (size_t*)calloc((size_t)T + 1, sizeof(size_t));
+  w->order = (uint32_t*)malloc((w->local.len ? w->local.len : 1) * sizeof(uint32_t));
+  for (size_t i = 0; i < w->local.cap; i++)
+    if (w->local.e[i].key != ~0ull) w->group[owner_of(w->local.e[i].key, T) + 1]++;
+  for (int t = 0; t < T; t++) w->group[t + 1] += w->group[t];
+  size_t* at = (size_t*)malloc((size_t)T * sizeof(size_t));
+  memcpy(at, w->group, (size_t)T * sizeof(size_t));
+  for (size_t i = 0; i < w->local.cap; i++)
+    if (w->local.e[i].key != ~0ull) w->order[at[owner_of(w->local.e[i].key, T)]++] = (uint32_t)i;
+  free(at);
   return NULL;
 }
-/* phase 2: thread id merges the keys with hash % T == id of every worker */
+/* phase 2: thread id merges the keys it owns out of every worker's map */
 static void* fmerge_main(void* p) {
   fworker* w = (fworker*)p;
   pin_to(w->id);
   fmap* out = w->shard_out;
   for (int t = 0; t < w->nworkers; t++) {
-    const fmap* src = &w->all[t].local;
-    for (size_t i = 0; i < src->cap; i++) {
-      const facc* a = &src->e[i];
-      if (a->key == ~0ull) continue;
-      if ((int)((h64(a->key) >> 40) % (uint64_t)w->nworkers) != w->id) continue;
+    const fworker* src = &w->all[t];
+    for (size_t k = src->group[w->id]; k < src->group[w->id + 1]; k++) {
+      const facc* a = &src->local.e[src->order[k]];
       facc* d = fmap_get(out, a->key);
       d->count += a->count; d->err5xx += a->err5xx; d->lat_sum += a->lat_sum;
       for (int b = 0; b < ALZ_NB; b++) d->hist[b] += a->hist[b];
@@ -179,7 +194,7 @@ void orc_fast_process(orc_fast* f, const alz_l7_rec* recs, size_t n, int nthread
       d->count += a->count; d->err5xx += a->err5xx; d->lat_sum += a->lat_sum;
       for (int b = 0; b < ALZ_NB; b++) d->hist[b] += a->hist[b];
     }
-    free(shards[t].e); free(w[t].local.e);
+    free(shards[t].e); free(w[t].local.e); free(w[t].order); free(w[t].group);
     f->st.events_in += w[t].st.events_in; f->st.rows_emitted += w[t].st.rows_emitted;
     f->st.not_request += w[t].st.not_request; f->st.src_unresolved += w[t].st.src_unresolved;
   }
