@@ -12,6 +12,7 @@
 #include "alz_oracle.h"
 
 #include <pthread.h>
+#include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -294,8 +295,14 @@ typedef struct worker {
   struct worker* all;
   int nworkers, id;
 } worker;
+/* one thread per logical CPU, pinned (best effort): unpinned runs of this arm varied 2.8x from box to box */
+static void pin_worker(int id) {
+  cpu_set_t set; CPU_ZERO(&set); CPU_SET(id % CPU_SETSIZE, &set);
+  pthread_setaffinity_np(pthread_self(), sizeof set, &set);
+}
 static void* worker_main(void* p) {
   worker* w = (worker*)p;
+  pin_worker(w->id);
   for (size_t i = 0; i < w->n; i++) process_l7(w->o, &w->recs[i], w->groups, &w->st, NULL);
   return NULL;
 }
@@ -303,6 +310,7 @@ static void merge_acc(acc* dst, const acc* src);
 /* phase 2: thread `id` folds shards id, id+T, ... of every worker into the shared result */
 static void* merge_main(void* p) {
   worker* w = (worker*)p;
+  pin_worker(w->id);
   for (int sh = w->id; sh < NSHARD; sh += w->nworkers) {
     smap* dst = &w->o->groups[sh];
     for (int t = 0; t < w->nworkers; t++) {
