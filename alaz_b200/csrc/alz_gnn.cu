@@ -215,7 +215,6 @@ constexpr uint32_t TM = 128, TK = 128, TN = 64;
 constexpr uint32_t A_BYTES = TM * TK * 4, B_BYTES = TN * TK * 4;
 constexpr uint32_t A_LBO = (TM / 8) * 128, A_SBO = 128;   // K-adjacent cores TM/8 cores apart; row groups adjacent
 constexpr uint32_t B_LBO = (TN / 8) * 128, B_SBO = 128;
-constexpr uint32_t SMEM_BYTES_OPERANDS = 2 * A_BYTES + 2 * B_BYTES;
 
 // byte offset of element (row r, k) in a K-major no-swizzle operand with R rows:
 // core matrix = 8 rows x 16 B; cores of one K-slice are contiguous over the row groups

@@ -560,6 +560,7 @@ ingest_pairs_v8_kernel(const uint32_t* __restrict__ recs, uint64_t n, AccTable p
   PROF_DECL;
   unsigned long long t_wait = 0, t_slow = 0;
   const long long p_begin = PROF_NOW();
+  (void)p_begin;
   uint32_t it = 0;
   for (uint32_t c = c_first; c < n_chunks; c += c_stride, ++it) {
     const uint32_t stage = it & 1u;
